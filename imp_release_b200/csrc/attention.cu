@@ -1,0 +1,462 @@
+// Flash-style multi-head attention for sm_100a (see attention.cuh).  One CTA = 128 query rows of one head of one
+// image; keys stream through in tiles of 128.
+//   warp 0    : TMA producer (Q once; K/V tiles into a 4-deep ring, 128B swizzle)
+//   warp 1    : UMMA issuer  S = Q K^T (SS, fp16, fp32 accum in TMEM, two S buffers) and O += P V (P from TMEM,
+//               V consumed token-major as an MN-major B operand); also owns the TMEM allocation
+//   warps 2-5 : softmax.  TMEM lane == query row, so a thread owns a whole score row: row max / sum need no
+//               shuffles.  exp2 with the 1/8*log2(e) scale folded into one FFMA, lazy rescaling of O (only when the
+//               running max grows by > 2^8), P written back to TMEM as packed fp16 over the S columns.
+// S(j+1) is issued before P(j) is awaited, so the tensor core computes the next score tile while the softmax warps
+// work on the current one.
+#include "attention.cuh"
+
+#include <math.h>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace imp {
+
+static constexpr int AT_BM = 128;
+static constexpr int AT_BN = 128;
+static constexpr int AT_D = 64;
+static constexpr int AT_HEADS = 4;
+static constexpr int AT_C = AT_D * AT_HEADS;
+static constexpr int AT_STAGES = 4;
+static constexpr int AT_THREADS = 192;
+static constexpr int AT_TILE_BYTES = AT_BN * AT_D * 2;  // 16 KB (Q, K and V tiles alike)
+static constexpr uint32_t AT_TMEM_COLS = 512;
+static constexpr uint32_t AT_COL_S = 0;    // two score buffers of 128 fp32 columns (P aliases the first 64)
+static constexpr uint32_t AT_COL_O = 256;  // 64 fp32 columns
+static constexpr float AT_SCALE_LOG2 = 0.125f * 1.4426950408889634f;
+static constexpr float AT_RESCALE_TAU = 8.0f;
+
+struct AttnKernelParams {
+  int n_img, src_offset, Nq_max, Nk_max, shared;
+  const int *nq, *nk;
+  float* lse;
+  __half *out_hi, *out_lo;
+  long long out_img_stride;
+};
+
+__global__ void __launch_bounds__(AT_THREADS, 1)
+attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem;
+  uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K at +0, V at +16 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + AT_STAGES * 2 * AT_TILE_BYTES);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;
+  uint64_t* kv_empty = kv_full + AT_STAGES;
+  uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
+  uint64_t* p_full = s_full + 2;            // [2]
+  uint64_t* o_done = p_full + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.x * AT_BM;
+  const int h = blockIdx.y;
+  const int img = blockIdx.z;
+  const int src = (img + p.src_offset) % p.n_img;
+  const int nq = p.nq ? p.nq[img] : p.Nq_max;
+  const int nk = p.nk ? p.nk[src] : p.Nk_max;
+  if (q0 >= nq) return;
+  const int T = (nk + AT_BN - 1) / AT_BN;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_q);
+    tma_prefetch_desc(&tm_k);
+    tma_prefetch_desc(&tm_v);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < AT_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&p_full[b], 128);
+    }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, AT_TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (elect_one() && T > 0) {
+      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+      tma_load_3d(s_q, &tm_q, q_full, h * AT_D, q0, img);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
+        uint8_t* st = s_kv + s * 2 * AT_TILE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE_BYTES);
+        tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * AT_BN, src);
+        tma_load_3d(st + AT_TILE_BYTES, &tm_v, &kv_full[s], h * AT_D, j * AT_BN, src);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ UMMA issuer
+    if (elect_one() && T > 0) {
+      constexpr uint32_t idesc_qk = make_idesc(FMT_F16, AT_BM, AT_BN, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(FMT_F16, AT_BM, AT_D, 0, 1);  // B = V, MN-major
+      const uint32_t q_addr = smem_u32(s_q);
+      auto issue_qk = [&](int j) {
+        const int s = j % AT_STAGES;
+        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t k_addr = smem_u32(s_kv + s * 2 * AT_TILE_BYTES);
+        const uint32_t d = tmem_base + AT_COL_S + (j & 1) * AT_BN;
+#pragma unroll
+        for (int kk = 0; kk < AT_D / 16; ++kk)
+          umma_f16_ss(d, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) issue_qk(j + 1);
+        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        tc_fence_after();
+        const int s = j % AT_STAGES;
+        const uint32_t v_addr = smem_u32(s_kv + s * 2 * AT_TILE_BYTES + AT_TILE_BYTES);
+        const uint32_t a_tmem = tmem_base + AT_COL_S + (j & 1) * AT_BN;
+#pragma unroll
+        for (int kk = 0; kk < AT_BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
+          umma_f16_ts(tmem_base + AT_COL_O, a_tmem + kk * 8, make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024),
+                      idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[s]);
+        umma_commit(o_done);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax / correction / epilogue
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane_id();
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int qrow = q0 + row;
+    const bool row_ok = qrow < nq;
+    float m_run = -INFINITY, l_run = 0.f;
+    float lse_in = 0.f;
+    if (p.shared && row_ok) lse_in = p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow];
+
+    for (int j = 0; j < T; ++j) {
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_base + lane_off + AT_COL_S + (j & 1) * AT_BN;
+      uint32_t r[AT_BN];
+      tmem_ld_x32(s_addr, r);
+      tmem_ld_x32(s_addr + 32, r + 32);
+      tmem_ld_x32(s_addr + 64, r + 64);
+      tmem_ld_x32(s_addr + 96, r + 96);
+      tmem_wait_ld();
+      const int kbase = j * AT_BN;
+      if (kbase + AT_BN > nk) {  // ragged last tile: keys beyond nk do not exist
+#pragma unroll
+        for (int c = 0; c < AT_BN; ++c)
+          if (kbase + c >= nk) r[c] = 0xff800000u;  // -inf
+      }
+      float neg_ref;
+      if (!p.shared) {
+        float mx = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < AT_BN; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+        const float m_new = fmaxf(m_run, mx * AT_SCALE_LOG2);
+        const bool need = m_new > m_run + AT_RESCALE_TAU;  // first tile: m_run = -inf
+        const bool any = __any_sync(0xffffffffu, need);
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);  // O += P(j-1) V(j-1) has landed
+          tc_fence_after();
+        }
+        if (any) {
+          const float alpha = need ? fast_exp2(m_run - m_new) : 1.f;
+          if (need) {
+            l_run *= alpha;
+            m_run = m_new;
+          }
+          if (j > 0) {
+            uint32_t o[AT_D];
+            const uint32_t o_addr = tmem_base + lane_off + AT_COL_O;
+            tmem_ld_x32(o_addr, o);
+            tmem_ld_x32(o_addr + 32, o + 32);
+            tmem_wait_ld();
+#pragma unroll
+            for (int c = 0; c < AT_D; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+            tmem_st_x32(o_addr, o);
+            tmem_st_x32(o_addr + 32, o + 32);
+          }
+        }
+        neg_ref = -m_run;
+      } else {
+        if (j > 0) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+        }
+        neg_ref = -lse_in;
+      }
+      uint32_t pk[AT_BN / 2];
+      float lsum = 0.f;
+#pragma unroll
+      for (int c = 0; c < AT_BN; c += 2) {
+        const float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+        const float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+        lsum += p0 + p1;
+        pk[c >> 1] = pack_half2(p0, p1);
+      }
+      l_run += lsum;
+      tmem_st_x32(s_addr, pk);
+      tmem_st_x32(s_addr + 32, pk + 32);
+      tmem_wait_st();
+      tc_fence_before();
+      mbar_arrive(&p_full[j & 1]);
+    }
+
+    // epilogue: O / l -> fp16 hi/lo planes; LSE for the sharing layers / column sums
+    __half* oh = p.out_hi + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
+    __half* ol = p.out_lo + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
+    float v[AT_D];
+    if (T > 0) {
+      mbar_wait(o_done, (T - 1) & 1);
+      tc_fence_after();
+      uint32_t o[AT_D];
+      const uint32_t o_addr = tmem_base + lane_off + AT_COL_O;
+      tmem_ld_x32(o_addr, o);
+      tmem_ld_x32(o_addr + 32, o + 32);
+      tmem_wait_ld();
+      const float inv = p.shared ? 1.f : 1.f / l_run;
+#pragma unroll
+      for (int c = 0; c < AT_D; ++c) v[c] = __uint_as_float(o[c]) * inv;
+    } else {
+#pragma unroll
+      for (int c = 0; c < AT_D; ++c) v[c] = 0.f;
+    }
+    if (row_ok) {
+#pragma unroll
+      for (int c = 0; c < AT_D; c += 8) {
+        uint32_t hi[4], lo[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          __half h0, l0, h1, l1;
+          split_f16x2(v[c + 2 * t], h0, l0);
+          split_f16x2(v[c + 2 * t + 1], h1, l1);
+          __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+          hi[t] = *reinterpret_cast<uint32_t*>(&hh);
+          lo[t] = *reinterpret_cast<uint32_t*>(&ll);
+        }
+        *reinterpret_cast<uint4*>(oh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(ol + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      if (!p.shared) p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow] = m_run + log2f(l_run);
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+  }
+}
+
+int launch_attention(const AttnArgs& a, cudaStream_t st) {
+  IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
+  CUtensorMap tq, tk, tv;
+  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, AT_C, a.q_img_stride, AT_D, AT_BM)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  AttnKernelParams p;
+  p.n_img = a.n_img;
+  p.src_offset = a.src_offset;
+  p.Nq_max = a.Nq_max;
+  p.Nk_max = a.Nk_max;
+  p.shared = a.shared;
+  p.nq = a.nq;
+  p.nk = a.nk;
+  p.lse = a.lse;
+  p.out_hi = reinterpret_cast<__half*>(a.out_hi);
+  p.out_lo = reinterpret_cast<__half*>(a.out_lo);
+  p.out_img_stride = a.out_img_stride;
+  const size_t smem = AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.Nq_max + AT_BM - 1) / AT_BM, AT_HEADS, a.n_img);
+  attention_kernel<<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Column sums of the attention map without materialising it: transposed score tiles S^T = K Q^T (keys on the TMEM
+// lanes), p = exp2(S^T c - lse[query]) summed along the row, accumulated over query tiles and heads.
+static constexpr int CS_THREADS = 192;
+static constexpr int CS_STAGES = 4;
+
+struct ColsumKernelParams {
+  int n_img, src_offset, Nq_max, Nk_max;
+  const int *nq, *nk;
+  const float* lse;
+  float* colsum;
+};
+
+__global__ void __launch_bounds__(CS_THREADS, 1)
+attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                        const ColsumKernelParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_k = smem;                   // the CTA's 128 keys (A operand)
+  uint8_t* s_q = smem + AT_TILE_BYTES;   // ring of query tiles (B operand)
+  float* s_lse = reinterpret_cast<float*>(s_q + CS_STAGES * AT_TILE_BYTES);  // [CS_STAGES][128]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lse + CS_STAGES * AT_BN);
+  uint64_t* k_full = bars;
+  uint64_t* q_full = bars + 1;
+  uint64_t* q_empty = q_full + CS_STAGES;
+  uint64_t* s_full = q_empty + CS_STAGES;  // [2]
+  uint64_t* s_free = s_full + 2;           // [2]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int k0 = blockIdx.x * AT_BN;
+  const int h = blockIdx.y;
+  const int img = blockIdx.z;  // query image; keys come from src
+  const int src = (img + p.src_offset) % p.n_img;
+  const int nq = p.nq ? p.nq[img] : p.Nq_max;
+  const int nk = p.nk ? p.nk[src] : p.Nk_max;
+  if (k0 >= nk) return;
+  const int T = (nq + AT_BM - 1) / AT_BM;
+
+  if (warp == 0 && elect_one()) {
+    mbar_init(k_full, 1);
+    for (int s = 0; s < CS_STAGES; ++s) {
+      mbar_init(&q_full[s], 1 + 128);  // TMA tx + the softmax threads that staged the LSE slice
+      mbar_init(&q_empty[s], 128);  // every softmax thread is done with the LSE slice (and the MMA with Q)
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&s_full[b], 1);
+      mbar_init(&s_free[b], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_ptr_smem, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (elect_one() && T > 0) {
+      mbar_arrive_expect_tx(k_full, AT_TILE_BYTES);
+      tma_load_3d(s_k, &tm_k, k_full, h * AT_D, k0, src);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % CS_STAGES;
+        mbar_wait(&q_empty[s], ((j / CS_STAGES) & 1) ^ 1);
+        mbar_arrive_expect_tx(&q_full[s], AT_TILE_BYTES);
+        tma_load_3d(s_q + s * AT_TILE_BYTES, &tm_q, &q_full[s], h * AT_D, j * AT_BM, img);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one() && T > 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_F16, AT_BN, AT_BM, 0, 0);
+      const uint32_t k_addr = smem_u32(s_k);
+      mbar_wait(k_full, 0);
+      for (int j = 0; j < T; ++j) {
+        const int s = j % CS_STAGES;
+        mbar_wait(&q_full[s], (j / CS_STAGES) & 1);
+        mbar_wait(&s_free[j & 1], ((j >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t q_addr = smem_u32(s_q + s * AT_TILE_BYTES);
+        const uint32_t d = tmem_base + (j & 1) * AT_BM;
+#pragma unroll
+        for (int kk = 0; kk < AT_D / 16; ++kk)
+          umma_f16_ss(d, make_smem_desc_sw128(k_addr + kk * 32, 16, 1024),
+                      make_smem_desc_sw128(q_addr + kk * 32, 16, 1024), idesc, kk > 0 ? 1u : 0u);
+        umma_commit(&s_full[j & 1]);
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int t128 = (warp - 2) * 32 + lane_id();  // 0..127 index among the softmax threads
+    const int row = quarter * 32 + lane_id();      // key row (TMEM lane)
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    float acc = 0.f;
+    // stage the LSE slices: thread t128 loads lse[query j*128 + t128] for tile j (prefetch distance = ring depth)
+    auto stage_lse = [&](int j) {
+      const int s = j % CS_STAGES;
+      if (j >= CS_STAGES) mbar_wait(&q_empty[s], ((j / CS_STAGES) & 1) ^ 1);
+      const int qi = j * AT_BM + t128;
+      s_lse[s * AT_BN + t128] = (qi < nq) ? p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qi] : INFINITY;
+      mbar_arrive(&q_full[s]);
+    };
+    for (int j = 0; j < T && j < CS_STAGES - 1; ++j) stage_lse(j);
+    for (int j = 0; j < T; ++j) {
+      if (j + CS_STAGES - 1 < T) stage_lse(j + CS_STAGES - 1);
+      const int s = j % CS_STAGES;
+      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      tc_fence_after();
+      const uint32_t s_addr = tmem_base + lane_off + (j & 1) * AT_BM;
+      const float* lse_t = s_lse + s * AT_BN;
+#pragma unroll
+      for (int cb = 0; cb < AT_BM; cb += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(s_addr + cb, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int c = 0; c < 32; ++c)
+          acc += fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, -lse_t[cb + c]));  // lse = +inf -> 0
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[j & 1]);
+      // this thread is done with the LSE slice; the MMA that read the Q tile completed before s_full fired
+      mbar_arrive(&q_empty[s]);
+    }
+    if (k0 + row < nk) atomicAdd(p.colsum + (long long)img * p.Nk_max + k0 + row, acc);
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+int launch_attention_colsum(const AttnColsumArgs& a, cudaStream_t st) {
+  IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention_colsum: empty problem");
+  CUtensorMap tq, tk;
+  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, AT_C, a.q_img_stride, AT_D, AT_BM)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  ColsumKernelParams p;
+  p.n_img = a.n_img;
+  p.src_offset = a.src_offset;
+  p.Nq_max = a.Nq_max;
+  p.Nk_max = a.Nk_max;
+  p.nq = a.nq;
+  p.nk = a.nk;
+  p.lse = a.lse;
+  p.colsum = a.colsum;
+  IMP_CUDA_OK(cudaMemsetAsync(a.colsum, 0, (size_t)a.n_img * a.Nk_max * sizeof(float), st));
+  const size_t smem = AT_TILE_BYTES + CS_STAGES * AT_TILE_BYTES + CS_STAGES * AT_BN * 4 + 1024 + 256;
+  static bool configured = false;
+  if (!configured) {
+    IMP_CUDA_OK(cudaFuncSetAttribute(attention_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((a.Nk_max + AT_BN - 1) / AT_BN, AT_HEADS, a.n_img);
+  attention_colsum_kernel<<<grid, CS_THREADS, smem, st>>>(tq, tk, p);
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace imp

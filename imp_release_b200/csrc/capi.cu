@@ -1,0 +1,68 @@
+// extern "C" surface of libimp_b200.so (declared in include/imp_b200.h).
+#include "../../include/imp_b200.h"
+
+#include "attention.cuh"
+#include "common.h"
+#include "elementwise.cuh"
+#include "gemm.cuh"
+#include "sinkhorn.cuh"
+
+namespace imp {
+int launch_pool_select(const imp_pool_args& a, cudaStream_t st);
+int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
+                        unsigned long long* col_key, int N0, int N1, int batch, cudaStream_t st);
+int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
+                        int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st);
+}  // namespace imp
+
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+IMP_API const char* imp_last_error(void) { return imp::last_error(); }
+IMP_API int imp_abi_version(void) { return IMP_B200_ABI_VERSION; }
+
+IMP_API int imp_split_planes(const float* x, const float* addend, void* hi, void* lo, int64_t n, void* stream) {
+  return imp::launch_split_planes(x, addend, hi, lo, n, ST(stream));
+}
+IMP_API int imp_merge_planes(const void* hi, const void* lo, float* x, int64_t n, void* stream) {
+  return imp::launch_merge_planes(hi, lo, x, n, ST(stream));
+}
+IMP_API int imp_gemm(const imp_gemm_args* args, void* stream) { return imp::launch_gemm(*args, ST(stream)); }
+IMP_API int imp_attention(const imp_attn_args* args, void* stream) { return imp::launch_attention(*args, ST(stream)); }
+IMP_API int imp_attention_colsum(const imp_attn_colsum_args* args, void* stream) {
+  return imp::launch_attention_colsum(*args, ST(stream));
+}
+IMP_API int imp_instnorm_relu(const float* H, int64_t h_bs, int32_t ldh, const int32_t* ns, int32_t Nmax, int32_t C,
+                      int32_t batch, float eps, int32_t relu, void* out_hi, void* out_lo, float* out_f32, int64_t o_bs,
+                      int32_t ldo, void* stream) {
+  return imp::launch_instnorm_relu_split(H, h_bs, ldh, ns, Nmax, C, batch, eps, relu, out_hi, out_lo, out_f32, o_bs, ldo,
+                                         ST(stream));
+}
+IMP_API int imp_kenc_input(const float* norm_kpts, const float* scores, float* out_xyz4, int64_t tokens, void* stream) {
+  return imp::launch_kenc_input(norm_kpts, scores, out_xyz4, tokens, ST(stream));
+}
+IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const float* bias, float* Y, int32_t ldy, int64_t rows,
+                     int32_t Cin, int32_t Cout, void* stream) {
+  return imp::launch_small_linear(X, ldx, W, bias, Y, ldy, rows, Cin, Cout, ST(stream));
+}
+IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream) { return imp::launch_sinkhorn(*args, ST(stream)); }
+IMP_API int imp_matches(const imp_match_args* args, void* stream) { return imp::launch_matches(*args, ST(stream)); }
+IMP_API int imp_dual_softmax(const float* dist, int64_t d_bs, int32_t ldd, const float* bin_score, float* P, int64_t p_bs,
+                     int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1, int32_t batch, void* stream) {
+  return imp::launch_dual_softmax(dist, d_bs, ldd, bin_score, P, p_bs, ldp, row_lse, col_lse, N0, N1, batch, ST(stream));
+}
+IMP_API int imp_score_argmax(const float* P, int64_t p_bs, int32_t ldp, float* row_max, int32_t* row_arg, uint64_t* col_key,
+                     int32_t N0, int32_t N1, int32_t batch, void* stream) {
+  return imp::launch_score_argmax(P, p_bs, ldp, row_max, row_arg, reinterpret_cast<unsigned long long*>(col_key), N0, N1,
+                                  batch, ST(stream));
+}
+IMP_API int imp_pool_select(const imp_pool_args* args, void* stream) { return imp::launch_pool_select(*args, ST(stream)); }
+IMP_API int imp_gather_rows(const void* in, int64_t in_bs, int32_t row_bytes_in, const int32_t* ids, int32_t ids_ld,
+                    const int32_t* cnt, void* out, int64_t out_bs, int32_t row_bytes_out, int32_t copy_bytes,
+                    int32_t max_rows, int32_t batch, void* stream) {
+  return imp::launch_gather_rows(in, in_bs, row_bytes_in, ids, ids_ld, cnt, out, out_bs, row_bytes_out, copy_bytes,
+                                 max_rows, batch, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,37 @@
+// Host-side helpers shared by the kernel launchers: error capture, driver entry points, tensor maps.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace imp {
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+
+#define IMP_CUDA_OK(expr)                                                                     \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) {                                                                  \
+      imp::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return 1;                                                                               \
+    }                                                                                         \
+  } while (0)
+
+#define IMP_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      imp::set_error(__VA_ARGS__);    \
+      return 2;                       \
+    }                                 \
+  } while (0)
+
+// 3-D fp16 tensor map {inner = k elements, rows, batch}, 128-byte swizzle, zero OOB fill.
+// row_stride / batch_stride in elements.  box = {box_inner (64 -> 128 B), box_rows, 1}.
+int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
+                     uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows);
+
+int num_sms();
+
+}  // namespace imp

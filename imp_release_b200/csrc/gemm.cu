@@ -1,0 +1,295 @@
+// tcgen05 split-precision GEMM (see gemm.cuh).  One 128 x BN output tile per CTA:
+//   warp 0  : TMA producer  (hi/lo planes of A and B, 64-wide K slabs, 128B swizzle)
+//   warp 1  : UMMA issuer   (one elected lane; accumulator 128 lanes x BN columns of TMEM)
+//   warp 2  : TMEM allocator
+//   warps 4-7: epilogue     (tcgen05.ld, bias / residual / hi-lo split, vectorised global stores)
+#include "gemm.cuh"
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace imp {
+
+static constexpr int GEMM_BM = 128;
+static constexpr int GEMM_BK = 64;  // fp16 elements = one 128-byte swizzle span
+static constexpr int GEMM_THREADS = 256;
+
+struct GemmKernelParams {
+  int M, N, KB1, KB, b_batched, nsplit, out_mode;
+  float alpha;
+  const float* bias;
+  void *out0, *out1;
+  const __half *res_hi, *res_lo;
+  long long out_row_stride, out_batch_stride;
+};
+
+template <int BN>
+struct GemmSmem {
+  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB per plane
+  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
+                     const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
+                     const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
+                     const GemmKernelParams p) {
+  using S = GemmSmem<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full_bar = empty_bar + STAGES;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int n0 = blockIdx.x * BN;
+  const int m0 = blockIdx.y * GEMM_BM;
+  const int z = blockIdx.z;
+  const bool split = p.nsplit == 3;
+
+  if (warp == 0 && elect_one()) {
+    tma_prefetch_desc(&tm_a_hi);
+    tma_prefetch_desc(&tm_b_hi);
+    if (split) {
+      tma_prefetch_desc(&tm_a_lo);
+      tma_prefetch_desc(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && elect_one()) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t tx = split ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
+        uint8_t* st = smem + s * S::STAGE_BYTES;
+        mbar_arrive_expect_tx(&full_bar[s], tx);
+        const bool seg2 = kb >= p.KB1;
+        const int ka = (seg2 ? kb - p.KB1 : kb) * GEMM_BK;
+        tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
+        tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * GEMM_BK, n0, p.b_batched ? z : 0);
+        if (split) {
+          tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
+          tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * GEMM_BK, n0,
+                      p.b_batched ? z : 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      constexpr uint32_t idesc = make_idesc(FMT_F16, GEMM_BM, BN, 0, 0);
+      for (int kb = 0; kb < p.KB; ++kb) {
+        const int s = kb % STAGES;
+        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+        const uint32_t a_lo = a_hi + S::A_BYTES;
+        const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+        const uint32_t b_lo = b_hi + S::B_BYTES;
+#pragma unroll
+        for (int k = 0; k < GEMM_BK / 16; ++k) {
+          const uint32_t off = k * 32;  // 16 fp16 along K inside the swizzle span
+          const uint64_t dah = make_smem_desc_sw128(a_hi + off, 16, 1024);
+          const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 16, 1024);
+          umma_f16_ss(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          if (split) {
+            const uint64_t dal = make_smem_desc_sw128(a_lo + off, 16, 1024);
+            const uint64_t dbl = make_smem_desc_sw128(b_lo + off, 16, 1024);
+            umma_f16_ss(tmem_base, dal, dbh, idesc, 1u);
+            umma_f16_ss(tmem_base, dah, dbl, idesc, 1u);
+          }
+        }
+        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+      }
+      umma_commit(tmem_full_bar);
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;  // TMEM lane quarter this warp may touch
+    const int row = q * 32 + lane_id();
+    const long long gm = m0 + row;
+    const bool row_ok = gm < p.M;
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    const long long obase = (long long)z * p.out_batch_stride + gm * p.out_row_stride;
+#pragma unroll 1
+    for (int c = 0; c < BN / 32; ++c) {
+      const int nc = n0 + c * 32;
+      if (nc >= p.N) break;  // warp-uniform
+      uint32_t r[32];
+      tmem_ld_x32(t_row + c * 32, r);
+      tmem_wait_ld();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+      const bool full = nc + 32 <= p.N;
+      if (p.bias != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (full || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
+      }
+      if (!row_ok) continue;
+      if (p.out_mode == GEMM_OUT_F32) {
+        float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4)
+            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        } else {
+          for (int j = 0; j < 32 && nc + j < p.N; ++j) o[j] = v[j];
+        }
+      } else if (p.out_mode == GEMM_OUT_F16) {
+        __half* o = reinterpret_cast<__half*>(p.out0) + obase + nc;
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint4 pk;
+            pk.x = pack_half2(v[j], v[j + 1]);
+            pk.y = pack_half2(v[j + 2], v[j + 3]);
+            pk.z = pack_half2(v[j + 4], v[j + 5]);
+            pk.w = pack_half2(v[j + 6], v[j + 7]);
+            *reinterpret_cast<uint4*>(o + j) = pk;
+          }
+        } else {
+          for (int j = 0; j < 32 && nc + j < p.N; ++j) o[j] = __float2half_rn(v[j]);
+        }
+      } else {
+        __half* oh = reinterpret_cast<__half*>(p.out0) + obase + nc;
+        __half* ol = reinterpret_cast<__half*>(p.out1) + obase + nc;
+        if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
+          const __half* rh = p.res_hi + obase + nc;
+          const __half* rl = p.res_lo + obase + nc;
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              const uint4 a = *reinterpret_cast<const uint4*>(rh + j);
+              const uint4 b = *reinterpret_cast<const uint4*>(rl + j);
+              const __half2* ah = reinterpret_cast<const __half2*>(&a);
+              const __half2* bh = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+              for (int t = 0; t < 4; ++t) {
+                const float2 fa = __half22float2(ah[t]);
+                const float2 fb = __half22float2(bh[t]);
+                v[j + 2 * t] += fa.x + fb.x;
+                v[j + 2 * t + 1] += fa.y + fb.y;
+              }
+            }
+          } else {
+            for (int j = 0; j < 32 && nc + j < p.N; ++j) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
+          }
+        }
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+              __half h0, l0, h1, l1;
+              split_f16x2(v[j + 2 * t], h0, l0);
+              split_f16x2(v[j + 2 * t + 1], h1, l1);
+              __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+              hi[t] = *reinterpret_cast<uint32_t*>(&hh);
+              lo[t] = *reinterpret_cast<uint32_t*>(&ll);
+            }
+            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(ol + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        } else {
+          for (int j = 0; j < 32 && nc + j < p.N; ++j) {
+            __half h, l;
+            split_f16x2(v[j], h, l);
+            oh[j] = h;
+            ol[j] = l;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, BN);
+  }
+}
+
+template <int BN, int STAGES>
+static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
+  using S = GemmSmem<BN>;
+  const bool split = g.nsplit == 3;
+  CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo;
+  const int Kt = g.K1 + g.K2;
+  if (make_tmap_f16_3d(&ta_hi, g.a_hi, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+  ta_lo = ta_hi;
+  if (split && make_tmap_f16_3d(&ta_lo, g.a_lo, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+  ta2_hi = ta_hi;
+  ta2_lo = ta_lo;
+  if (g.K2 > 0) {
+    if (make_tmap_f16_3d(&ta2_hi, g.a2_hi, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+    ta2_lo = ta2_hi;
+    if (split && make_tmap_f16_3d(&ta2_lo, g.a2_lo, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+  }
+  const int bb = g.b_batched ? g.batch : 1;
+  if (make_tmap_f16_3d(&tb_hi, g.b_hi, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, GEMM_BK, BN)) return 3;
+  tb_lo = tb_hi;
+  if (split && make_tmap_f16_3d(&tb_lo, g.b_lo, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, GEMM_BK, BN)) return 3;
+
+  GemmKernelParams p;
+  p.M = g.M;
+  p.N = g.N;
+  p.KB1 = g.K1 / GEMM_BK;
+  p.KB = Kt / GEMM_BK;
+  p.b_batched = g.b_batched;
+  p.nsplit = g.nsplit;
+  p.out_mode = g.out_mode;
+  p.alpha = g.alpha;
+  p.bias = g.bias;
+  p.out0 = g.out0;
+  p.out1 = g.out1;
+  p.res_hi = reinterpret_cast<const __half*>(g.res_hi);
+  p.res_lo = reinterpret_cast<const __half*>(g.res_lo);
+  p.out_row_stride = g.out_row_stride;
+  p.out_batch_stride = g.out_batch_stride;
+
+  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256;
+  auto kern = gemm_f16split_kernel<BN, STAGES>;
+  static bool configured = false;
+  if (!configured) {
+    IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.batch);
+  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo, p);
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
+  IMP_REQUIRE(g.nsplit == 1 || g.nsplit == 3, "gemm: nsplit must be 1 or 3");
+  IMP_REQUIRE(g.K1 > 0 && g.K1 % GEMM_BK == 0 && g.K2 % GEMM_BK == 0, "gemm: K segments must be multiples of 64 (got %d, %d)", g.K1, g.K2);
+  IMP_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0, "gemm: empty problem");
+  IMP_REQUIRE(g.out_row_stride % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+  if (g.N > 128) return launch_impl<256, 2>(g, stream);
+  return launch_impl<128, 3>(g, stream);
+}
+
+}  // namespace imp

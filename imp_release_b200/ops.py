@@ -1,0 +1,240 @@
+"""Tensor-level wrappers around the C ABI (device memory and streams come from PyTorch; all arithmetic runs
+in libimp_b200.so).  Every function enqueues on the current CUDA stream and never synchronises."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (AttnArgs, AttnColsumArgs, GemmArgs, MatchArgs, PoolArgs, SinkhornArgs, check, ptr, stream_ptr)
+
+OUT_F32, OUT_F16, OUT_SPLIT, OUT_SPLIT_RESID = 0, 1, 2, 3
+
+
+def _require_cuda(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.ImpLibraryError('imp_release_b200 kernels need CUDA tensors (there is no CPU path)')
+
+
+class Planes:
+    """fp16 hi/lo plane pair representing an fp32 tensor (x ~= hi + lo, ~22 mantissa bits)."""
+    __slots__ = ('hi', 'lo')
+
+    def __init__(self, hi: torch.Tensor, lo: torch.Tensor):
+        self.hi, self.lo = hi, lo
+
+    @staticmethod
+    def empty(shape, device) -> 'Planes':
+        return Planes(torch.zeros(shape, dtype=torch.float16, device=device),
+                      torch.zeros(shape, dtype=torch.float16, device=device))
+
+    @property
+    def shape(self):
+        return self.hi.shape
+
+    def float(self) -> torch.Tensor:
+        out = torch.empty(self.hi.shape, dtype=torch.float32, device=self.hi.device)
+        merge_planes(self, out)
+        return out
+
+
+def split_planes(x: torch.Tensor, out: Optional[Planes] = None, addend: Optional[torch.Tensor] = None) -> Planes:
+    _require_cuda(x)
+    x = x.contiguous()
+    if addend is not None:
+        addend = addend.contiguous()
+    if out is None:
+        out = Planes.empty(x.shape, x.device)
+    check(_lib.load().imp_split_planes(ptr(x), ptr(addend), ptr(out.hi), ptr(out.lo), x.numel(), stream_ptr()),
+          'imp_split_planes')
+    return out
+
+
+def merge_planes(p: Planes, out: torch.Tensor) -> torch.Tensor:
+    check(_lib.load().imp_merge_planes(ptr(p.hi), ptr(p.lo), ptr(out), p.hi.numel(), stream_ptr()), 'imp_merge_planes')
+    return out
+
+
+def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row_stride: int, a_batch_stride: int = 0,
+         b_row_stride: int, b_batch_stride: int = 0, b_batched: bool = False, a2: Optional[Planes] = None, K2: int = 0,
+         a2_row_stride: int = 0, a2_batch_stride: int = 0, nsplit: int = 3, alpha: float = 1.0,
+         bias: Optional[torch.Tensor] = None, out_mode: int = OUT_F32, out0: torch.Tensor = None,
+         out1: Optional[torch.Tensor] = None, out_row_stride: int = 0, out_batch_stride: int = 0,
+         res: Optional[Planes] = None, a_offset: int = 0, a2_offset: int = 0, b_offset: int = 0, out_offset: int = 0):
+    """D = alpha * A.B^T (+bias)(+res).  Offsets are in elements from the start of the plane tensors."""
+    g = GemmArgs()
+    esz = 2
+    g.a_hi = a.hi.data_ptr() + a_offset * esz
+    g.a_lo = a.lo.data_ptr() + a_offset * esz
+    if a2 is not None:
+        g.a2_hi = a2.hi.data_ptr() + a2_offset * esz
+        g.a2_lo = a2.lo.data_ptr() + a2_offset * esz
+    g.a_row_stride, g.a_batch_stride = a_row_stride, a_batch_stride
+    g.a2_row_stride, g.a2_batch_stride = a2_row_stride, a2_batch_stride
+    g.b_hi = b.hi.data_ptr() + b_offset * esz
+    g.b_lo = b.lo.data_ptr() + b_offset * esz
+    g.b_row_stride, g.b_batch_stride = b_row_stride, b_batch_stride
+    g.M, g.N, g.K1, g.K2, g.batch, g.b_batched = M, N, K1, K2, batch, int(b_batched)
+    g.nsplit, g.alpha = nsplit, alpha
+    g.bias = ptr(bias)
+    g.out_mode = out_mode
+    osz = 4 if out_mode == OUT_F32 else 2
+    g.out0 = out0.data_ptr() + out_offset * osz
+    g.out1 = (out1.data_ptr() + out_offset * osz) if out1 is not None else None
+    g.out_row_stride, g.out_batch_stride = out_row_stride, out_batch_stride
+    if res is not None:
+        g.res_hi = res.hi.data_ptr() + out_offset * esz
+        g.res_lo = res.lo.data_ptr() + out_offset * esz
+    check(_lib.load().imp_gemm(C.byref(g), stream_ptr()), 'imp_gemm')
+
+
+def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, shared: bool, lse,
+              out: Planes, q_img_stride: Optional[int] = None, kv_img_stride: Optional[int] = None):
+    a = AttnArgs()
+    a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
+    a.q_img_stride = q_img_stride if q_img_stride is not None else Nq_max * 256
+    a.kv_img_stride = kv_img_stride if kv_img_stride is not None else Nk_max * 256
+    a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
+    a.nq, a.nk = ptr(nq), ptr(nk)
+    a.shared = int(shared)
+    a.lse = ptr(lse)
+    a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
+    a.out_img_stride = Nq_max * 256
+    check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
+
+
+def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, lse, colsum):
+    a = AttnColsumArgs()
+    a.q, a.k = ptr(q), ptr(k)
+    a.q_img_stride, a.kv_img_stride = Nq_max * 256, Nk_max * 256
+    a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
+    a.nq, a.nk = ptr(nq), ptr(nk)
+    a.lse, a.colsum = ptr(lse), ptr(colsum)
+    check(_lib.load().imp_attention_colsum(C.byref(a), stream_ptr()), 'imp_attention_colsum')
+
+
+def instnorm_relu(H: torch.Tensor, *, batch: int, Nmax: int, C_: int, ns=None, eps: float = 1e-3, relu: bool = True,
+                  out: Optional[Planes] = None, out_f32: Optional[torch.Tensor] = None):
+    """H [batch, Nmax, C] fp32 contiguous -> planes / fp32 of the same logical shape."""
+    check(_lib.load().imp_instnorm_relu(ptr(H), Nmax * C_, C_, ptr(ns), Nmax, C_, batch, eps, int(relu),
+                                        ptr(out.hi) if out is not None else None,
+                                        ptr(out.lo) if out is not None else None, ptr(out_f32), Nmax * C_, C_,
+                                        stream_ptr()), 'imp_instnorm_relu')
+
+
+def kenc_input(norm_kpts: torch.Tensor, scores: torch.Tensor, out: torch.Tensor):
+    check(_lib.load().imp_kenc_input(ptr(norm_kpts), ptr(scores), ptr(out), scores.numel(), stream_ptr()),
+          'imp_kenc_input')
+
+
+def small_linear(X, ldx, W, bias, Y, ldy, rows, cin, cout):
+    check(_lib.load().imp_small_linear(ptr(X), ldx, ptr(W), ptr(bias), ptr(Y), ldy, rows, cin, cout, stream_ptr()),
+          'imp_small_linear')
+
+
+class SinkhornWorkspace:
+    """Buffers for one Sinkhorn + matching call on [batch, N0max, N1max] problems."""
+
+    def __init__(self, batch: int, N0max: int, N1max: int, device, want_mass: bool = False):
+        self.batch, self.N0max, self.N1max = batch, N0max, N1max
+        self.ldp = (N1max + 1 + 3) // 4 * 4
+        f32 = dict(dtype=torch.float32, device=device)
+        self.P = torch.zeros(batch, N0max + 1, self.ldp, **f32)
+        self.u = torch.empty(batch, N0max + 1, **f32)
+        self.colbuf = torch.empty(3, batch, self.ldp, **f32)
+        self.row_max = torch.zeros(batch, N0max, **f32)
+        self.row_arg = torch.zeros(batch, N0max, dtype=torch.int32, device=device)
+        self.col_key = torch.zeros(batch, N1max, dtype=torch.int64, device=device)
+        self.row_mass = torch.zeros(batch, N0max, **f32) if want_mass else None
+        self.col_mass = torch.zeros(batch, N1max, **f32) if want_mass else None
+
+    def scores(self) -> torch.Tensor:
+        """[batch, N0max+1, N1max+1] view of the padded score buffer (a real torch.Tensor)."""
+        return self.P[:, :, :self.N1max + 1]
+
+
+def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, ws: SinkhornWorkspace, n0s=None,
+             n1s=None, dist_batch_stride: Optional[int] = None):
+    a = SinkhornArgs()
+    a.dist = ptr(dist)
+    a.dist_batch_stride = dist_batch_stride if dist_batch_stride is not None else ws.N0max * ldd
+    a.ldd, a.iters = ldd, iters
+    a.bin_score = ptr(bin_score)
+    a.P, a.p_batch_stride, a.ldp = ptr(ws.P), (ws.N0max + 1) * ws.ldp, ws.ldp
+    a.u, a.colbuf = ptr(ws.u), ptr(ws.colbuf)
+    a.row_max, a.row_arg, a.col_key = ptr(ws.row_max), ptr(ws.row_arg), ptr(ws.col_key)
+    a.row_mass, a.col_mass = ptr(ws.row_mass), ptr(ws.col_mass)
+    a.n0s, a.n1s = ptr(n0s), ptr(n1s)
+    a.N0max, a.N1max, a.batch = ws.N0max, ws.N1max, ws.batch
+    check(_lib.load().imp_sinkhorn(C.byref(a), stream_ptr()), 'imp_sinkhorn')
+
+
+def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int, batch: int, n0s=None, n1s=None,
+            want1: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor, Optional[torch.Tensor]]:
+    dev = ws_row_max.device
+    i0 = torch.full((batch, N0max), -1, dtype=torch.int64, device=dev)
+    m0 = torch.zeros(batch, N0max, dtype=torch.float32, device=dev)
+    i1 = torch.full((batch, N1max), -1, dtype=torch.int64, device=dev) if want1 else None
+    m1 = torch.zeros(batch, N1max, dtype=torch.float32, device=dev) if want1 else None
+    m = MatchArgs()
+    m.row_max, m.row_arg, m.col_key = ptr(ws_row_max), ptr(ws_row_arg), ptr(ws_col_key)
+    m.p_thresh = p
+    m.indices0, m.indices1, m.mscores0, m.mscores1 = ptr(i0), ptr(i1), ptr(m0), ptr(m1)
+    m.n0s, m.n1s = ptr(n0s), ptr(n1s)
+    m.N0max, m.N1max, m.batch = N0max, N1max, batch
+    m.out0_batch_stride, m.out1_batch_stride = N0max, N1max
+    check(_lib.load().imp_matches(C.byref(m), stream_ptr()), 'imp_matches')
+    return i0, i1, m0, m1
+
+
+def score_argmax(P: torch.Tensor, N0: int, N1: int):
+    """Row/col arg-max over P[:, :N0, :N1] for an arbitrary (possibly strided-row) fp32 score tensor."""
+    batch = P.shape[0]
+    assert P.stride(2) == 1
+    dev = P.device
+    row_max = torch.empty(batch, N0, dtype=torch.float32, device=dev)
+    row_arg = torch.empty(batch, N0, dtype=torch.int32, device=dev)
+    col_key = torch.empty(batch, N1, dtype=torch.int64, device=dev)
+    check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key), N0, N1,
+                                       batch, stream_ptr()), 'imp_score_argmax')
+    return row_max, row_arg, col_key
+
+
+def dual_softmax(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, N0: int, N1: int, batch: int):
+    dev = dist.device
+    ldp = (N1 + 1 + 3) // 4 * 4
+    P = torch.empty(batch, N0 + 1, ldp, dtype=torch.float32, device=dev)
+    row_lse = torch.empty(batch, N0 + 1, dtype=torch.float32, device=dev)
+    col_lse = torch.empty(batch, N1 + 1, dtype=torch.float32, device=dev)
+    check(_lib.load().imp_dual_softmax(ptr(dist), N0 * ldd, ldd, ptr(bin_score), ptr(P), (N0 + 1) * ldp, ldp,
+                                       ptr(row_lse), ptr(col_lse), N0, N1, batch, stream_ptr()), 'imp_dual_softmax')
+    return P[:, :, :N1 + 1]
+
+
+def pool_select(mass, a_self, a_cross, n_full, ids_in, cnt_in, thresh: float, n_min_tokens: int):
+    batch, Nmax = ids_in.shape
+    dev = ids_in.device
+    ids_out = torch.zeros_like(ids_in)
+    cnt_out = torch.zeros(batch, dtype=torch.int32, device=dev)
+    changed = torch.zeros(batch, dtype=torch.int32, device=dev)
+    a = PoolArgs()
+    a.mass, a.a_self, a.a_cross = ptr(mass), ptr(a_self), ptr(a_cross)
+    a.n_full_ld, a.Nmax = a_self.stride(0), Nmax
+    a.n_full, a.ids_in, a.cnt_in = ptr(n_full), ptr(ids_in), ptr(cnt_in)
+    a.ids_out, a.cnt_out, a.changed = ptr(ids_out), ptr(cnt_out), ptr(changed)
+    a.thresh, a.n_min_tokens, a.batch = thresh, n_min_tokens, batch
+    check(_lib.load().imp_pool_select(C.byref(a), stream_ptr()), 'imp_pool_select')
+    return ids_out, cnt_out, changed
+
+
+def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: torch.Tensor, max_rows: int):
+    """out[b, r, :] = src[b, ids[b, r], :] for r < cnt[b]; src/out [batch, rows, C] contiguous, same dtype."""
+    batch = src.shape[0]
+    rb_in = src.stride(1) * src.element_size()
+    rb_out = out.stride(1) * out.element_size()
+    copy = src.shape[2] * src.element_size()
+    check(_lib.load().imp_gather_rows(ptr(src), src.stride(0) * src.element_size(), rb_in, ptr(ids), ids.stride(0),
+                                      ptr(cnt), ptr(out), out.stride(0) * out.element_size(), rb_out, copy, max_rows,
+                                      batch, stream_ptr()), 'imp_gather_rows')

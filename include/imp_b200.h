@@ -1,0 +1,175 @@
+/* imp_b200.h -- C ABI of libimp_b200.so: the sm_100a kernels behind the IMP / EIMP matcher hot path.
+ *
+ * Drop-in boundary: the reference (feixue94/imp-release) is pure PyTorch; its hot path is the set of
+ * nn.Module methods in nets/layers.py, nets/gm.py, nets/gms.py, nets/adgm.py that eval/eval_imp.py and
+ * eval/matching.py call.  The host side of this repo (imp_release_b200/nets/*.py, re-exported as `nets.*` by
+ * dropin/) keeps those Python signatures and state_dict keys and binds the entry points below through ctypes
+ * (INTEGRATION.md shows the binding).  Every entry point cites the reference lines it replaces.
+ *
+ * Conventions: all pointers are DEVICE pointers unless noted; the caller (PyTorch) owns every buffer; nothing is
+ * allocated inside; every call enqueues work on `stream` (a cudaStream_t passed as void*) and returns 0 on success,
+ * non-zero on error with a message available from imp_last_error() (thread local).  Token tensors are token-major
+ * [images, N, C].  "hi/lo planes" = two fp16 tensors whose sum carries ~22 mantissa bits of an fp32 value; the
+ * tensor-core GEMMs consume them with a 3-product split (hi*hi + lo*hi + hi*lo) for fp32-level accuracy.
+ */
+#ifndef IMP_B200_H_
+#define IMP_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IMP_B200_ABI_VERSION 1
+#if defined(__GNUC__)
+#define IMP_API __attribute__((visibility("default")))
+#else
+#define IMP_API
+#endif
+
+IMP_API const char* imp_last_error(void);
+IMP_API int imp_abi_version(void);
+
+/* ---- fp32 <-> hi/lo planes (boundary conversions; `addend` may be NULL) -------------------------------------- */
+/* desc + keypoint encoding, nets/gms.py:171-172 */
+IMP_API int imp_split_planes(const float* x, const float* addend, void* hi, void* lo, int64_t n, void* stream);
+IMP_API int imp_merge_planes(const void* hi, const void* lo, float* x, int64_t n, void* stream);
+
+/* ---- split-precision tensor-core GEMM: D = alpha * A . B^T (+bias) (+residual) -------------------------------
+ * replaces every Conv1d(kernel_size=1): nets/layers.py:119 (Q/K/V proj), :134 (merge, folded into W0),
+ * :149/:218 + :59-77 (MLP convs), nets/gm.py:291-292 (final_proj) and the score einsum nets/gm.py:293-294. */
+enum { IMP_GEMM_OUT_F32 = 0, IMP_GEMM_OUT_F16 = 1, IMP_GEMM_OUT_SPLIT = 2, IMP_GEMM_OUT_SPLIT_RESID = 3 };
+
+typedef struct imp_gemm_args {
+  const void *a_hi, *a_lo, *a2_hi, *a2_lo; /* A [batch, M, K1] (+ second K segment [batch, M, K2]) fp16 planes */
+  int64_t a_row_stride, a_batch_stride, a2_row_stride, a2_batch_stride; /* in elements */
+  const void *b_hi, *b_lo; /* B [b_batched ? batch : 1, N, K1+K2] fp16 planes */
+  int64_t b_row_stride, b_batch_stride;
+  int32_t M, N, K1, K2, batch, b_batched;
+  int32_t nsplit; /* 3 = hi/lo split (fp32-level accuracy), 1 = hi planes only */
+  float alpha;
+  const float* bias; /* [N] or NULL */
+  int32_t out_mode;
+  int32_t _pad;
+  void *out0, *out1; /* F32: out0 fp32 | F16: out0 fp16 | SPLIT*: out0 = hi plane, out1 = lo plane */
+  int64_t out_row_stride, out_batch_stride;
+  const void *res_hi, *res_lo; /* SPLIT_RESID: residual planes, same strides as out (may alias out) */
+} imp_gemm_args;
+IMP_API int imp_gemm(const imp_gemm_args* args, void* stream);
+
+/* ---- multi-head attention core (QK^T softmax PV), nets/layers.py:121-131 and :211-214 ----------------------- */
+typedef struct imp_attn_args {
+  const void *q, *k, *v; /* fp16 [n_img, N*_max, 256], heads contiguous */
+  int64_t q_img_stride, kv_img_stride;
+  int32_t n_img, src_offset, Nq_max, Nk_max;
+  const int32_t *nq, *nk; /* [n_img] valid rows (NULL -> max) */
+  int32_t shared;         /* 1: reuse previous probabilities via lse (SharedAttentionalPropagation) */
+  int32_t _pad;
+  float* lse;            /* [n_img, 4, Nq_max] log2-domain LSE; written if !shared, read if shared */
+  void *out_hi, *out_lo; /* [n_img, Nq_max, 256] fp16 planes */
+  int64_t out_img_stride;
+} imp_attn_args;
+IMP_API int imp_attention(const imp_attn_args* args, void* stream);
+
+/* attention received per source token, nets/adgm.py:424-427, :557-560 (prob.sum(1).sum(1)) */
+typedef struct imp_attn_colsum_args {
+  const void *q, *k;
+  int64_t q_img_stride, kv_img_stride;
+  int32_t n_img, src_offset, Nq_max, Nk_max;
+  const int32_t *nq, *nk;
+  const float* lse;
+  float* colsum; /* [n_img, Nk_max], indexed by QUERY image; row img = attention received by keys of image src(img) */
+} imp_attn_colsum_args;
+IMP_API int imp_attention_colsum(const imp_attn_colsum_args* args, void* stream);
+
+/* ---- InstanceNorm1d(eps, affine=False) over tokens + ReLU, nets/layers.py:68-72 ----------------------------- */
+/* H fp32 [batch, N, C] (row stride ldh) -> fp16 planes (or fp32 if out_f32 != NULL) with row stride ldo */
+IMP_API int imp_instnorm_relu(const float* H, int64_t h_batch_stride, int32_t ldh, const int32_t* ns, int32_t Nmax, int32_t C,
+                      int32_t batch, float eps, int32_t relu, void* out_hi, void* out_lo, float* out_f32,
+                      int64_t o_batch_stride, int32_t ldo, void* stream);
+
+/* ---- keypoint encoder narrow layers (3->32, 32->64), nets/layers.py:80-90 ----------------------------------- */
+IMP_API int imp_kenc_input(const float* norm_kpts, const float* scores, float* out_xyz4, int64_t tokens, void* stream);
+IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const float* bias, float* Y, int32_t ldy,
+                     int64_t rows, int32_t Cin, int32_t Cout, void* stream);
+
+/* ---- Sinkhorn optimal transport + fused arg-max, nets/layers.py:27-46 (sink_algorithm / sinkhorn) ----------- */
+typedef struct imp_sinkhorn_args {
+  const float* dist; /* [batch, N0max, ldd] */
+  int64_t dist_batch_stride;
+  int32_t ldd;
+  int32_t iters;
+  const float* bin_score; /* device scalar (model.bin_score) */
+  float* P;               /* [batch, N0max+1, ldp] workspace = output scores (row stride ldp, multiple of 4) */
+  int64_t p_batch_stride;
+  int32_t ldp;
+  int32_t _pad;
+  float* u;          /* [batch, N0max+1] */
+  float* colbuf;     /* [3, batch, ldp] */
+  float* row_max;    /* [batch, N0max] */
+  int32_t* row_arg;  /* [batch, N0max] */
+  uint64_t* col_key; /* [batch, N1max] packed column arg-max */
+  float* row_mass;   /* [batch, N0max] or NULL: sum_j scores[i, :N1] (pooling, nets/adgm.py:476) */
+  float* col_mass;   /* [batch, N1max] or NULL */
+  const int32_t *n0s, *n1s; /* per-sample sizes or NULL */
+  int32_t N0max, N1max, batch, _pad2;
+} imp_sinkhorn_args;
+IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
+
+/* mutual-NN matches, GM.compute_matches nets/gm.py:305-320 (int64 indices like torch) */
+typedef struct imp_match_args {
+  const float* row_max;
+  const int32_t* row_arg;
+  const uint64_t* col_key;
+  float p_thresh;
+  int32_t _pad;
+  int64_t *indices0, *indices1;
+  float *mscores0, *mscores1;
+  const int32_t *n0s, *n1s;
+  int32_t N0max, N1max, batch, _pad2;
+  int64_t out0_batch_stride, out1_batch_stride;
+} imp_match_args;
+IMP_API int imp_matches(const imp_match_args* args, void* stream);
+
+/* dual-softmax scorer, nets/layers.py:20-24 (with_sinkhorn=False) */
+IMP_API int imp_dual_softmax(const float* dist, int64_t dist_batch_stride, int32_t ldd, const float* bin_score, float* P,
+                     int64_t p_batch_stride, int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1,
+                     int32_t batch, void* stream);
+/* row / column arg-max of an existing score matrix (compute_matches on caller-provided scores) */
+IMP_API int imp_score_argmax(const float* P, int64_t p_batch_stride, int32_t ldp, float* row_max, int32_t* row_arg,
+                     uint64_t* col_key, int32_t N0, int32_t N1, int32_t batch, void* stream);
+
+/* ---- EIMP adaptive pooling, nets/adgm.py:463-500 and :552-605 ------------------------------------------------
+ * keep = { i : mass_i >= thresh } U { i : a_self_i >= lower_median(a_self[pids]) } U { i : a_cross_i >= ... },
+ * evaluated on the current kept subset ids_in[0..cnt_in) (global ids, sorted); writes the new sorted global ids
+ * and count.  If cnt_in <= n_min_tokens or no row passes the threshold the subset is copied unchanged and
+ * changed[b] = 0.  a_self / a_cross are UN-normalised received-attention sums indexed by GLOBAL id; they are
+ * normalised by their full-row sums inside (nets/adgm.py:429-432). */
+typedef struct imp_pool_args {
+  const float* mass;  /* [batch, Nmax] indexed by subset position */
+  const float *a_self, *a_cross; /* [batch, Nmax] indexed by global id */
+  int32_t n_full_ld;  /* row stride of a_self / a_cross */
+  int32_t Nmax;
+  const int32_t* n_full;  /* [batch] number of tokens of the full image (normalisation length) */
+  const int32_t* ids_in;  /* [batch, Nmax] */
+  const int32_t* cnt_in;  /* [batch] */
+  int32_t* ids_out;       /* [batch, Nmax] */
+  int32_t* cnt_out;       /* [batch] */
+  int32_t* changed;       /* [batch] */
+  float thresh;
+  int32_t n_min_tokens;
+  int32_t batch;
+  int32_t _pad;
+} imp_pool_args;
+IMP_API int imp_pool_select(const imp_pool_args* args, void* stream);
+
+/* row gather for compaction: out[b, r, :copy_bytes] = in[b, ids[b, r], :copy_bytes], r < cnt[b] */
+IMP_API int imp_gather_rows(const void* in, int64_t in_batch_stride_bytes, int32_t row_bytes_in, const int32_t* ids,
+                    int32_t ids_ld, const int32_t* cnt, void* out, int64_t out_batch_stride_bytes,
+                    int32_t row_bytes_out, int32_t copy_bytes, int32_t max_rows, int32_t batch, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IMP_B200_H_ */
