@@ -35,14 +35,14 @@ class GemmArgs(C.Structure):
 
 class AttnArgs(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('q_img_stride', c_i64), ('kv_img_stride', c_i64),
-                ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
+                ('q_row_stride', c_i32), ('kv_row_stride', c_i32), ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
                 ('nq', c_vp), ('nk', c_vp), ('shared', c_i32), ('_pad', c_i32), ('lse', c_vp),
                 ('out_hi', c_vp), ('out_lo', c_vp), ('out_img_stride', c_i64)]
 
 
 class AttnColsumArgs(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('q_img_stride', c_i64), ('kv_img_stride', c_i64),
-                ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
+                ('q_row_stride', c_i32), ('kv_row_stride', c_i32), ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
                 ('nq', c_vp), ('nk', c_vp), ('lse', c_vp), ('colsum', c_vp)]
 
 
@@ -61,8 +61,8 @@ class MatchArgs(C.Structure):
 
 
 class PoolArgs(C.Structure):
-    _fields_ = [('mass', c_vp), ('a_self', c_vp), ('a_cross', c_vp), ('n_full_ld', c_i32), ('Nmax', c_i32),
-                ('n_full', c_vp), ('ids_in', c_vp), ('cnt_in', c_vp), ('ids_out', c_vp), ('cnt_out', c_vp),
+    _fields_ = [('mass', c_vp), ('a_self', c_vp), ('a_cross', c_vp), ('ld', c_i32), ('_pad0', c_i32),
+                ('ids_in', c_vp), ('cnt_in', c_vp), ('ids_out', c_vp), ('cnt_out', c_vp),
                 ('changed', c_vp), ('thresh', c_f32), ('n_min_tokens', c_i32), ('batch', c_i32), ('_pad', c_i32)]
 
 
@@ -84,6 +84,7 @@ SIGNATURES = {
     'imp_dual_softmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'imp_pool_select': (C.c_int, [C.POINTER(PoolArgs), c_vp]),
+    'imp_scatter_matches': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'imp_gather_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
 }
 

@@ -269,10 +269,11 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
+  IMP_REQUIRE(a.q_row_stride >= AT_C && a.kv_row_stride >= AT_C, "attention: row strides must be >= 256");
   CUtensorMap tq, tk, tv;
-  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, AT_C, a.q_img_stride, AT_D, AT_BM)) return 3;
-  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
-  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
   AttnKernelParams p;
   p.n_img = a.n_img;
   p.src_offset = a.src_offset;
@@ -435,8 +436,8 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
 int launch_attention_colsum(const AttnColsumArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention_colsum: empty problem");
   CUtensorMap tq, tk;
-  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, AT_C, a.q_img_stride, AT_D, AT_BM)) return 3;
-  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, AT_C, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
   ColsumKernelParams p;
   p.n_img = a.n_img;
   p.src_offset = a.src_offset;

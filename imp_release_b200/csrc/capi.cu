@@ -9,6 +9,9 @@
 
 namespace imp {
 int launch_pool_select(const imp_pool_args& a, cudaStream_t st);
+int launch_scatter_matches(const long long* idx0, const float* ms0, int ld_sub, const int* gids0, const int* gids1,
+                           int ld_ids, const int* cnt0, long long* out_idx, float* out_ms, int ld_out, int batch,
+                           cudaStream_t st);
 int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
                         unsigned long long* col_key, int N0, int N1, int batch, cudaStream_t st);
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
@@ -58,6 +61,12 @@ IMP_API int imp_score_argmax(const float* P, int64_t p_bs, int32_t ldp, float* r
                                   batch, ST(stream));
 }
 IMP_API int imp_pool_select(const imp_pool_args* args, void* stream) { return imp::launch_pool_select(*args, ST(stream)); }
+IMP_API int imp_scatter_matches(const int64_t* idx0, const float* ms0, int32_t ld_sub, const int32_t* gids0, const int32_t* gids1,
+                        int32_t ld_ids, const int32_t* cnt0, int64_t* out_idx, float* out_ms, int32_t ld_out, int32_t batch,
+                        void* stream) {
+  return imp::launch_scatter_matches(reinterpret_cast<const long long*>(idx0), ms0, ld_sub, gids0, gids1, ld_ids, cnt0,
+                                     reinterpret_cast<long long*>(out_idx), out_ms, ld_out, batch, ST(stream));
+}
 IMP_API int imp_gather_rows(const void* in, int64_t in_bs, int32_t row_bytes_in, const int32_t* ids, int32_t ids_ld,
                     const int32_t* cnt, void* out, int64_t out_bs, int32_t row_bytes_out, int32_t copy_bytes,
                     int32_t max_rows, int32_t batch, void* stream) {

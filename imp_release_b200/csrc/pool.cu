@@ -57,12 +57,11 @@ pool_select_kernel(const imp_pool_args a) {
   __shared__ int s_cnt;
   const int b = blockIdx.x;
   const int cnt = a.cnt_in[b];
-  const int nfull = a.n_full[b];
-  const int* ids_in = a.ids_in + (long long)b * a.Nmax;
-  int* ids_out = a.ids_out + (long long)b * a.Nmax;
-  const float* mass = a.mass + (long long)b * a.Nmax;
-  const float* as = a.a_self + (long long)b * a.n_full_ld;
-  const float* ac = a.a_cross + (long long)b * a.n_full_ld;
+  const int* ids_in = a.ids_in + (long long)b * a.ld;
+  int* ids_out = a.ids_out + (long long)b * a.ld;
+  const float* mass = a.mass + (long long)b * a.ld;
+  const float* as = a.a_self + (long long)b * a.ld;
+  const float* ac = a.a_cross + (long long)b * a.ld;
 
   // pids and their count
   int local = 0;
@@ -77,9 +76,9 @@ pool_select_kernel(const imp_pool_args a) {
     }
     return;
   }
-  // normalisation sums over the FULL token set (norm_prob = sum_prob / sum(sum_prob), nets/adgm.py:429-432)
+  // normalisation sums (norm_prob = sum_prob / sum(sum_prob), nets/adgm.py:429-432; pruned tokens contribute 0)
   float ls = 0.f, lc = 0.f;
-  for (int i = threadIdx.x; i < nfull; i += POOL_THREADS) {
+  for (int i = threadIdx.x; i < cnt; i += POOL_THREADS) {
     ls += as[i];
     lc += ac[i];
   }
@@ -94,7 +93,7 @@ pool_select_kernel(const imp_pool_args a) {
     const float* arr = which == 0 ? as : ac;
     const float tot = which == 0 ? tot_s : tot_c;
     for (int i = threadIdx.x; i < n2; i += POOL_THREADS)
-      s_val[i] = (i < cnt && mass[i] >= a.thresh) ? arr[ids_in[i]] / tot : FLT_MAX;
+      s_val[i] = (i < cnt && mass[i] >= a.thresh) ? arr[i] / tot : FLT_MAX;
     __syncthreads();
     bitonic_sort(s_val, n2);
     med[which] = s_val[kth];
@@ -108,7 +107,7 @@ pool_select_kernel(const imp_pool_args a) {
     int keep = 0, g = 0;
     if (i < cnt) {
       g = ids_in[i];
-      keep = (mass[i] >= a.thresh) || (as[g] / tot_s >= med[0]) || (ac[g] / tot_c >= med[1]);
+      keep = (mass[i] >= a.thresh) || (as[i] / tot_s >= med[0]) || (ac[i] / tot_c >= med[1]);
     }
     const unsigned bal = __ballot_sync(0xffffffffu, keep);
     const int w = threadIdx.x >> 5;
@@ -132,9 +131,36 @@ pool_select_kernel(const imp_pool_args a) {
 }
 
 int launch_pool_select(const imp_pool_args& a, cudaStream_t st) {
-  IMP_REQUIRE(a.Nmax <= POOL_MAXN, "pool_select: at most %d tokens per image supported (got %d)", POOL_MAXN, a.Nmax);
+  IMP_REQUIRE(a.ld <= POOL_MAXN, "pool_select: at most %d tokens per image supported (got %d)", POOL_MAXN, a.ld);
   if (a.batch == 0) return 0;
   pool_select_kernel<<<a.batch, POOL_THREADS, 0, st>>>(a);
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace imp
+
+namespace imp {
+
+__global__ void scatter_matches_kernel(const long long* __restrict__ idx0, const float* __restrict__ ms0, int ld_sub,
+                                       const int* __restrict__ gids0, const int* __restrict__ gids1, int ld_ids,
+                                       const int* __restrict__ cnt0, long long* __restrict__ out_idx,
+                                       float* __restrict__ out_ms, int ld_out) {
+  const int b = blockIdx.y;
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= cnt0[b]) return;
+  const int g0 = gids0[(long long)b * ld_ids + r];
+  const long long j = idx0[(long long)b * ld_sub + r];
+  out_ms[(long long)b * ld_out + g0] = ms0[(long long)b * ld_sub + r];
+  if (j >= 0) out_idx[(long long)b * ld_out + g0] = gids1[(long long)b * ld_ids + j];
+}
+
+int launch_scatter_matches(const long long* idx0, const float* ms0, int ld_sub, const int* gids0, const int* gids1,
+                           int ld_ids, const int* cnt0, long long* out_idx, float* out_ms, int ld_out, int batch,
+                           cudaStream_t st) {
+  if (batch == 0 || ld_sub == 0) return 0;
+  scatter_matches_kernel<<<dim3((ld_sub + 255) / 256, batch), 256, 0, st>>>(idx0, ms0, ld_sub, gids0, gids1, ld_ids, cnt0,
+                                                                            out_idx, out_ms, ld_out);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }

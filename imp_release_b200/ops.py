@@ -90,12 +90,20 @@ def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row
     check(_lib.load().imp_gemm(C.byref(g), stream_ptr()), 'imp_gemm')
 
 
+def _p(t):
+    """tensor or raw integer device address"""
+    return t if isinstance(t, int) or t is None else t.data_ptr()
+
+
 def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, shared: bool, lse,
-              out: Planes, q_img_stride: Optional[int] = None, kv_img_stride: Optional[int] = None):
+              out: Planes, q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
+              kv_img_stride: Optional[int] = None):
+    """q/k/v: fp16 tensors or raw device addresses (slices of a fused projection buffer)."""
     a = AttnArgs()
-    a.q, a.k, a.v = ptr(q), ptr(k), ptr(v)
-    a.q_img_stride = q_img_stride if q_img_stride is not None else Nq_max * 256
-    a.kv_img_stride = kv_img_stride if kv_img_stride is not None else Nk_max * 256
+    a.q, a.k, a.v = _p(q), _p(k), _p(v)
+    a.q_row_stride, a.kv_row_stride = q_row_stride, kv_row_stride
+    a.q_img_stride = q_img_stride if q_img_stride is not None else Nq_max * q_row_stride
+    a.kv_img_stride = kv_img_stride if kv_img_stride is not None else Nk_max * kv_row_stride
     a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
     a.nq, a.nk = ptr(nq), ptr(nk)
     a.shared = int(shared)
@@ -105,10 +113,14 @@ def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int,
     check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
 
 
-def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, lse, colsum):
+def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, lse, colsum,
+                     q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
+                     kv_img_stride: Optional[int] = None):
     a = AttnColsumArgs()
-    a.q, a.k = ptr(q), ptr(k)
-    a.q_img_stride, a.kv_img_stride = Nq_max * 256, Nk_max * 256
+    a.q, a.k = _p(q), _p(k)
+    a.q_row_stride, a.kv_row_stride = q_row_stride, kv_row_stride
+    a.q_img_stride = q_img_stride if q_img_stride is not None else Nq_max * q_row_stride
+    a.kv_img_stride = kv_img_stride if kv_img_stride is not None else Nk_max * kv_row_stride
     a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
     a.nq, a.nk = ptr(nq), ptr(nk)
     a.lse, a.colsum = ptr(lse), ptr(colsum)
@@ -213,20 +225,29 @@ def dual_softmax(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, N0: int,
     return P[:, :, :N1 + 1]
 
 
-def pool_select(mass, a_self, a_cross, n_full, ids_in, cnt_in, thresh: float, n_min_tokens: int):
-    batch, Nmax = ids_in.shape
+def pool_select(mass, a_self, a_cross, ids_in, cnt_in, thresh: float, n_min_tokens: int):
+    """All of mass / a_self / a_cross / ids_in are [batch, ld] and indexed by subset position."""
+    batch, ld = ids_in.shape
     dev = ids_in.device
+    assert mass.stride(0) == ld and a_self.stride(0) == ld and a_cross.stride(0) == ld
     ids_out = torch.zeros_like(ids_in)
     cnt_out = torch.zeros(batch, dtype=torch.int32, device=dev)
     changed = torch.zeros(batch, dtype=torch.int32, device=dev)
     a = PoolArgs()
     a.mass, a.a_self, a.a_cross = ptr(mass), ptr(a_self), ptr(a_cross)
-    a.n_full_ld, a.Nmax = a_self.stride(0), Nmax
-    a.n_full, a.ids_in, a.cnt_in = ptr(n_full), ptr(ids_in), ptr(cnt_in)
+    a.ld = ld
+    a.ids_in, a.cnt_in = ptr(ids_in), ptr(cnt_in)
     a.ids_out, a.cnt_out, a.changed = ptr(ids_out), ptr(cnt_out), ptr(changed)
     a.thresh, a.n_min_tokens, a.batch = thresh, n_min_tokens, batch
     check(_lib.load().imp_pool_select(C.byref(a), stream_ptr()), 'imp_pool_select')
     return ids_out, cnt_out, changed
+
+
+def scatter_matches(idx0, ms0, gids0, gids1, cnt0, out_idx, out_ms):
+    batch, ld_sub = idx0.shape
+    check(_lib.load().imp_scatter_matches(ptr(idx0), ptr(ms0), ld_sub, ptr(gids0), ptr(gids1), gids0.stride(0), ptr(cnt0),
+                                          ptr(out_idx), ptr(out_ms), out_idx.stride(0), batch, stream_ptr()),
+          'imp_scatter_matches')
 
 
 def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: torch.Tensor, max_rows: int):

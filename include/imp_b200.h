@@ -60,8 +60,9 @@ IMP_API int imp_gemm(const imp_gemm_args* args, void* stream);
 
 /* ---- multi-head attention core (QK^T softmax PV), nets/layers.py:121-131 and :211-214 ----------------------- */
 typedef struct imp_attn_args {
-  const void *q, *k, *v; /* fp16 [n_img, N*_max, 256], heads contiguous */
-  int64_t q_img_stride, kv_img_stride;
+  const void *q, *k, *v; /* fp16 [n_img, N*_max, (row stride)], 256 used columns, heads contiguous */
+  int64_t q_img_stride, kv_img_stride; /* elements */
+  int32_t q_row_stride, kv_row_stride; /* elements (256 for packed tensors, 768 inside a fused QKV buffer) */
   int32_t n_img, src_offset, Nq_max, Nk_max;
   const int32_t *nq, *nk; /* [n_img] valid rows (NULL -> max) */
   int32_t shared;         /* 1: reuse previous probabilities via lse (SharedAttentionalPropagation) */
@@ -76,6 +77,7 @@ IMP_API int imp_attention(const imp_attn_args* args, void* stream);
 typedef struct imp_attn_colsum_args {
   const void *q, *k;
   int64_t q_img_stride, kv_img_stride;
+  int32_t q_row_stride, kv_row_stride;
   int32_t n_img, src_offset, Nq_max, Nk_max;
   const int32_t *nq, *nk;
   const float* lse;
@@ -142,19 +144,19 @@ IMP_API int imp_score_argmax(const float* P, int64_t p_batch_stride, int32_t ldp
 
 /* ---- EIMP adaptive pooling, nets/adgm.py:463-500 and :552-605 ------------------------------------------------
  * keep = { i : mass_i >= thresh } U { i : a_self_i >= lower_median(a_self[pids]) } U { i : a_cross_i >= ... },
- * evaluated on the current kept subset ids_in[0..cnt_in) (global ids, sorted); writes the new sorted global ids
- * and count.  If cnt_in <= n_min_tokens or no row passes the threshold the subset is copied unchanged and
- * changed[b] = 0.  a_self / a_cross are UN-normalised received-attention sums indexed by GLOBAL id; they are
- * normalised by their full-row sums inside (nets/adgm.py:429-432). */
+ * evaluated on the current kept subset of cnt_in[b] tokens whose global ids are ids_in[b, 0..cnt) (sorted); writes
+ * the new sorted global ids and count.  If cnt_in <= n_min_tokens or no row passes the threshold the subset is
+ * copied unchanged and changed[b] = 0.  mass / a_self / a_cross are indexed by SUBSET POSITION; a_* are the
+ * un-normalised received-attention sums (pruned tokens receive exactly 0 in the reference, so normalising by the
+ * subset total equals nets/adgm.py:429-432). */
 typedef struct imp_pool_args {
-  const float* mass;  /* [batch, Nmax] indexed by subset position */
-  const float *a_self, *a_cross; /* [batch, Nmax] indexed by global id */
-  int32_t n_full_ld;  /* row stride of a_self / a_cross */
-  int32_t Nmax;
-  const int32_t* n_full;  /* [batch] number of tokens of the full image (normalisation length) */
-  const int32_t* ids_in;  /* [batch, Nmax] */
+  const float* mass;             /* [batch, ld] */
+  const float *a_self, *a_cross; /* [batch, ld] */
+  int32_t ld;                    /* row stride of mass / a_self / a_cross / ids */
+  int32_t _pad0;
+  const int32_t* ids_in;  /* [batch, ld] */
   const int32_t* cnt_in;  /* [batch] */
-  int32_t* ids_out;       /* [batch, Nmax] */
+  int32_t* ids_out;       /* [batch, ld] */
   int32_t* cnt_out;       /* [batch] */
   int32_t* changed;       /* [batch] */
   float thresh;
@@ -163,6 +165,13 @@ typedef struct imp_pool_args {
   int32_t _pad;
 } imp_pool_args;
 IMP_API int imp_pool_select(const imp_pool_args* args, void* stream);
+
+/* scatter subset-coordinate matches back to global ids (nets/adgm.py:458-460):
+ *   out_idx[b, gids0[b, r]] = gids1[b, idx0[b, r]] if idx0[b, r] >= 0;  out_ms[b, gids0[b, r]] = ms0[b, r];  r < cnt0[b]
+ * out_idx must be pre-filled with -1 and out_ms with 0. */
+IMP_API int imp_scatter_matches(const int64_t* idx0, const float* ms0, int32_t ld_sub, const int32_t* gids0,
+                        const int32_t* gids1, int32_t ld_ids, const int32_t* cnt0, int64_t* out_idx, float* out_ms,
+                        int32_t ld_out, int32_t batch, void* stream);
 
 /* row gather for compaction: out[b, r, :copy_bytes] = in[b, ids[b, r], :copy_bytes], r < cnt[b] */
 IMP_API int imp_gather_rows(const void* in, int64_t in_batch_stride_bytes, int32_t row_bytes_in, const int32_t* ids,
