@@ -82,7 +82,7 @@ SIGNATURES = {
     'imp_sinkhorn': (C.c_int, [C.POINTER(SinkhornArgs), c_vp]),
     'imp_matches': (C.c_int, [C.POINTER(MatchArgs), c_vp]),
     'imp_dual_softmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
-    'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'imp_pool_select': (C.c_int, [C.POINTER(PoolArgs), c_vp]),
     'imp_scatter_matches': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'imp_gather_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),

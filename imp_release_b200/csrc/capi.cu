@@ -13,7 +13,8 @@ int launch_scatter_matches(const long long* idx0, const float* ms0, int ld_sub, 
                            int ld_ids, const int* cnt0, long long* out_idx, float* out_ms, int ld_out, int batch,
                            cudaStream_t st);
 int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
-                        unsigned long long* col_key, int N0, int N1, int batch, cudaStream_t st);
+                        unsigned long long* col_key, float* row_mass, float* col_mass, int N0, int N1, int batch,
+                        cudaStream_t st);
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
                         int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st);
 }  // namespace imp
@@ -56,9 +57,9 @@ IMP_API int imp_dual_softmax(const float* dist, int64_t d_bs, int32_t ldd, const
   return imp::launch_dual_softmax(dist, d_bs, ldd, bin_score, P, p_bs, ldp, row_lse, col_lse, N0, N1, batch, ST(stream));
 }
 IMP_API int imp_score_argmax(const float* P, int64_t p_bs, int32_t ldp, float* row_max, int32_t* row_arg, uint64_t* col_key,
-                     int32_t N0, int32_t N1, int32_t batch, void* stream) {
-  return imp::launch_score_argmax(P, p_bs, ldp, row_max, row_arg, reinterpret_cast<unsigned long long*>(col_key), N0, N1,
-                                  batch, ST(stream));
+                     float* row_mass, float* col_mass, int32_t N0, int32_t N1, int32_t batch, void* stream) {
+  return imp::launch_score_argmax(P, p_bs, ldp, row_max, row_arg, reinterpret_cast<unsigned long long*>(col_key),
+                                  row_mass, col_mass, N0, N1, batch, ST(stream));
 }
 IMP_API int imp_pool_select(const imp_pool_args* args, void* stream) { return imp::launch_pool_select(*args, ST(stream)); }
 IMP_API int imp_scatter_matches(const int64_t* idx0, const float* ms0, int32_t ld_sub, const int32_t* gids0, const int32_t* gids1,

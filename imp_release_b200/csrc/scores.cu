@@ -15,20 +15,22 @@ __device__ __forceinline__ unsigned long long pack_key(float val, int idx) {
 
 // rows: one warp per row over the non-dustbin block [N0, N1]
 __global__ void row_argmax_kernel(const float* __restrict__ P, long long p_bs, int ldp, float* __restrict__ row_max,
-                                  int* __restrict__ row_arg, int N0, int N1) {
+                                  int* __restrict__ row_arg, float* __restrict__ row_mass, int N0, int N1) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (i >= N0) return;
   const float* row = P + b * p_bs + (long long)i * ldp;
-  float best = -FLT_MAX;
+  float best = -FLT_MAX, mass = 0.f;
   int bj = 0x7fffffff;
   for (int j = lane_id(); j < N1; j += 32) {
     const float v = row[j];
+    mass += v;
     if (v > best) {
       best = v;
       bj = j;
     }
   }
+  mass = warp_sum(mass);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
     const float ob = __shfl_xor_sync(0xffffffffu, best, o);
@@ -41,37 +43,45 @@ __global__ void row_argmax_kernel(const float* __restrict__ P, long long p_bs, i
   if (lane_id() == 0) {
     row_max[(long long)b * N0 + i] = best;
     row_arg[(long long)b * N0 + i] = bj;
+    if (row_mass) row_mass[(long long)b * N0 + i] = mass;
   }
 }
 
 // columns: thread per column over a slab of rows, merged with a packed atomicMax (lowest row wins ties)
 __global__ void col_argmax_kernel(const float* __restrict__ P, long long p_bs, int ldp,
-                                  unsigned long long* __restrict__ col_key, int N0, int N1, int rows_per_slab) {
+                                  unsigned long long* __restrict__ col_key, float* __restrict__ col_mass, int N0,
+                                  int N1, int rows_per_slab) {
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= N1) return;
   const int i0 = blockIdx.y * rows_per_slab;
   const int i1 = min(i0 + rows_per_slab, N0);
-  float best = -FLT_MAX;
+  float best = -FLT_MAX, mass = 0.f;
   int bi = 0;
   for (int i = i0; i < i1; ++i) {
     const float v = P[b * p_bs + (long long)i * ldp + j];
+    mass += v;
     if (v > best) {
       best = v;
       bi = i;
     }
   }
-  if (i1 > i0) atomicMax(col_key + (long long)b * N1 + j, pack_key(fmaxf(best, 0.f), bi));
+  if (i1 > i0) {
+    atomicMax(col_key + (long long)b * N1 + j, pack_key(fmaxf(best, 0.f), bi));
+    if (col_mass) atomicAdd(col_mass + (long long)b * N1 + j, mass);
+  }
 }
 
 int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
-                        unsigned long long* col_key, int N0, int N1, int batch, cudaStream_t st) {
+                        unsigned long long* col_key, float* row_mass, float* col_mass, int N0, int N1, int batch,
+                        cudaStream_t st) {
   if (batch == 0 || N0 == 0 || N1 == 0) return 0;
   IMP_CUDA_OK(cudaMemsetAsync(col_key, 0, (size_t)batch * N1 * sizeof(unsigned long long), st));
-  row_argmax_kernel<<<dim3((N0 + 7) / 8, batch), 256, 0, st>>>(P, p_bs, ldp, row_max, row_arg, N0, N1);
+  if (col_mass) IMP_CUDA_OK(cudaMemsetAsync(col_mass, 0, (size_t)batch * N1 * sizeof(float), st));
+  row_argmax_kernel<<<dim3((N0 + 7) / 8, batch), 256, 0, st>>>(P, p_bs, ldp, row_max, row_arg, row_mass, N0, N1);
   const int slab = 64;
-  col_argmax_kernel<<<dim3((N1 + 127) / 128, (N0 + slab - 1) / slab, batch), 128, 0, st>>>(P, p_bs, ldp, col_key, N0,
-                                                                                           N1, slab);
+  col_argmax_kernel<<<dim3((N1 + 127) / 128, (N0 + slab - 1) / slab, batch), 128, 0, st>>>(P, p_bs, ldp, col_key,
+                                                                                           col_mass, N0, N1, slab);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -1,0 +1,51 @@
+"""DGNNS ("IMP") -- GM with attention sharing (nets/gms.py:15-317)."""
+from __future__ import annotations
+
+import torch
+
+from .gm import GM
+from .layers import SHARING_LAYERS, normalize_keypoints  # noqa: F401
+
+
+class DGNNS(GM):
+    _sharing = SHARING_LAYERS
+
+    def __init__(self, config={}):
+        super().__init__(config=config)
+
+    def produce_matches(self, data, p=0.2, only_last=False, **kwargs):
+        """nets/gms.py:139-258: per iteration self layer, cross layer, then (every iteration or last only)
+        final_proj -> Sinkhorn -> matches.  The reference also returns the four [B,4,N,M] attention maps per
+        iteration ('prob00' ...); no caller reads them and the B200 path never materialises them, so those lists
+        hold ``None`` placeholders (documented deviation)."""
+        desc0, desc1 = data['descriptors0'], data['descriptors1']
+        kpts0, kpts1 = data['keypoints0'], data['keypoints1']
+        if kpts0.shape[1] == 0 or kpts1.shape[1] == 0:
+            return self._empty_result(kpts0, kpts1)
+        nk0, nk1 = self._norm_kpts(data)
+        st = self._begin(desc0, desc1, nk0, nk1, data['scores0'], data['scores1'])
+        eng = self.engine()
+        nI = self.config['n_layers']
+        all_i0, all_m0 = [], []
+        for ni in range(nI):
+            eng.layer(st, 2 * ni)
+            eng.layer(st, 2 * ni + 1)
+            if only_last and ni != nI - 1:
+                continue
+            _, i0, _, m0, _, _ = self._score(st, ni, p, keep_scores=False)
+            all_i0.append(i0); all_m0.append(m0)
+        none = [None] * nI
+        return {'indices0': all_i0, 'mscores0': all_m0, 'prob00': list(none), 'prob01': list(none),
+                'prob11': list(none), 'prob10': list(none)}
+
+    def run(self, data):
+        """nets/gms.py:284-314."""
+        out = self.produce_matches(
+            data={'descriptors0': data['desc1'], 'descriptors1': data['desc2'],
+                  'keypoints0': data['x1'][:, :, :2], 'keypoints1': data['x2'][:, :, :2],
+                  'norm_keypoints0': data['x1'][:, :, :2], 'norm_keypoints1': data['x2'][:, :, :2],
+                  'scores0': data['x1'][:, :, -1], 'scores1': data['x2'][:, :, -1]},
+            p=self.config['match_threshold'], only_last=True)
+        indices0 = out['indices0'][-1][0]
+        index0 = torch.where(indices0 >= 0)[0]
+        return {'index0': index0, 'index1': indices0[index0]}

@@ -201,16 +201,21 @@ def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int
     return i0, i1, m0, m1
 
 
-def score_argmax(P: torch.Tensor, N0: int, N1: int):
-    """Row/col arg-max over P[:, :N0, :N1] for an arbitrary (possibly strided-row) fp32 score tensor."""
+def score_argmax(P: torch.Tensor, N0: int, N1: int, want_mass: bool = False):
+    """Row/col arg-max (and masses) over P[:, :N0, :N1] for an arbitrary (possibly strided-row) fp32 score tensor."""
     batch = P.shape[0]
-    assert P.stride(2) == 1
+    if P.stride(2) != 1:
+        P = P.contiguous()
     dev = P.device
     row_max = torch.empty(batch, N0, dtype=torch.float32, device=dev)
     row_arg = torch.empty(batch, N0, dtype=torch.int32, device=dev)
     col_key = torch.empty(batch, N1, dtype=torch.int64, device=dev)
-    check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key), N0, N1,
-                                       batch, stream_ptr()), 'imp_score_argmax')
+    row_mass = torch.empty(batch, N0, dtype=torch.float32, device=dev) if want_mass else None
+    col_mass = torch.empty(batch, N1, dtype=torch.float32, device=dev) if want_mass else None
+    check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key),
+                                       ptr(row_mass), ptr(col_mass), N0, N1, batch, stream_ptr()), 'imp_score_argmax')
+    if want_mass:
+        return row_max, row_arg, col_key, row_mass, col_mass
     return row_max, row_arg, col_key
 
 

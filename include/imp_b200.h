@@ -138,9 +138,11 @@ IMP_API int imp_matches(const imp_match_args* args, void* stream);
 IMP_API int imp_dual_softmax(const float* dist, int64_t dist_batch_stride, int32_t ldd, const float* bin_score, float* P,
                      int64_t p_batch_stride, int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1,
                      int32_t batch, void* stream);
-/* row / column arg-max of an existing score matrix (compute_matches on caller-provided scores) */
+/* row / column arg-max (and optional masses, may be NULL) of an existing score matrix over P[:, :N0, :N1]
+ * (compute_matches / pool on caller-provided scores) */
 IMP_API int imp_score_argmax(const float* P, int64_t p_batch_stride, int32_t ldp, float* row_max, int32_t* row_arg,
-                     uint64_t* col_key, int32_t N0, int32_t N1, int32_t batch, void* stream);
+                     uint64_t* col_key, float* row_mass, float* col_mass, int32_t N0, int32_t N1, int32_t batch,
+                     void* stream);
 
 /* ---- EIMP adaptive pooling, nets/adgm.py:463-500 and :552-605 ------------------------------------------------
  * keep = { i : mass_i >= thresh } U { i : a_self_i >= lower_median(a_self[pids]) } U { i : a_cross_i >= ... },

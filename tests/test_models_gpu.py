@@ -1,0 +1,77 @@
+"""End-to-end parity (GPU): GM / DGNNS / AdaGMN through the reference-shaped Python API vs the CPU oracle."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from imp_release_b200 import GM, DGNNS, AdaGMN  # noqa: E402
+from oracle import imp_oracle, synth  # noqa: E402
+
+
+def cfg(nl, **kw):
+    c = dict(n_layers=nl, GNN_layers=['self', 'cross'] * nl, norm_fn='in', ac_fn='relu', sinkhorn_iterations=20,
+             with_sinkhorn=True, descriptor_dim=256)
+    c.update(kw)
+    return c
+
+
+def to_cuda(d):
+    return {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()}
+
+
+def compare(out, ref, tol=1e-3):
+    assert len(out['indices0']) == len(ref['indices0'])
+    for ni, (a, b) in enumerate(zip(out['indices0'], ref['indices0'])):
+        assert a.dtype == torch.int64
+        mism = int((a.cpu() != b).sum())
+        assert mism == 0, f'iteration {ni}: {mism} index mismatches'
+    for ni, (a, b) in enumerate(zip(out['mscores0'], ref['mscores0'])):
+        d = float((a.cpu() - b).abs().max())
+        assert d < tol, f'iteration {ni}: mscores differ by {d}'
+
+
+@pytest.mark.parametrize('N0,N1,B', [(512, 512, 1)])
+def test_gm_config1(N0, N1, B):
+    """BASELINE.json configs[0]: GM.forward, N=512, 3 iterations."""
+    c = cfg(3)
+    sd = synth.make_state_dict('GM', 3, seed=5)
+    data = synth.make_pair_batch(seed=0, batch=B, n0=N0, n1=N1)
+    ref = imp_oracle.Oracle('GM', c, sd).forward(data)
+    net = GM(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(to_cuda(data))
+    compare(out, ref)
+    for a, b in zip(out['scores'], ref['scores']):
+        assert a.shape == b.shape
+        assert float((a.cpu()[:, :-1, :-1] - b[:, :-1, :-1]).abs().max()) < 1e-3
+
+
+@pytest.mark.parametrize('N0,N1,B,nl,only_last', [(500, 460, 2, 9, False), (300, 260, 1, 9, True), (1000, 960, 1, 9, False),
+                                                   (700, 900, 1, 15, True)])
+def test_dgnns(N0, N1, B, nl, only_last):
+    c = cfg(nl)
+    sd = synth.make_state_dict('DGNNS', nl, seed=7)
+    data = synth.make_pair_batch(seed=3, batch=B, n0=N0, n1=N1)
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches(data, p=0.2, only_last=only_last)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net.produce_matches(to_cuda(data), p=0.2, only_last=only_last)
+    compare(out, ref)
+
+
+@pytest.mark.parametrize('N0,N1,B,seed', [(500, 460, 2, 7), (1000, 960, 1, 11)])
+def test_adagmn_batched_pruning(N0, N1, B, seed):
+    """BASELINE.json configs[2] shape: EIMP with adaptive pooling (bin_score raised so that pruning happens)."""
+    c = cfg(9, n_min_tokens=256)
+    sd = synth.make_state_dict('AdaGMN', 9, seed=seed, bin_score=6.0)
+    data = synth.make_pair_batch(seed=seed + 1, batch=B, n0=N0, n1=N1)
+    ref = imp_oracle.Oracle('AdaGMN', c, sd).forward(data)
+    net = AdaGMN(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(to_cuda(data))
+    cnt, ids = net._kept
+    kept = cnt.cpu().tolist()
+    assert kept[:B] == ref['kept0'][-1] and kept[B:] == ref['kept1'][-1], (kept, ref['kept0'][-1], ref['kept1'][-1])
+    assert min(kept) < min(N0, N1), 'test vector must actually prune'
+    compare(out, ref)
+    assert out['scores'][0].shape == ref['scores'][0].shape

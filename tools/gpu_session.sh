@@ -6,7 +6,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.used --for
 for t in "$@"; do
   name=$(echo "$t" | tr '/:[], ' '______')
   echo "=== $t" | tee -a gpurun_out/session.log
-  timeout 300 python -m pytest "$t" -m gpu -q --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
+  timeout 600 python -m pytest "$t" -m gpu -q --no-header -p no:cacheprovider > "gpurun_out/$name.log" 2>&1
   rc=$?
   echo "rc=$rc" | tee -a gpurun_out/session.log
   tail -n 25 "gpurun_out/$name.log" | tee -a gpurun_out/session.log
