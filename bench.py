@@ -1,0 +1,327 @@
+#!/usr/bin/env python
+"""bench.py -- image-pairs/sec of the IMP matching hot path on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host cores (oracle port)
+
+Workload (BASELINE.json configs[1]): DGNNS ("IMP"), 9 iterations, batch of 64 synthetic pairs, N = 2000 keypoints,
+D = 256, ``model(data)`` = Sinkhorn + matches at every iteration.  A step = one such forward on one batch.
+  value : pairs/s with the inputs already resident in HBM, timed with CUDA events, max over ranks
+  e2e   : the same forward through the public API with pinned HOST inputs (H2D inside the timed region) and a
+          D2H read of the last iteration's matches (plus, for N > 1, the NCCL gather of all ranks' matches)
+Each rank works on its own 64 pairs (weak scaling, replicas + one gather).
+Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_KPTS, N_ITERS, BATCH = 2000, 9, 64
+METRIC = 'image-pairs/sec at N=2000 kpts, 9 iters (IMP / DGNNS.forward, Sinkhorn every iteration)'
+
+
+def model_config(n_layers=N_ITERS):
+    return dict(n_layers=n_layers, GNN_layers=['self', 'cross'] * n_layers, norm_fn='in', ac_fn='relu',
+                sinkhorn_iterations=20, with_sinkhorn=True, descriptor_dim=256, n_min_tokens=256)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, 'measured (MEASURED_PEAKS.json)'
+    return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}, 'fallback (B200_PROFILING.md)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.idx), f'--query-gpu={self.Q}',
+                                          '--format=csv,noheader,nounits', '-lms', '100'], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        # median of the samples taken under load (upper half: idle samples at the edges are lower)
+        under = sm[len(sm) // 2:] if sm else []
+        med = under[len(under) // 2] if under else None
+        return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def attention_flops_per_pair(n, iters):
+    from oracle.imp_oracle import attention_flops
+    return attention_flops(n, n, iters)
+
+
+# ----------------------------------------------------------------------------------------------- CPU legs
+def cpu_reference_step(n_pairs=1, n=N_KPTS, iters=N_ITERS, repeats=1, seed=1):
+    """The reference algorithm (oracle port of nets/gms.py:139-258) on the host cores: seconds per forward."""
+    from oracle import imp_oracle, synth
+    cfg = model_config(iters)
+    sd = synth.make_state_dict('DGNNS', iters, seed=7)
+    data = synth.make_pair_batch(seed=seed, batch=n_pairs, n0=n, n1=n)
+    orc = imp_oracle.Oracle('DGNNS', cfg, sd)
+    best = float('inf')
+    with torch.no_grad():
+        for _ in range(repeats):
+            t = time.perf_counter()
+            orc.forward(data)
+            best = min(best, time.perf_counter() - t)
+    return best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count() or 1)
+    cores = torch.get_num_threads()
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step()
+    times = [cpu_reference_step() for _ in range(max(1, min(args.steps, 5)))]
+    ms = 1e3 * sum(times) / len(times)
+    value = 1.0 / (ms / 1e3)
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
+        'steps': len(times), 'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': f'DGNNS.forward 9 iters, N={N_KPTS}, D=256; each step = a bounded sample of 1 pair of the '
+                               f'{BATCH}-pair batch (per-pair CPU time is flat in batch size, BASELINE.md section 3)'},
+        'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
+                         'sample': '1 pair per step, oracle/imp_oracle.py (torch CPU fp32, all host threads)'},
+        'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+def run_gpu(args, rank, world, local_rank):
+    import torch.distributed as dist
+    from imp_release_b200 import DGNNS, ops
+    from oracle import synth
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    cfg = model_config()
+    net = DGNNS(cfg)
+    net.load_state_dict(synth.make_state_dict('DGNNS', N_ITERS, seed=7), strict=True)
+    net = net.to(dev).eval()
+
+    host = synth.make_pair_batch(seed=1 + rank, batch=BATCH, n0=N_KPTS, n1=N_KPTS)
+    keys = ['descriptors0', 'descriptors1', 'keypoints0', 'keypoints1', 'scores0', 'scores1']
+    pinned = {k: host[k].pin_memory() for k in keys}
+    shapes = {'image0': host['image0'], 'image1': host['image1']}      # only .shape is read (nets/gms.py:162-164)
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    resident.update(shapes)
+    h2d = sum(v.numel() * v.element_size() for v in pinned.values())
+    n_pairs_total = BATCH * world
+
+    def step_resident():
+        with torch.no_grad():
+            return net(resident)
+
+    out_i = torch.empty(BATCH, N_KPTS, dtype=torch.int64).pin_memory()
+    out_s = torch.empty(BATCH, N_KPTS, dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        with torch.no_grad():
+            d = {k: v.to(dev, non_blocking=True) for k, v in pinned.items()}
+            d.update(shapes)
+            out = net(d)
+            i0, s0 = out['indices0'][-1], out['mscores0'][-1]
+            if world > 1:
+                # fixed-stride gather of every rank's matches to rank 0 (24 KB per pair), cf. shard.gather_matches
+                gi = [torch.empty_like(i0) for _ in range(world)] if rank == 0 else None
+                gs = [torch.empty_like(s0) for _ in range(world)] if rank == 0 else None
+                dist.gather(i0, gi, dst=0)
+                dist.gather(s0, gs, dst=0)
+            out_i.copy_(i0, non_blocking=True)
+            out_s.copy_(s0, non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms) / steps, wall
+
+    for _ in range(args.warmup):
+        step_resident()
+    if args.ncu:
+        step_resident()
+        torch.cuda.synchronize()
+        return
+    step_e2e()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = ops.LAUNCHES
+    ms_dev, _ = timed(step_resident, args.steps)
+    launches = ops.LAUNCHES - launches0
+    clocks = sampler.stop()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    # per-kernel breakdown with CUDA events on the launching stream (separate pass so `value` is unperturbed)
+    ops.PROFILE = {}
+    barrier()
+    for _ in range(max(1, min(args.steps, 3))):
+        step_resident()
+    torch.cuda.synchronize()
+    prof = {}
+    for name, spans in ops.PROFILE.items():
+        tot = sum(a.elapsed_time(b) for a, b, _ in spans)
+        work = sum(w for _, _, w in spans)
+        prof[name] = (tot, len(spans), work)
+    ops.PROFILE = None
+    total_prof = sum(v[0] for v in prof.values()) or 1.0
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_src = measured_peaks()
+    value = n_pairs_total / (ms_dev / 1e3)
+    e2e_value = n_pairs_total / (ms_e2e / 1e3)
+    top = max(prof.items(), key=lambda kv: kv[1][0])[0]
+    kernels = {k: {'ms_per_step_share': round(v[0] / total_prof, 4), 'avg_ms': round(v[0] / v[1], 4), 'calls': v[1]}
+               for k, v in sorted(prof.items(), key=lambda kv: -kv[1][0])}
+
+    def roof(name):
+        tot, n, work = prof[name]
+        avg_s = tot / n / 1e3
+        if name.startswith('sinkhorn'):
+            ach = work / n / avg_s / 1e9
+            return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+                    'frac': ach / peaks['hbm_gbs'], 'traffic': None,
+                    'note': 'algorithmic bytes = (2 sweeps/iteration * 20 + init + final) * matrix bytes; one launch group '
+                            '= one full Sinkhorn (22 kernels)'}
+        pk = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
+        ach = work / n / avg_s / 1e12
+        return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk,
+                'traffic': None, 'note': 'algorithmic FLOPs / launch (SURVEY.md 8(d)) over the CUDA-event launch time; '
+                                         'peak = sustained dense bf16/fp16 cuBLAS of ' + peak_src}
+    roofline = roof(top)
+    extra = {k: roof(k) for k in ('attention', 'attention_shared', 'sinkhorn') if k in prof and k != top}
+    tr = os.path.join(ROOT, 'profiles', 'traffic.json')
+    if os.path.isfile(tr):
+        with open(tr) as f:
+            t = json.load(f)
+        for r in [roofline] + list(extra.values()):
+            if r['kernel'] in t:
+                r['traffic'] = t[r['kernel']]
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_s = cpu_reference_step(repeats=2) if world == 1 and not args.no_cpu_baseline else None
+    cpu_baseline = None
+    if cpu_s is not None:
+        cpu_baseline = {'value': 1.0 / cpu_s, 'unit': 'pairs/s', 'cores': torch.get_num_threads(), 'kind': 'port',
+                        'sample': 'best of 2 forwards of 1 pair (N=2000, 9 iters) with oracle/imp_oracle.py on all host '
+                                  'threads; per-pair CPU time is flat in batch size'}
+    att = attention_flops_per_pair(N_KPTS, N_ITERS)
+    line = {
+        'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+        'dtype': 'f16x3 split (fp32-equivalent) projections/scores, f16 attention operands, f32 accumulate/softmax/Sinkhorn',
+        'data': 'synthetic',
+        'config': {'workload': f'BASELINE.json configs[1]: DGNNS.forward (IMP), batch={BATCH} pairs/GPU, N={N_KPTS}, D=256, '
+                               f'{N_ITERS} iters, Sinkhorn(20)+matches every iteration',
+                   'l2': 'per-step inputs (264 MB) and working set (>5 GB) exceed the 126 MB L2; no explicit flush',
+                   'parallelism': f'replicas x{world}, pairs sharded by rank, one gather of matches'},
+        'clocks': clocks,
+        'e2e': {'value': e2e_value, 'unit': 'pairs/s', 'ms_per_step': ms_e2e, 'h2d_bytes_per_step': h2d,
+                'd2h_bytes_per_step': out_i.numel() * 8 + out_s.numel() * 4},
+        'gpu_launches': launches,
+        'roofline': roofline,
+        'roofline_other': extra,
+        'attention_tflops_whole_step': att * n_pairs_total / (ms_dev / 1e3) / 1e12,
+        'kernels': kernels,
+        'cpu_baseline': cpu_baseline,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--ncu', action='store_true', help='profiling aid: 1 warm-up + 1 resident step, nothing else (numbers invalid)')
+    args = ap.parse_args()
+    rank = int(os.environ.get('RANK', '0'))
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if args.impl == 'reference':
+        return run_reference(args, rank, world)
+    if args.warmup < 3 and not args.ncu:
+        args.warmup = 3
+    if not torch.cuda.is_available():
+        raise SystemExit('bench.py: no CUDA device (the B200 path has no CPU fallback; use --impl reference for the CPU arm)')
+    run_gpu(args, rank, world, local_rank)
+
+
+if __name__ == '__main__':
+    main()

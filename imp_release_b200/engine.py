@@ -189,9 +189,12 @@ class Engine:
             else:
                 ops.gather_rows(src3[:, :, 2 * D:], st.key_ids, st.key_cnt, dst3[:, :, D:], Np)  # new V, same key set
             k_ptr, v_ptr, kv_rs, nk = kvc.data_ptr(), kvc.data_ptr() + 2 * D, 2 * D, st.key_cnt
+        pairs_qk = st.B * (2 * st.N0 * st.N1 if cross else st.N0 * st.N0 + st.N1 * st.N1)
+        ops.ATTN_WORK_HINT = (2.0 if L['sharing'] else 4.0) * D * pairs_qk   # algorithmic FLOPs
         ops.attention(base, k_ptr, v_ptr, n_img=n_img, src_offset=(st.B if cross else 0), Nq_max=Np, Nk_max=Np,
                       nq=st.n_tok, nk=nk, shared=L['sharing'], lse=lse, out=ws.A, q_row_stride=3 * D,
                       kv_row_stride=kv_rs)
+        ops.ATTN_WORK_HINT = None
         ops.gemm(ws.X, L['W0'], M=T, N=2 * D, K1=D, K2=D, a2=ws.A, a_row_stride=D, a2_row_stride=D, b_row_stride=2 * D,
                  bias=L['b0'], out_mode=ops.OUT_F32, out0=ws.H, out_row_stride=2 * D)
         ops.instnorm_relu(ws.H, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=ws.Hn)

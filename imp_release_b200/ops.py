@@ -12,6 +12,35 @@ from ._lib import (AttnArgs, AttnColsumArgs, GemmArgs, MatchArgs, PoolArgs, Sink
 
 OUT_F32, OUT_F16, OUT_SPLIT, OUT_SPLIT_RESID = 0, 1, 2, 3
 
+# Launch accounting (bench.py): LAUNCHES counts kernels of libimp_b200.so enqueued through this module;
+# when PROFILE is a dict, every wrapper brackets its launches with CUDA events on the current stream
+# (name -> list of (start, end, work) tuples; `work` = algorithmic FLOPs or bytes of that call).
+LAUNCHES = 0
+PROFILE = None
+ATTN_WORK_HINT = None   # set by callers that know the true (ragged / pruned) sizes
+
+
+class _Span:
+    __slots__ = ('name', 'n', 'work', 'ev')
+
+    def __init__(self, name: str, n_kernels: int, work: float = 0.0):
+        self.name, self.n, self.work, self.ev = name, n_kernels, work, None
+
+    def __enter__(self):
+        global LAUNCHES
+        LAUNCHES += self.n
+        if PROFILE is not None:
+            self.ev = torch.cuda.Event(enable_timing=True)
+            self.ev.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.ev is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            PROFILE.setdefault(self.name, []).append((self.ev, end, self.work))
+        return False
+
 
 def _require_cuda(t: torch.Tensor):
     if not t.is_cuda:
@@ -47,13 +76,15 @@ def split_planes(x: torch.Tensor, out: Optional[Planes] = None, addend: Optional
         addend = addend.contiguous()
     if out is None:
         out = Planes.empty(x.shape, x.device)
-    check(_lib.load().imp_split_planes(ptr(x), ptr(addend), ptr(out.hi), ptr(out.lo), x.numel(), stream_ptr()),
-          'imp_split_planes')
+    with _Span('split_planes', 1, 8.0 * x.numel() * (2 if addend is not None else 1.5)):
+        check(_lib.load().imp_split_planes(ptr(x), ptr(addend), ptr(out.hi), ptr(out.lo), x.numel(), stream_ptr()),
+              'imp_split_planes')
     return out
 
 
 def merge_planes(p: Planes, out: torch.Tensor) -> torch.Tensor:
-    check(_lib.load().imp_merge_planes(ptr(p.hi), ptr(p.lo), ptr(out), p.hi.numel(), stream_ptr()), 'imp_merge_planes')
+    with _Span('merge_planes', 1):
+        check(_lib.load().imp_merge_planes(ptr(p.hi), ptr(p.lo), ptr(out), p.hi.numel(), stream_ptr()), 'imp_merge_planes')
     return out
 
 
@@ -87,7 +118,8 @@ def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row
     if res is not None:
         g.res_hi = res.hi.data_ptr() + out_offset * esz
         g.res_lo = res.lo.data_ptr() + out_offset * esz
-    check(_lib.load().imp_gemm(C.byref(g), stream_ptr()), 'imp_gemm')
+    with _Span(f'gemm_n{N}_k{K1 + K2}' + ('_b' if b_batched else ''), 1, 2.0 * M * N * (K1 + K2) * batch):
+        check(_lib.load().imp_gemm(C.byref(g), stream_ptr()), 'imp_gemm')
 
 
 def _p(t):
@@ -98,7 +130,9 @@ def _p(t):
 def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, shared: bool, lse,
               out: Planes, q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
               kv_img_stride: Optional[int] = None):
-    """q/k/v: fp16 tensors or raw device addresses (slices of a fused projection buffer)."""
+    """q/k/v: fp16 tensors or raw device addresses (slices of a fused projection buffer).
+    ``work_hint``: algorithmic FLOPs of this call (QK^T + PV = 4*d per score element), for the profiler only."""
+    attn_work = ATTN_WORK_HINT if ATTN_WORK_HINT is not None else 4.0 * 64 * 4 * n_img * Nq_max * Nk_max
     a = AttnArgs()
     a.q, a.k, a.v = _p(q), _p(k), _p(v)
     a.q_row_stride, a.kv_row_stride = q_row_stride, kv_row_stride
@@ -110,7 +144,8 @@ def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int,
     a.lse = ptr(lse)
     a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
     a.out_img_stride = Nq_max * 256
-    check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
+    with _Span('attention_shared' if shared else 'attention', 1, attn_work):
+        check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
 
 
 def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, lse, colsum,
@@ -124,26 +159,30 @@ def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: 
     a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
     a.nq, a.nk = ptr(nq), ptr(nk)
     a.lse, a.colsum = ptr(lse), ptr(colsum)
-    check(_lib.load().imp_attention_colsum(C.byref(a), stream_ptr()), 'imp_attention_colsum')
+    with _Span('attention_colsum', 1, 2.0 * 64 * 4 * n_img * Nq_max * Nk_max):
+        check(_lib.load().imp_attention_colsum(C.byref(a), stream_ptr()), 'imp_attention_colsum')
 
 
 def instnorm_relu(H: torch.Tensor, *, batch: int, Nmax: int, C_: int, ns=None, eps: float = 1e-3, relu: bool = True,
                   out: Optional[Planes] = None, out_f32: Optional[torch.Tensor] = None):
     """H [batch, Nmax, C] fp32 contiguous -> planes / fp32 of the same logical shape."""
-    check(_lib.load().imp_instnorm_relu(ptr(H), Nmax * C_, C_, ptr(ns), Nmax, C_, batch, eps, int(relu),
-                                        ptr(out.hi) if out is not None else None,
-                                        ptr(out.lo) if out is not None else None, ptr(out_f32), Nmax * C_, C_,
-                                        stream_ptr()), 'imp_instnorm_relu')
+    with _Span(f'instnorm_c{C_}', 1, 8.0 * batch * Nmax * C_):
+        check(_lib.load().imp_instnorm_relu(ptr(H), Nmax * C_, C_, ptr(ns), Nmax, C_, batch, eps, int(relu),
+                                            ptr(out.hi) if out is not None else None,
+                                            ptr(out.lo) if out is not None else None, ptr(out_f32), Nmax * C_, C_,
+                                            stream_ptr()), 'imp_instnorm_relu')
 
 
 def kenc_input(norm_kpts: torch.Tensor, scores: torch.Tensor, out: torch.Tensor):
-    check(_lib.load().imp_kenc_input(ptr(norm_kpts), ptr(scores), ptr(out), scores.numel(), stream_ptr()),
-          'imp_kenc_input')
+    with _Span('kenc_input', 1):
+        check(_lib.load().imp_kenc_input(ptr(norm_kpts), ptr(scores), ptr(out), scores.numel(), stream_ptr()),
+              'imp_kenc_input')
 
 
 def small_linear(X, ldx, W, bias, Y, ldy, rows, cin, cout):
-    check(_lib.load().imp_small_linear(ptr(X), ldx, ptr(W), ptr(bias), ptr(Y), ldy, rows, cin, cout, stream_ptr()),
-          'imp_small_linear')
+    with _Span('small_linear', 1, 2.0 * rows * cin * cout):
+        check(_lib.load().imp_small_linear(ptr(X), ldx, ptr(W), ptr(bias), ptr(Y), ldy, rows, cin, cout, stream_ptr()),
+              'imp_small_linear')
 
 
 class SinkhornWorkspace:
@@ -180,7 +219,10 @@ def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, 
     a.row_mass, a.col_mass = ptr(ws.row_mass), ptr(ws.col_mass)
     a.n0s, a.n1s = ptr(n0s), ptr(n1s)
     a.N0max, a.N1max, a.batch = ws.N0max, ws.N1max, ws.batch
-    check(_lib.load().imp_sinkhorn(C.byref(a), stream_ptr()), 'imp_sinkhorn')
+    mat_bytes = 4.0 * ws.batch * (ws.N0max + 1) * (ws.N1max + 1)
+    # algorithmic traffic: 2 sweeps per iteration + init (read dist, write p) + final (read, write)
+    with _Span('sinkhorn', 2 + max(iters - 1, 0), mat_bytes * (2 * iters + 4)):
+        check(_lib.load().imp_sinkhorn(C.byref(a), stream_ptr()), 'imp_sinkhorn')
 
 
 def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int, batch: int, n0s=None, n1s=None,
@@ -197,7 +239,8 @@ def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int
     m.n0s, m.n1s = ptr(n0s), ptr(n1s)
     m.N0max, m.N1max, m.batch = N0max, N1max, batch
     m.out0_batch_stride, m.out1_batch_stride = N0max, N1max
-    check(_lib.load().imp_matches(C.byref(m), stream_ptr()), 'imp_matches')
+    with _Span('matches', 1):
+        check(_lib.load().imp_matches(C.byref(m), stream_ptr()), 'imp_matches')
     return i0, i1, m0, m1
 
 
@@ -212,8 +255,9 @@ def score_argmax(P: torch.Tensor, N0: int, N1: int, want_mass: bool = False):
     col_key = torch.empty(batch, N1, dtype=torch.int64, device=dev)
     row_mass = torch.empty(batch, N0, dtype=torch.float32, device=dev) if want_mass else None
     col_mass = torch.empty(batch, N1, dtype=torch.float32, device=dev) if want_mass else None
-    check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key),
-                                       ptr(row_mass), ptr(col_mass), N0, N1, batch, stream_ptr()), 'imp_score_argmax')
+    with _Span('score_argmax', 2):
+        check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key),
+                                           ptr(row_mass), ptr(col_mass), N0, N1, batch, stream_ptr()), 'imp_score_argmax')
     if want_mass:
         return row_max, row_arg, col_key, row_mass, col_mass
     return row_max, row_arg, col_key
@@ -225,8 +269,9 @@ def dual_softmax(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, N0: int,
     P = torch.empty(batch, N0 + 1, ldp, dtype=torch.float32, device=dev)
     row_lse = torch.empty(batch, N0 + 1, dtype=torch.float32, device=dev)
     col_lse = torch.empty(batch, N1 + 1, dtype=torch.float32, device=dev)
-    check(_lib.load().imp_dual_softmax(ptr(dist), N0 * ldd, ldd, ptr(bin_score), ptr(P), (N0 + 1) * ldp, ldp,
-                                       ptr(row_lse), ptr(col_lse), N0, N1, batch, stream_ptr()), 'imp_dual_softmax')
+    with _Span('dual_softmax', 3):
+        check(_lib.load().imp_dual_softmax(ptr(dist), N0 * ldd, ldd, ptr(bin_score), ptr(P), (N0 + 1) * ldp, ldp,
+                                           ptr(row_lse), ptr(col_lse), N0, N1, batch, stream_ptr()), 'imp_dual_softmax')
     return P[:, :, :N1 + 1]
 
 
@@ -244,15 +289,17 @@ def pool_select(mass, a_self, a_cross, ids_in, cnt_in, thresh: float, n_min_toke
     a.ids_in, a.cnt_in = ptr(ids_in), ptr(cnt_in)
     a.ids_out, a.cnt_out, a.changed = ptr(ids_out), ptr(cnt_out), ptr(changed)
     a.thresh, a.n_min_tokens, a.batch = thresh, n_min_tokens, batch
-    check(_lib.load().imp_pool_select(C.byref(a), stream_ptr()), 'imp_pool_select')
+    with _Span('pool_select', 1):
+        check(_lib.load().imp_pool_select(C.byref(a), stream_ptr()), 'imp_pool_select')
     return ids_out, cnt_out, changed
 
 
 def scatter_matches(idx0, ms0, gids0, gids1, cnt0, out_idx, out_ms):
     batch, ld_sub = idx0.shape
-    check(_lib.load().imp_scatter_matches(ptr(idx0), ptr(ms0), ld_sub, ptr(gids0), ptr(gids1), gids0.stride(0), ptr(cnt0),
-                                          ptr(out_idx), ptr(out_ms), out_idx.stride(0), batch, stream_ptr()),
-          'imp_scatter_matches')
+    with _Span('scatter_matches', 1):
+        check(_lib.load().imp_scatter_matches(ptr(idx0), ptr(ms0), ld_sub, ptr(gids0), ptr(gids1), gids0.stride(0), ptr(cnt0),
+                                              ptr(out_idx), ptr(out_ms), out_idx.stride(0), batch, stream_ptr()),
+              'imp_scatter_matches')
 
 
 def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: torch.Tensor, max_rows: int):
@@ -261,6 +308,7 @@ def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: to
     rb_in = src.stride(1) * src.element_size()
     rb_out = out.stride(1) * out.element_size()
     copy = src.shape[2] * src.element_size()
-    check(_lib.load().imp_gather_rows(ptr(src), src.stride(0) * src.element_size(), rb_in, ptr(ids), ids.stride(0),
-                                      ptr(cnt), ptr(out), out.stride(0) * out.element_size(), rb_out, copy, max_rows,
-                                      batch, stream_ptr()), 'imp_gather_rows')
+    with _Span('gather_rows', 1):
+        check(_lib.load().imp_gather_rows(ptr(src), src.stride(0) * src.element_size(), rb_in, ptr(ids), ids.stride(0),
+                                          ptr(cnt), ptr(out), out.stride(0) * out.element_size(), rb_out, copy, max_rows,
+                                          batch, stream_ptr()), 'imp_gather_rows')

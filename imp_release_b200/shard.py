@@ -1,0 +1,56 @@
+"""Multi-GPU evaluation harness: image pairs are independent, so rank r of W processes (one per
+B200) takes pairs r, r+W, ... with a full model replica; the only exchange is one gather of fixed-stride match
+results (indices + scores) to rank 0.  No collective inside an iteration.  Works with any torch.distributed backend
+(NCCL over NVLink on the B200 box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_pairs: int, rank: int, world: int) -> List[int]:
+    """Rank-strided partition: pair i goes to rank i % world."""
+    return list(range(rank, n_pairs, world))
+
+
+def gather_matches(indices0: torch.Tensor, mscores0: torch.Tensor, n_pairs: int, rank: int, world: int,
+                   n_max: int) -> Optional[Tuple[torch.Tensor, torch.Tensor]]:
+    """indices0 [local, n_max] int64 (-1 padded), mscores0 [local, n_max] fp32 for this rank's pairs in shard order.
+    Returns ([n_pairs, n_max], [n_pairs, n_max]) in GLOBAL pair order on rank 0, None elsewhere."""
+    local_max = (n_pairs + world - 1) // world
+    dev = indices0.device
+    pad_i = torch.full((local_max, n_max), -1, dtype=torch.int64, device=dev)
+    pad_s = torch.zeros(local_max, n_max, dtype=torch.float32, device=dev)
+    pad_i[:indices0.shape[0]] = indices0
+    pad_s[:mscores0.shape[0]] = mscores0
+    if world == 1 or not dist.is_initialized():
+        return pad_i[:n_pairs], pad_s[:n_pairs]
+    out_i = [torch.empty_like(pad_i) for _ in range(world)] if rank == 0 else None
+    out_s = [torch.empty_like(pad_s) for _ in range(world)] if rank == 0 else None
+    dist.gather(pad_i, out_i, dst=0)
+    dist.gather(pad_s, out_s, dst=0)
+    if rank != 0:
+        return None
+    full_i = torch.full((n_pairs, n_max), -1, dtype=torch.int64, device=dev)
+    full_s = torch.zeros(n_pairs, n_max, dtype=torch.float32, device=dev)
+    for r in range(world):
+        ids = shard_indices(n_pairs, r, world)
+        if ids:
+            full_i[ids] = out_i[r][:len(ids)]
+            full_s[ids] = out_s[r][:len(ids)]
+    return full_i, full_s
+
+
+def match_sharded(match_fn: Callable[[Sequence[int]], Tuple[torch.Tensor, torch.Tensor]], n_pairs: int, n_max: int,
+                  rank: int, world: int):
+    """Run ``match_fn(pair_ids) -> (indices0 [len, n_max], mscores0 [len, n_max])`` on this rank's shard and gather."""
+    ids = shard_indices(n_pairs, rank, world)
+    if ids:
+        i0, s0 = match_fn(ids)
+    else:
+        dev = torch.device('cuda', torch.cuda.current_device()) if torch.cuda.is_available() else torch.device('cpu')
+        i0 = torch.empty(0, n_max, dtype=torch.int64, device=dev)
+        s0 = torch.empty(0, n_max, dtype=torch.float32, device=dev)
+    return gather_matches(i0, s0, n_pairs, rank, world, n_max)
