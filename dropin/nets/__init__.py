@@ -1,0 +1,9 @@
+"""Drop-in `nets` package: put this directory in front of the reference tree on sys.path and the reference's
+eval/eval_imp.py / eval/matching.py import the B200 implementation instead of its own nets/*.py
+(INTEGRATION.md).  Pure re-exports; the implementation lives in imp_release_b200."""
+import os
+import sys
+
+_repo = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+if _repo not in sys.path:
+    sys.path.insert(0, _repo)

@@ -1,0 +1,130 @@
+"""GPU: the CUDA path (through the reference-shaped Python API -> C ABI) against the committed outputs of the
+unmodified reference (tests/golden/reference_outputs.npz).  Indices bit-exact, scores within 1e-3."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from imp_release_b200 import GM, DGNNS, AdaGMN, normalize_keypoints  # noqa: E402
+from oracle import synth  # noqa: E402
+from tests.golden.make_golden import CASES, cfg  # noqa: E402
+
+G = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_outputs.npz'))
+CLS = {'GM': GM, 'DGNNS': DGNNS, 'AdaGMN': AdaGMN}
+
+
+def cuda(d):
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.parametrize('name', list(CASES))
+def test_models_match_reference_outputs(name):
+    kind, nl, wseed, bin_score, dseed, B, n0, n1, kw = CASES[name]
+    sd = synth.make_state_dict(kind, nl, seed=wseed, bin_score=bin_score)
+    data = synth.make_pair_batch(seed=dseed, batch=B, n0=n0, n1=n1)
+    net = CLS[kind](cfg(nl))
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net.produce_matches(cuda(data), **kw) if kw else net(cuda(data))
+    i0 = torch.stack(out['indices0']).cpu().numpy()
+    m0 = torch.stack(out['mscores0']).cpu().numpy()
+    assert i0.dtype == np.int64
+    assert np.array_equal(i0, G[f'{name}/indices0']), f'{(i0 != G[f"{name}/indices0"]).sum()} index mismatches'
+    assert np.abs(m0 - G[f'{name}/mscores0']).max() < 1e-3
+    if f'{name}/scores_last_shape' in G:
+        s = out['scores'][-1]
+        assert list(s.shape) == G[f'{name}/scores_last_shape'].tolist()
+        ref = G[f'{name}/scores_last_rowsum']
+        assert np.abs(s.sum(-1).cpu().numpy() - ref).max() / np.abs(ref).max() < 1e-4
+        d = min(s.shape[1:])
+        assert np.abs(s[:, torch.arange(d), torch.arange(d)].cpu().numpy() - G[f'{name}/scores_last_diag']).max() < 1e-3 * max(1.0, float(np.abs(G[f'{name}/scores_last_diag']).max()))
+
+
+@pytest.mark.parametrize('kind,bin_score', [('DGNNS', 1.0), ('AdaGMN', 6.0)])
+def test_layer_api_matches_reference_outputs(kind, bin_score):
+    """The call sequence of eval/matching.py:45-61 (+ pool, :254) against the reference's own results."""
+    nl, n0, n1 = 9, 330, 300
+    tag = f'layerapi_{kind.lower()}'
+    sd = synth.make_state_dict(kind, nl, seed=11, bin_score=bin_score)
+    data = cuda(synth.make_pair_batch(seed=12, batch=1, n0=n0, n1=n1))
+    m = CLS[kind](cfg(nl))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        nk0 = normalize_keypoints(data['keypoints0'], data['image0'].shape)
+        nk1 = normalize_keypoints(data['keypoints1'], data['image1'].shape)
+        e0, e1 = m.encode_keypoint(norm_kpts0=nk0, norm_kpts1=nk1, scores0=data['scores0'], scores1=data['scores1'])
+        d0 = data['descriptors0'].transpose(1, 2) + e0
+        d1 = data['descriptors1'].transpose(1, 2) + e1
+        for it in range(4):
+            d0, d1 = m.forward_one_layer(desc0=d0, desc1=d1, M0=None, M1=None, layer_i=2 * it)
+            d0, d1 = m.forward_one_layer(desc0=d0, desc1=d1, M0=None, M1=None, layer_i=2 * it + 1)
+        assert d0.shape == (1, 256, n0) and d1.shape == (1, 256, n1)
+        dist = m.compute_distance(desc0=d0, desc1=d1, layer_id=3)
+        score = m.compute_score(dist=dist, dustbin=m.bin_score, iteration=m.sinkhorn_iterations)
+        i0, i1, m0, m1 = m.compute_matches(scores=score, p=0.1)
+        assert score.shape == (1, n0 + 1, n1 + 1) and isinstance(score.cpu().numpy()[0, :-1, :-1], np.ndarray)
+    assert np.abs(d0.cpu().numpy()[:, :, ::7] - G[f'{tag}/desc0_it3']).max() < 2e-3
+    assert np.array_equal(i0.cpu().numpy(), G[f'{tag}/indices0']) and np.array_equal(i1.cpu().numpy(), G[f'{tag}/indices1'])
+    assert np.abs(m0.cpu().numpy() - G[f'{tag}/mscores0']).max() < 1e-3
+    assert np.abs(m1.cpu().numpy() - G[f'{tag}/mscores1']).max() < 1e-3
+    # re-thresholding an existing score tensor (eval/matching.py:119)
+    j0, _, _, _ = m.compute_matches(scores=score.clone(), p=0.1)
+    assert torch.equal(j0, i0)
+    if kind == 'AdaGMN':
+        ids0, ids1 = m.pool(pred_score=score, prob00=m.self_prob0, prob01=m.cross_prob0, prob11=m.self_prob1,
+                            prob10=m.cross_prob1, mscore_th=0.2, uncertainty_ratio=1.0)
+        r0, r1 = G[f'{tag}/pool_ids0'], G[f'{tag}/pool_ids1']
+        # received attention comes from fp16 tensor-core scores: tokens sitting exactly at the median may flip
+        assert len(set(ids0.cpu().tolist()) ^ set(r0.tolist())) <= 2 and len(set(ids1.cpu().tolist()) ^ set(r1.tolist())) <= 2
+        assert ids0.dtype == torch.int64
+        # the caller compacts with these ids (eval/matching.py:167) and continues with the next (non-sharing) layer
+        d0c, d1c = d0[:, :, ids0], d1[:, :, ids1]
+        d0n, d1n = m.forward_one_layer(desc0=d0c, desc1=d1c, M0=None, M1=None, layer_i=8)
+        assert d0n.shape == (1, 256, len(ids0)) and torch.isfinite(d0n).all()
+    else:
+        assert m.pool(pred_score=score) == (None, None)
+
+
+def test_known_answers_free_functions():
+    m = GM(cfg(1)).cuda().eval()
+    M = torch.from_numpy(G['fn/sink_in']).cuda()
+    bs = torch.tensor(0.8).cuda()
+    for it, key in ((20, 'fn/sink_out20'), (0, 'fn/sink_out0')):
+        out = m.compute_score(M, bs, it).cpu().numpy()
+        assert np.abs(out - G[key]).max() / np.abs(G[key]).max() < 2e-5
+    m.with_sinkhorn = False
+    assert np.abs(m.compute_score(M, bs, 0).cpu().numpy() - G['fn/dual_softmax']).max() < 1e-5
+    i0, i1, m0, m1 = m.compute_matches(torch.from_numpy(G['fn/ties_in']).cuda(), 0.2)
+    assert np.array_equal(i0.cpu().numpy(), G['fn/ties_i0']) and np.array_equal(i1.cpu().numpy(), G['fn/ties_i1'])
+    assert np.array_equal(m0.cpu().numpy(), G['fn/ties_m0']) and np.array_equal(m1.cpu().numpy(), G['fn/ties_m1'])
+    kp = torch.from_numpy(G['fn/normkp_in']).cuda()
+    assert np.abs(normalize_keypoints(kp, (1, 1, 480, 640)).cpu().numpy() - G['fn/normkp_out']).max() < 1e-6
+
+
+def test_full_size_properties():
+    """BASELINE.json full size (N = 2000): size-independent properties instead of a CPU oracle run --
+    Sinkhorn column marginals are met exactly (the loop ends on a column update), mutual matches are
+    a partial permutation, and self-matching an image with itself recovers the identity."""
+    nl = 9
+    net = DGNNS(cfg(nl))
+    net.load_state_dict(synth.make_state_dict('DGNNS', nl, seed=7), strict=True)
+    net = net.cuda().eval()
+    data = synth.make_pair_batch(seed=21, batch=2, n0=2000, n1=2000, noise=0.0)
+    data['descriptors1'], data['keypoints1'], data['scores1'] = data['descriptors0'], data['keypoints0'], data['scores0']
+    with torch.no_grad():
+        out = net.produce_matches(cuda(data), p=0.2, only_last=True)
+        st = net._last_sk
+    i0 = out['indices0'][-1]
+    valid = i0 >= 0
+    assert int(valid.sum()) > 1000
+    assert torch.equal(i0[valid], torch.arange(2000, device='cuda').repeat(2, 1)[valid])       # identity pairing
+    cols = st.scores().sum(1)
+    assert float((cols[:, :-1] - 1).abs().max()) < 1e-4 and float((cols[:, -1] - 2001).abs().max()) < 1e-1
+    for b in range(2):
+        v = i0[b][i0[b] >= 0]
+        assert v.numel() == v.unique().numel()                                                  # injective

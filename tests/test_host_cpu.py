@@ -1,0 +1,126 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol include/imp_b200.h declares,
+the model classes keep the reference's state_dict layout, the product path refuses to run without CUDA, and the
+multi-process sharding / gather logic (gloo, world_size 2)."""
+import os
+import re
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from imp_release_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, 'include', 'imp_b200.h')).read()
+    declared = set(re.findall(r'IMP_API\s+(?:const\s+char\*|int)\s+(imp_[a-z0-9_]+)\s*\(', hdr))
+    assert declared, 'no declarations parsed'
+    assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.imp_abi_version() == _lib.ABI_VERSION
+    # ctypes struct sizes must match the C structs (checked against the compiler)
+    src = '#include <stdio.h>\n#include "imp_b200.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu", sizeof(imp_gemm_args), ' \
+          'sizeof(imp_attn_args), sizeof(imp_attn_colsum_args), sizeof(imp_sinkhorn_args), sizeof(imp_match_args), sizeof(imp_pool_args));}'
+    exe = os.path.join('/tmp', f'imp_sizes_{os.getpid()}')
+    subprocess.run(['gcc', '-x', 'c', '-', '-I', os.path.join(ROOT, 'include'), '-o', exe], input=src.encode(), check=True)
+    sizes = [int(x) for x in subprocess.run([exe], capture_output=True, check=True).stdout.split()]
+    import ctypes as C
+    got = [C.sizeof(t) for t in (_lib.GemmArgs, _lib.AttnArgs, _lib.AttnColsumArgs, _lib.SinkhornArgs, _lib.MatchArgs,
+                                 _lib.PoolArgs)]
+    assert sizes == got, (sizes, got)
+
+
+def test_state_dict_layout_matches_reference_spec():
+    from imp_release_b200 import GM, DGNNS, AdaGMN
+    from oracle import synth
+    for kind, cls, nl in (('GM', GM, 3), ('DGNNS', DGNNS, 15), ('AdaGMN', AdaGMN, 15)):
+        m = cls(dict(n_layers=nl, GNN_layers=['self', 'cross'] * nl, norm_fn='in', ac_fn='relu'))
+        spec = synth.state_dict_spec(kind, nl)
+        sd = m.state_dict()
+        assert list(sd.keys()).sort() == list(spec.keys()).sort()
+        assert set(sd.keys()) == set(spec.keys())
+        for k, shape in spec.items():
+            assert tuple(sd[k].shape) == tuple(shape), k
+        m.load_state_dict(synth.make_state_dict(kind, nl, seed=1), strict=True)
+    assert sum(p.numel() for p in DGNNS(dict(n_layers=15, GNN_layers=['self', 'cross'] * 15, norm_fn='in')).parameters()) == 19231809
+
+
+def test_product_path_fails_loudly_without_cuda():
+    from imp_release_b200 import DGNNS
+    from imp_release_b200._lib import ImpLibraryError
+    from oracle import synth
+    if torch.cuda.is_available():
+        pytest.skip('CUDA present')
+    m = DGNNS(dict(n_layers=3, GNN_layers=['self', 'cross'] * 3, norm_fn='in')).eval()
+    data = synth.make_pair_batch(seed=0, batch=1, n0=16, n1=16)
+    with pytest.raises(ImpLibraryError):
+        m(data)
+    with pytest.raises(NotImplementedError):
+        DGNNS(dict(n_layers=3, GNN_layers=['self', 'cross'] * 3, norm_fn='bn'))
+    with pytest.raises(ValueError):          # nets/gms.py:166
+        bad = {k: v for k, v in data.items() if not k.startswith('image')}
+        DGNNS._norm_kpts(bad)
+    empty = dict(data)
+    empty['keypoints0'] = torch.zeros(1, 0, 2)
+    out = m.produce_matches(empty)            # empty-keypoint early return, nets/gms.py:148-156
+    assert out['skip_train'] is True and out['matches0'].numel() == 0
+
+
+def test_dropin_exports_reference_module_paths():
+    code = ('import sys; sys.path.insert(0, %r); from nets.gms import DGNNS; from nets.adgm import AdaGMN; '
+            'from nets.gm import GM, normalize_keypoints; from nets.layers import normalize_keypoints as nk2; '
+            'import imp_release_b200 as p; assert DGNNS is p.DGNNS and AdaGMN is p.AdaGMN and GM is p.GM; print("ok")'
+            % os.path.join(ROOT, 'dropin'))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT)
+    assert r.returncode == 0 and 'ok' in r.stdout, r.stderr
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %(root)r)
+from imp_release_b200 import shard
+from oracle import imp_oracle, synth
+rank, world = int(sys.argv[1]), int(sys.argv[2])
+os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=sys.argv[3])
+dist.init_process_group('gloo', rank=rank, world_size=world)
+torch.set_num_threads(2)
+nl, n_pairs, n = 2, 5, 48
+cfg = dict(n_layers=nl, GNN_layers=['self', 'cross'] * nl, norm_fn='in', ac_fn='relu', sinkhorn_iterations=5)
+orc = imp_oracle.Oracle('DGNNS', cfg, synth.make_state_dict('DGNNS', nl, seed=2))
+def match_fn(ids):     # pair i = seeded synthetic pair i (seed = pair index, SURVEY.md 8(d) config 4)
+    out_i, out_s = [], []
+    for i in ids:
+        o = orc.produce_matches(synth.make_pair_batch(seed=100 + i, batch=1, n0=n, n1=n - 4), only_last=True)
+        out_i.append(o['indices0'][-1][0]); out_s.append(o['mscores0'][-1][0])
+    return torch.stack(out_i), torch.stack(out_s)
+res = shard.match_sharded(match_fn, n_pairs, n, rank, world)
+if rank == 0:
+    full_i, full_s = match_fn(list(range(n_pairs)))
+    assert torch.equal(res[0], full_i) and torch.equal(res[1], full_s)
+    print('SHARD_OK')
+else:
+    assert res is None
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_matching_equals_single_process_gloo():
+    """world_size-2 gloo run: rank-strided shards + one gather reproduce the single-process result exactly."""
+    port = str(29500 + os.getpid() % 2000)
+    script = _WORKER % {'root': ROOT}
+    procs = [subprocess.Popen([sys.executable, '-c', script, str(r), '2', port], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    assert all(p.returncode == 0 for p in procs), [o[1][-800:] for o in outs]
+    assert 'SHARD_OK' in outs[0][0]
+
+
+def test_shard_indices_cover_everything():
+    from imp_release_b200.shard import shard_indices
+    for n, w in ((4000, 8), (7, 2), (3, 4)):
+        seen = sorted(i for r in range(w) for i in shard_indices(n, r, w))
+        assert seen == list(range(n))
