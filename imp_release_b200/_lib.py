@@ -50,7 +50,7 @@ class SinkhornArgs(C.Structure):
     _fields_ = [('dist', c_vp), ('dist_batch_stride', c_i64), ('ldd', c_i32), ('iters', c_i32), ('bin_score', c_vp),
                 ('P', c_vp), ('p_batch_stride', c_i64), ('ldp', c_i32), ('_pad', c_i32), ('u', c_vp), ('colbuf', c_vp),
                 ('row_max', c_vp), ('row_arg', c_vp), ('col_key', c_vp), ('row_mass', c_vp), ('col_mass', c_vp),
-                ('n0s', c_vp), ('n1s', c_vp), ('N0max', c_i32), ('N1max', c_i32), ('batch', c_i32), ('_pad2', c_i32)]
+                ('n0s', c_vp), ('n1s', c_vp), ('N0max', c_i32), ('N1max', c_i32), ('batch', c_i32), ('write_scores', c_i32)]
 
 
 class MatchArgs(C.Structure):

@@ -3,13 +3,16 @@
 // S x { u = r / (sum_j p v + 1e-8);  v = c / (sum_i p u + 1e-8) },  out = (p u) v,
 // r = [1..1, N0+1], c = [1..1, N1+1].  Row softmax is the max-subtracted (LSE-stabilised) form.
 //
-// HBM/L2-bound streaming kernels.  One launch per Sinkhorn iteration reads the matrix ONCE: a warp
-// keeps a whole row in registers, reduces it against v (warp shuffles) to get u_i, then immediately
-// folds p_ij * u_i into per-lane column accumulators; the CTA combines its warps in shared memory and
-// issues one global atomicAdd per column.  v is never materialised: the next launch recomputes
-// c_j / (colsum_j + eps) on the fly from the accumulated column sums (three rotating buffers: read /
-// accumulate / being-zeroed).  The final launch applies (p u) v in place and fuses the row / column
-// arg-max (lowest index wins ties, like torch.max on CPU) and the row / column masses EIMP's pooling needs.
+// HBM-bound streaming kernels built around one "row ring": a producer warp streams whole matrix rows (8 KB at
+// N = 2000) into a shared-memory ring with 1-D bulk TMA copies (cp.async.bulk + mbarrier complete_tx), ~100 KB in
+// flight per CTA, two CTAs per SM; four consumer warps take rows off the ring.  One launch per Sinkhorn iteration
+// reads the matrix ONCE: the consumer reduces the row against v (warp shuffles) to get u_i, then immediately folds
+// p_ij * u_i into per-lane column accumulators; the CTA combines its warps in shared memory and issues one global
+// atomicAdd per column.  v is never materialised: the next launch recomputes c_j / (colsum_j + eps) on the fly from
+// the accumulated column sums (three rotating buffers: read / accumulate / being-zeroed).  The final launch applies
+// (p u) v (written back only when the caller wants the score matrix) with the row arg-max and the row / column
+// masses EIMP's pooling needs; a coalesced column pass produces the column arg-max (lowest index wins ties, like
+// torch.max on CPU).
 #include "sinkhorn.cuh"
 
 #include <float.h>
@@ -19,14 +22,14 @@
 
 namespace imp {
 
-static constexpr int SK_THREADS = 256;
-static constexpr int SK_WARPS = SK_THREADS / 32;
 static constexpr float SK_EPS = 1e-8f;
+static constexpr int SKR_CONSUMERS = 4;
+static constexpr int SKR_THREADS = (SKR_CONSUMERS + 1) * 32;  // + one producer warp
+static constexpr int SKR_SMEM_BUDGET = 110 * 1024;            // two CTAs per SM
 
 struct SkDims {
   int R, C;  // augmented rows / cols of this sample
 };
-
 __device__ __forceinline__ SkDims sk_dims(const int* n0s, const int* n1s, int b, int N0max, int N1max) {
   SkDims d;
   d.R = (n0s ? n0s[b] : N0max) + 1;
@@ -34,22 +37,40 @@ __device__ __forceinline__ SkDims sk_dims(const int* n0s, const int* n1s, int b,
   return d;
 }
 
-// Row loader: lane l owns float4 groups g = l + 32*k (columns 4g..4g+3), k < NV.
-template <int NV>
-__device__ __forceinline__ void load_row(const float* __restrict__ row, int C, float4 (&x)[NV]) {
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c0 = 4 * (lane_id() + 32 * k);
-    if (c0 < C)  // ld is a multiple of 4 and the pad columns hold zeros, so a full float4 is always readable
-      x[k] = *reinterpret_cast<const float4*>(row + c0);
-    else
-      x[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
+struct SkParams {
+  const float* dist;
+  long long dist_bs;
+  int ldd;
+  const float* bin_score;
+  float* P;
+  long long p_bs;
+  int ldp;
+  float* u;
+  const float* col_prev;
+  float* col_acc;
+  float* col_zero;
+  float* row_max;
+  int* row_arg;
+  float* row_mass;
+  float* col_mass;
+  const int *n0s, *n1s;
+  int N0max, N1max;
+  int rows_per_cta, ring_slots;
+  int do_iter;       // init: also perform the first half-iteration;  final: Sinkhorn ran at least once
+  int write_scores;  // final: store (p u) v back into P
+};
+
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
 }
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SKR_CONSUMERS * 32) : "memory"); }
 
 __device__ __forceinline__ float4 v_from_colsum(const float* __restrict__ colsum, int c0, int C) {
   // v_j = c_j / (colsum_j + eps);  c_j = 1, last real column C-1 has mass C;  pad columns -> 0
-  float4 s = *reinterpret_cast<const float4*>(colsum + c0);
+  const float4 s = *reinterpret_cast<const float4*>(colsum + c0);
   float4 v;
   v.x = (c0 + 0 < C) ? ((c0 + 0 == C - 1) ? (float)C : 1.f) / (s.x + SK_EPS) : 0.f;
   v.y = (c0 + 1 < C) ? ((c0 + 1 == C - 1) ? (float)C : 1.f) / (s.y + SK_EPS) : 0.f;
@@ -58,154 +79,249 @@ __device__ __forceinline__ float4 v_from_colsum(const float* __restrict__ colsum
   return v;
 }
 
-template <int NV>
-__device__ __forceinline__ void flush_colacc(float4 (&acc)[NV], float* s_col, float* __restrict__ g_col, int C) {
-  // combine the CTA's warps in shared memory, then one global atomic per column
-  for (int j = threadIdx.x; j < ((C + 3) & ~3); j += SK_THREADS) s_col[j] = 0.f;
-  __syncthreads();
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int c0 = 4 * (lane_id() + 32 * k);
-    if (c0 < C) {
-      atomicAdd(s_col + c0 + 0, acc[k].x);
-      atomicAdd(s_col + c0 + 1, acc[k].y);
-      atomicAdd(s_col + c0 + 2, acc[k].z);
-      atomicAdd(s_col + c0 + 3, acc[k].w);
+enum { SK_INIT = 0, SK_ITER = 1, SK_FINAL = 2 };
+
+// MODE: SK_INIT  P = softmax_rows(pad(dist)) (+ first half-iteration: u with v = 1, column sums with that u)
+//       SK_ITER  one full Sinkhorn iteration (u, then column sums) in a single sweep over P
+//       SK_FINAL out = (p u) v, row arg-max / masses over the non-dustbin block
+template <int NV, int MODE>
+__global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams p) {
+  extern __shared__ __align__(16) float sk_smem[];
+  const int b = blockIdx.y;
+  const SkDims d = sk_dims(p.n0s, p.n1s, b, p.N0max, p.N1max);
+  const int row0 = blockIdx.x * p.rows_per_cta;
+  if (row0 >= d.R) return;
+  const int nrows = min(p.rows_per_cta, d.R - row0);
+  const int S = p.ring_slots;
+  float* ring = sk_smem;                         // [S][ldp]
+  float* s_v = ring + (size_t)S * p.ldp;         // [ldp]
+  float* s_col = s_v + p.ldp;                    // [ldp]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_col + p.ldp);
+  uint64_t* empty_bar = full_bar + S;
+  const int warp = threadIdx.x >> 5;
+  const int C4 = (d.C + 3) & ~3;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
     }
+    fence_barrier_init();
   }
   __syncthreads();
-  for (int j = threadIdx.x; j < C; j += SK_THREADS) atomicAdd(g_col + j, s_col[j]);
-}
 
-// ---------------------------------------------------------------------------------------------
-// init: P = softmax_rows(pad(dist)); optionally also the first Sinkhorn half-steps (u with v = 1,
-// column sums with that u).  Zeroes the NEXT column-sum buffer.
-template <int NV>
-__global__ void __launch_bounds__(SK_THREADS)
-sk_init_kernel(const float* __restrict__ dist, long long dist_bs, int ldd, const float* __restrict__ bin_score,
-               float* __restrict__ P, long long p_bs, int ldp, float* __restrict__ u, float* __restrict__ col_acc,
-               float* __restrict__ col_zero, const int* __restrict__ n0s, const int* __restrict__ n1s, int N0max,
-               int N1max, int rows_per_cta, int do_iter) {
-  extern __shared__ float s_col[];
-  const int b = blockIdx.y;
-  const SkDims d = sk_dims(n0s, n1s, b, N0max, N1max);
-  const int row0 = blockIdx.x * rows_per_cta;
-  if (row0 >= d.R) return;
-  const int warp = threadIdx.x >> 5;
-  const float bin = *bin_score;
+  if (warp == SKR_CONSUMERS) {
+    // ------------------------------------------------------------------ producer: stream rows into the ring
+    if (lane_id() == 0) {
+      const float* src = (MODE == SK_INIT) ? p.dist + b * p.dist_bs : p.P + b * p.p_bs;
+      const long long ld = (MODE == SK_INIT) ? p.ldd : p.ldp;
+      const uint32_t bytes = (MODE == SK_INIT) ? (uint32_t)(((d.C - 1 + 3) & ~3) * 4) : (uint32_t)(C4 * 4);
+      for (int r = 0; r < nrows; ++r) {
+        const int s = r % S;
+        mbar_wait(&empty_bar[s], ((r / S) & 1) ^ 1);
+        const int i = row0 + r;
+        if (MODE == SK_INIT && (i == d.R - 1 || bytes == 0)) {
+          mbar_arrive(&full_bar[s]);  // the dustbin row has no source: the consumer synthesises it
+        } else {
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          bulk_copy_g2s(ring + (size_t)s * p.ldp, src + (long long)i * ld, bytes, &full_bar[s]);
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- consumers
+  const int ct = threadIdx.x;  // 0..127
+  if (blockIdx.x == 0 && p.col_zero != nullptr)
+    for (int j = ct; j < p.ldp; j += SKR_CONSUMERS * 32) p.col_zero[(long long)b * p.ldp + j] = 0.f;
+  for (int c0 = 4 * ct; c0 < C4; c0 += 4 * SKR_CONSUMERS * 32) {
+    float4 v = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (MODE == SK_ITER || (MODE == SK_FINAL && p.do_iter)) v = v_from_colsum(p.col_prev + (long long)b * p.ldp, c0, d.C);
+    *reinterpret_cast<float4*>(s_v + c0) = v;
+    *reinterpret_cast<float4*>(s_col + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  consumer_sync();
+
+  const float bin = (MODE == SK_INIT) ? *p.bin_score : 0.f;
+  const bool want_col = (MODE != SK_FINAL) ? (p.do_iter != 0 || MODE == SK_ITER) : (p.col_mass != nullptr);
   float4 acc[NV];
 #pragma unroll
   for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (blockIdx.x == 0 && col_zero != nullptr)
-    for (int j = threadIdx.x; j < ldp; j += SK_THREADS) col_zero[(long long)b * ldp + j] = 0.f;
 
-  const int row_end = min(row0 + rows_per_cta, d.R);
-  for (int i = row0 + warp; i < row_end; i += SK_WARPS) {
-    float4 x[NV];
-    const bool bin_row = (i == d.R - 1);
-    const float* drow = dist + b * dist_bs + (long long)i * ldd;
-    float m = -FLT_MAX;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      float e[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        const int c = c0 + t;
-        float val = -FLT_MAX;
-        if (c < d.C) val = (bin_row || c == d.C - 1) ? bin : drow[c];
-        e[t] = val;
-        m = fmaxf(m, val);
-      }
-      x[k] = make_float4(e[0], e[1], e[2], e[3]);
-    }
-    m = warp_max(m);
-    float s = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      x[k].x = (c0 + 0 < d.C) ? expf(x[k].x - m) : 0.f;
-      x[k].y = (c0 + 1 < d.C) ? expf(x[k].y - m) : 0.f;
-      x[k].z = (c0 + 2 < d.C) ? expf(x[k].z - m) : 0.f;
-      x[k].w = (c0 + 3 < d.C) ? expf(x[k].w - m) : 0.f;
-      s += (x[k].x + x[k].y) + (x[k].z + x[k].w);
-    }
-    s = warp_sum(s);
-    float* prow = P + b * p_bs + (long long)i * ldp;
-    float rs = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      x[k].x = x[k].x / s;
-      x[k].y = x[k].y / s;
-      x[k].z = x[k].z / s;
-      x[k].w = x[k].w / s;
-      rs += (x[k].x + x[k].y) + (x[k].z + x[k].w);
-      if (c0 < ldp) *reinterpret_cast<float4*>(prow + c0) = x[k];
-    }
-    if (do_iter) {
-      rs = warp_sum(rs);  // sum_j p_ij * v_j with v = 1
-      const float ui = (bin_row ? (float)d.R : 1.f) / (rs + SK_EPS);
-      if (lane_id() == 0) u[(long long)b * (N0max + 1) + i] = ui;
+  for (int r = warp; r < nrows; r += SKR_CONSUMERS) {
+    const int s = r % S;
+    const int i = row0 + r;
+    mbar_wait(&full_bar[s], (r / S) & 1);
+    float* srow = ring + (size_t)s * p.ldp;
+    // Rows are re-read from the ring instead of being held in registers (keeps the kernel at ~2 CTAs/SM without
+    // spills); each lane only ever touches its own float4 groups, so in-place updates of the slot are race-free.
+    if (MODE == SK_INIT) {
+      const bool bin_row = (i == d.R - 1);
+      float m = -FLT_MAX;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
-        acc[k].x += x[k].x * ui;
-        acc[k].y += x[k].y * ui;
-        acc[k].z += x[k].z * ui;
-        acc[k].w += x[k].w * ui;
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          float4 t = make_float4(bin, bin, bin, bin);
+          if (!bin_row && c0 < d.C - 1) t = *reinterpret_cast<const float4*>(srow + c0);
+          t.x = (c0 + 0 < d.C) ? ((bin_row || c0 + 0 == d.C - 1) ? bin : t.x) : -FLT_MAX;
+          t.y = (c0 + 1 < d.C) ? ((bin_row || c0 + 1 == d.C - 1) ? bin : t.y) : -FLT_MAX;
+          t.z = (c0 + 2 < d.C) ? ((bin_row || c0 + 2 == d.C - 1) ? bin : t.z) : -FLT_MAX;
+          t.w = (c0 + 3 < d.C) ? ((bin_row || c0 + 3 == d.C - 1) ? bin : t.w) : -FLT_MAX;
+          *reinterpret_cast<float4*>(srow + c0) = t;
+          m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+        }
+      }
+      m = warp_max(m);
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          t.x = (c0 + 0 < d.C) ? expf(t.x - m) : 0.f;
+          t.y = (c0 + 1 < d.C) ? expf(t.y - m) : 0.f;
+          t.z = (c0 + 2 < d.C) ? expf(t.z - m) : 0.f;
+          t.w = (c0 + 3 < d.C) ? expf(t.w - m) : 0.f;
+          *reinterpret_cast<float4*>(srow + c0) = t;
+          sum += (t.x + t.y) + (t.z + t.w);
+        }
+      }
+      sum = warp_sum(sum);
+      float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
+      float rs = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          t.x = t.x / sum;
+          t.y = t.y / sum;
+          t.z = t.z / sum;
+          t.w = t.w / sum;
+          *reinterpret_cast<float4*>(srow + c0) = t;
+          *reinterpret_cast<float4*>(prow + c0) = t;
+          rs += (t.x + t.y) + (t.z + t.w);
+        } else if (c0 < p.ldp) {
+          *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      if (p.do_iter) {
+        rs = warp_sum(rs);  // sum_j p_ij * v_j with v = 1
+        const float ui = (bin_row ? (float)d.R : 1.f) / (rs + SK_EPS);
+        if (lane_id() == 0) p.u[(long long)b * (p.N0max + 1) + i] = ui;
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+          const int c0 = 4 * (lane_id() + 32 * k);
+          if (c0 < d.C) {
+            const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+            acc[k].x += t.x * ui;
+            acc[k].y += t.y * ui;
+            acc[k].z += t.z * ui;
+            acc[k].w += t.w * ui;
+          }
+        }
+      }
+    } else if (MODE == SK_ITER) {
+      float rs = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
+          rs += (t.x * v.x + t.y * v.y) + (t.z * v.z + t.w * v.w);
+        }
+      }
+      rs = warp_sum(rs);
+      const float ui = ((i == d.R - 1) ? (float)d.R : 1.f) / (rs + SK_EPS);
+      if (lane_id() == 0) p.u[(long long)b * (p.N0max + 1) + i] = ui;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          acc[k].x += t.x * ui;
+          acc[k].y += t.y * ui;
+          acc[k].z += t.z * ui;
+          acc[k].w += t.w * ui;
+        }
+      }
+    } else {  // SK_FINAL
+      const float ui = p.do_iter ? p.u[(long long)b * (p.N0max + 1) + i] : 1.f;
+      const bool inner_row = i < d.R - 1;
+      float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
+      float best = -1.f, mass = 0.f;
+      int best_j = 0x7fffffff;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 >= d.C) continue;
+        const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+        const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
+        const float o[4] = {(t.x * ui) * v.x, (t.y * ui) * v.y, (t.z * ui) * v.z, (t.w * ui) * v.w};
+        if (p.write_scores) *reinterpret_cast<float4*>(prow + c0) = make_float4(o[0], o[1], o[2], o[3]);
+        if (inner_row) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            if (c0 + q < d.C - 1) {
+              mass += o[q];
+              if (o[q] > best) {  // strict: keeps the lowest column among equal values in this lane
+                best = o[q];
+                best_j = c0 + q;
+              }
+            }
+          }
+          if (want_col) {
+            acc[k].x += o[0];
+            acc[k].y += o[1];
+            acc[k].z += o[2];
+            acc[k].w += o[3];
+          }
+        }
+      }
+      if (inner_row) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {  // warp arg-max, lowest index wins ties
+          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+          const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+          if (ob > best || (ob == best && oj < best_j)) {
+            best = ob;
+            best_j = oj;
+          }
+        }
+        mass = warp_sum(mass);
+        if (lane_id() == 0) {
+          p.row_max[(long long)b * p.N0max + i] = best;
+          p.row_arg[(long long)b * p.N0max + i] = best_j;
+          if (p.row_mass) p.row_mass[(long long)b * p.N0max + i] = mass;
+        }
       }
     }
+    __syncwarp();
+    if (lane_id() == 0) mbar_arrive(&empty_bar[s]);  // the ring slot is free again
   }
-  if (do_iter) flush_colacc<NV>(acc, s_col, col_acc + (long long)b * ldp, d.C);
-}
 
-// one full Sinkhorn iteration (u then column sums) in a single sweep over P
-template <int NV>
-__global__ void __launch_bounds__(SK_THREADS)
-sk_iter_kernel(const float* __restrict__ P, long long p_bs, int ldp, const float* __restrict__ col_prev,
-               float* __restrict__ col_acc, float* __restrict__ col_zero, float* __restrict__ u,
-               const int* __restrict__ n0s, const int* __restrict__ n1s, int N0max, int N1max, int rows_per_cta) {
-  extern __shared__ float s_col[];
-  const int b = blockIdx.y;
-  const SkDims d = sk_dims(n0s, n1s, b, N0max, N1max);
-  const int row0 = blockIdx.x * rows_per_cta;
-  if (row0 >= d.R) return;
-  const int warp = threadIdx.x >> 5;
-  if (blockIdx.x == 0)
-    for (int j = threadIdx.x; j < ldp; j += SK_THREADS) col_zero[(long long)b * ldp + j] = 0.f;
-
-  float4 acc[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-  float* s_v = s_col + ldp;  // v_j for this sample, shared by the CTA's warps
-  for (int c0 = 4 * threadIdx.x; c0 < ((d.C + 3) & ~3); c0 += 4 * SK_THREADS)
-    *reinterpret_cast<float4*>(s_v + c0) = v_from_colsum(col_prev + (long long)b * ldp, c0, d.C);
-  __syncthreads();
-  const int row_end = min(row0 + rows_per_cta, d.R);
-  for (int i = row0 + warp; i < row_end; i += SK_WARPS) {
-    float4 x[NV];
-    load_row<NV>(P + b * p_bs + (long long)i * ldp, d.C, x);
-    float rs = 0.f;
+  if (want_col) {
+    // combine the CTA's warps in shared memory, then one global atomic per column
 #pragma unroll
     for (int k = 0; k < NV; ++k) {
       const int c0 = 4 * (lane_id() + 32 * k);
       if (c0 < d.C) {
-        const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
-        rs += (x[k].x * v.x + x[k].y * v.y) + (x[k].z * v.z + x[k].w * v.w);
+        atomicAdd(s_col + c0 + 0, acc[k].x);
+        atomicAdd(s_col + c0 + 1, acc[k].y);
+        atomicAdd(s_col + c0 + 2, acc[k].z);
+        atomicAdd(s_col + c0 + 3, acc[k].w);
       }
     }
-    rs = warp_sum(rs);
-    const float ui = ((i == d.R - 1) ? (float)d.R : 1.f) / (rs + SK_EPS);
-    if (lane_id() == 0) u[(long long)b * (N0max + 1) + i] = ui;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      acc[k].x += x[k].x * ui;
-      acc[k].y += x[k].y * ui;
-      acc[k].z += x[k].z * ui;
-      acc[k].w += x[k].w * ui;
+    consumer_sync();
+    if (MODE == SK_FINAL) {
+      for (int j = ct; j < d.C - 1; j += SKR_CONSUMERS * 32) atomicAdd(p.col_mass + (long long)b * p.N1max + j, s_col[j]);
+    } else {
+      for (int j = ct; j < d.C; j += SKR_CONSUMERS * 32) atomicAdd(p.col_acc + (long long)b * p.ldp + j, s_col[j]);
     }
   }
-  flush_colacc<NV>(acc, s_col, col_acc + (long long)b * ldp, d.C);
 }
 
 __device__ __forceinline__ unsigned long long pack_max_key(float val, int idx) {
@@ -213,88 +329,33 @@ __device__ __forceinline__ unsigned long long pack_max_key(float val, int idx) {
   return (static_cast<unsigned long long>(__float_as_uint(val)) << 32) | (0xFFFFFFFFu - (unsigned)idx);
 }
 
-// final scaling out = (p u) v in place + fused row/col arg-max and masses over the non-dustbin block
-template <int NV>
-__global__ void __launch_bounds__(SK_THREADS)
-sk_final_kernel(float* __restrict__ P, long long p_bs, int ldp, const float* __restrict__ col_last,
-                const float* __restrict__ u, int has_iter, float* __restrict__ row_max, int* __restrict__ row_arg,
-                unsigned long long* __restrict__ col_key, float* __restrict__ row_mass, float* __restrict__ col_mass,
-                const int* __restrict__ n0s, const int* __restrict__ n1s, int N0max, int N1max, int rows_per_cta) {
-  extern __shared__ float s_col[];  // [ldp] masses, then [ldp] u64 keys
-  const int b = blockIdx.y;
+// column arg-max over the non-dustbin block: thread per column (coalesced), 256-row slabs, packed atomicMax
+__global__ void __launch_bounds__(128)
+sk_colmax_kernel(const float* __restrict__ P, long long p_bs, int ldp, const float* __restrict__ u,
+                 const float* __restrict__ col_last, int scaled, int has_iter, unsigned long long* __restrict__ col_key,
+                 const int* __restrict__ n0s, const int* __restrict__ n1s, int N0max, int N1max, int slab) {
+  const int b = blockIdx.z;
   const SkDims d = sk_dims(n0s, n1s, b, N0max, N1max);
-  const int row0 = blockIdx.x * rows_per_cta;
-  if (row0 >= d.R) return;
-  const int warp = threadIdx.x >> 5;
-  const int ldp4 = (d.C + 3) & ~3;
-  unsigned long long* s_key = reinterpret_cast<unsigned long long*>(s_col + ((ldp + 1) & ~1));
-  for (int j = threadIdx.x; j < ldp4; j += SK_THREADS) {
-    s_col[j] = 0.f;
-    s_key[j] = 0ull;
-  }
-
-  float* s_v = reinterpret_cast<float*>(s_key + ldp);
-  for (int c0 = 4 * threadIdx.x; c0 < ldp4; c0 += 4 * SK_THREADS)
-    *reinterpret_cast<float4*>(s_v + c0) =
-        has_iter ? v_from_colsum(col_last + (long long)b * ldp, c0, d.C) : make_float4(1.f, 1.f, 1.f, 1.f);
-  __syncthreads();
-  const int row_end = min(row0 + rows_per_cta, d.R);
-  for (int i = row0 + warp; i < row_end; i += SK_WARPS) {
-    float4 x[NV];
-    float* prow = P + b * p_bs + (long long)i * ldp;
-    load_row<NV>(prow, d.C, x);
-    const float ui = has_iter ? u[(long long)b * (N0max + 1) + i] : 1.f;
-    const bool inner_row = i < d.R - 1;
-    float best = -1.f;
-    int best_j = 0x7fffffff;
-    float mass = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 >= d.C) continue;
-      const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
-      float o[4] = {(x[k].x * ui) * v.x, (x[k].y * ui) * v.y, (x[k].z * ui) * v.z, (x[k].w * ui) * v.w};
-      *reinterpret_cast<float4*>(prow + c0) = make_float4(o[0], o[1], o[2], o[3]);
-      if (inner_row) {
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          const int c = c0 + t;
-          if (c < d.C - 1) {
-            mass += o[t];
-            if (o[t] > best) {  // strict: keeps the lowest column among equal values in this lane
-              best = o[t];
-              best_j = c;
-            }
-            if (col_mass) atomicAdd(s_col + c, o[t]);
-            atomicMax(s_key + c, pack_max_key(o[t], i));
-          }
-        }
-      }
-    }
-    if (inner_row) {
-      // warp arg-max with lowest-index tie break
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-        if (ob > best || (ob == best && oj < best_j)) {
-          best = ob;
-          best_j = oj;
-        }
-      }
-      mass = warp_sum(mass);
-      if (lane_id() == 0) {
-        row_max[(long long)b * N0max + i] = best;
-        row_arg[(long long)b * N0max + i] = best_j;
-        if (row_mass) row_mass[(long long)b * N0max + i] = mass;
-      }
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i0 = blockIdx.y * slab;
+  if (j >= d.C - 1 || i0 >= d.R - 1) return;
+  const int i1 = min(i0 + slab, d.R - 1);
+  float vj = 1.f;
+  if (!scaled && has_iter) vj = 1.f / (col_last[(long long)b * ldp + j] + SK_EPS);  // c_j = 1 for j < C-1
+  const float* base = P + b * p_bs + j;
+  const float* ub = u + (long long)b * (N0max + 1);
+  float best = -1.f;
+  int bi = 0;
+#pragma unroll 4
+  for (int i = i0; i < i1; ++i) {
+    float val = base[(long long)i * ldp];
+    if (!scaled) val = (val * (has_iter ? ub[i] : 1.f)) * vj;
+    if (val > best) {
+      best = val;
+      bi = i;
     }
   }
-  __syncthreads();
-  for (int j = threadIdx.x; j < d.C - 1; j += SK_THREADS) {
-    atomicMax(col_key + (long long)b * N1max + j, s_key[j]);
-    if (col_mass) atomicAdd(col_mass + (long long)b * N1max + j, s_col[j]);
-  }
+  atomicMax(col_key + (long long)b * N1max + j, pack_max_key(best, bi));
 }
 
 // mutual nearest-neighbour check + threshold (GM.compute_matches, nets/gm.py:305-320)
@@ -331,29 +392,69 @@ __global__ void sk_matches_kernel(const float* __restrict__ row_max, const int* 
 template <int NV>
 static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   const int R = a.N0max + 1;
-  // aim for >= 2 waves of CTAs; a warp handles rows_per_cta / 8 rows
-  int rows_per_cta = 32;
-  while (rows_per_cta > 8 && (long long)a.batch * ((R + rows_per_cta - 1) / rows_per_cta) < 2LL * num_sms()) rows_per_cta >>= 1;
+  SkParams p;
+  p.dist = a.dist;
+  p.dist_bs = a.dist_batch_stride;
+  p.ldd = a.ldd;
+  p.bin_score = a.bin_score;
+  p.P = a.P;
+  p.p_bs = a.p_batch_stride;
+  p.ldp = a.ldp;
+  p.u = a.u;
+  p.row_max = a.row_max;
+  p.row_arg = a.row_arg;
+  p.row_mass = a.row_mass;
+  p.col_mass = a.col_mass;
+  p.n0s = a.n0s;
+  p.n1s = a.n1s;
+  p.N0max = a.N0max;
+  p.N1max = a.N1max;
+  p.write_scores = a.write_scores;
+  // a CTA owns up to 128 consecutive rows of one matrix; shrink the blocks until there are >= 4 CTAs per SM
+  int rows_per_cta = 128;
+  while (rows_per_cta > 8 && (long long)a.batch * ((R + rows_per_cta - 1) / rows_per_cta) < 4LL * num_sms()) rows_per_cta >>= 1;
+  p.rows_per_cta = rows_per_cta;
+  const size_t row_bytes = (size_t)a.ldp * sizeof(float);
+  const size_t fixed = 2 * row_bytes + 2 * 64 * sizeof(uint64_t);
+  int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
+  if (slots > 64) slots = 64;
+  if (slots > rows_per_cta) slots = rows_per_cta;
+  IMP_REQUIRE(slots >= 2, "sinkhorn: a row of %d floats does not fit the shared-memory ring", a.ldp);
+  p.ring_slots = slots;
+  const size_t smem = (size_t)slots * row_bytes + fixed;
+  static bool configured = false;
+  if (!configured) {
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
+    configured = true;
+  }
   dim3 grid((R + rows_per_cta - 1) / rows_per_cta, a.batch);
-  const size_t smem_col = 2 * (size_t)a.ldp * sizeof(float);
-  const size_t smem_fin = (size_t)((a.ldp + 1) & ~1) * sizeof(float) + (size_t)a.ldp * (sizeof(unsigned long long) + sizeof(float));
   float* col[3] = {a.colbuf, a.colbuf + (size_t)a.batch * a.ldp, a.colbuf + 2 * (size_t)a.batch * a.ldp};
   const int iters = a.iters;
   IMP_CUDA_OK(cudaMemsetAsync(col[0], 0, (size_t)a.batch * a.ldp * sizeof(float), st));
-  sk_init_kernel<NV><<<grid, SK_THREADS, smem_col, st>>>(a.dist, a.dist_batch_stride, a.ldd, a.bin_score, a.P,
-                                                          a.p_batch_stride, a.ldp, a.u, col[0], col[1], a.n0s, a.n1s,
-                                                          a.N0max, a.N1max, rows_per_cta, iters > 0 ? 1 : 0);
+  p.col_prev = nullptr;
+  p.col_acc = col[0];
+  p.col_zero = col[1];
+  p.do_iter = iters > 0 ? 1 : 0;
+  sk_ring_kernel<NV, SK_INIT><<<grid, SKR_THREADS, smem, st>>>(p);
   for (int k = 1; k < iters; ++k) {
-    sk_iter_kernel<NV><<<grid, SK_THREADS, smem_col, st>>>(a.P, a.p_batch_stride, a.ldp, col[(k - 1) % 3], col[k % 3],
-                                                            col[(k + 1) % 3], a.u, a.n0s, a.n1s, a.N0max, a.N1max,
-                                                            rows_per_cta);
+    p.col_prev = col[(k - 1) % 3];
+    p.col_acc = col[k % 3];
+    p.col_zero = col[(k + 1) % 3];
+    sk_ring_kernel<NV, SK_ITER><<<grid, SKR_THREADS, smem, st>>>(p);
   }
+  const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
   IMP_CUDA_OK(cudaMemsetAsync(a.col_key, 0, (size_t)a.batch * a.N1max * sizeof(unsigned long long), st));
   if (a.col_mass) IMP_CUDA_OK(cudaMemsetAsync(a.col_mass, 0, (size_t)a.batch * a.N1max * sizeof(float), st));
-  sk_final_kernel<NV><<<grid, SK_THREADS, smem_fin, st>>>(a.P, a.p_batch_stride, a.ldp,
-                                                           col[(iters > 0 ? iters - 1 : 0) % 3], a.u, iters > 0 ? 1 : 0,
-                                                           a.row_max, a.row_arg, reinterpret_cast<unsigned long long*>(a.col_key), a.row_mass, a.col_mass,
-                                                           a.n0s, a.n1s, a.N0max, a.N1max, rows_per_cta);
+  p.col_prev = col_last;
+  p.col_acc = nullptr;
+  p.col_zero = nullptr;
+  sk_ring_kernel<NV, SK_FINAL><<<grid, SKR_THREADS, smem, st>>>(p);
+  const int slab = 256;
+  sk_colmax_kernel<<<dim3((a.N1max + 127) / 128, (a.N0max + slab - 1) / slab, a.batch), 128, 0, st>>>(
+      a.P, a.p_batch_stride, a.ldp, a.u, col_last, a.write_scores, iters > 0 ? 1 : 0,
+      reinterpret_cast<unsigned long long*>(a.col_key), a.n0s, a.n1s, a.N0max, a.N1max, slab);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -362,12 +463,16 @@ int launch_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.batch > 0 && a.N0max > 0 && a.N1max > 0, "sinkhorn: empty problem");
   IMP_REQUIRE(a.ldp % 4 == 0 && a.ldp >= a.N1max + 1, "sinkhorn: ldp must be a multiple of 4 and >= N1+1");
   IMP_REQUIRE(a.iters >= 0, "sinkhorn: negative iteration count");
+  IMP_REQUIRE(a.ldd % 4 == 0 && a.ldd >= ((a.N1max + 3) & ~3) && a.dist_batch_stride % 4 == 0 &&
+                  (reinterpret_cast<uintptr_t>(a.dist) & 15) == 0 && (reinterpret_cast<uintptr_t>(a.P) & 15) == 0,
+              "sinkhorn: dist / P must be 16-byte aligned with row strides that are multiples of 4 floats "
+              "(ldd %d, N1 %d)", a.ldd, a.N1max);
   const int C = a.N1max + 1;
   if (C <= 4 * 32 * 5) return run_sinkhorn<5>(a, st);
   if (C <= 4 * 32 * 9) return run_sinkhorn<9>(a, st);
   if (C <= 4 * 32 * 17) return run_sinkhorn<17>(a, st);
-  if (C <= 4 * 32 * 33) return run_sinkhorn<33>(a, st);
-  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4 * 32 * 33 - 1);
+  if (C <= 4 * 32 * 25) return run_sinkhorn<25>(a, st);
+  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4 * 32 * 25 - 1);
   return 2;
 }
 

@@ -61,7 +61,8 @@ class AdaGMN(GM):
             eng.layer(st, 2 * ni + 1)
             update = ni >= self.first_it_to_update and self.sharing_layers[2 * ni]
             if st.key_ids is None:
-                _, i0, _, m0, _, sk = self._score(st, ni, p, keep_scores=False, want_mass=update)
+                _, i0, _, m0, _, sk = self._score(st, ni, p, keep_scores=False, want_mass=update,
+                                                  write_scores=(ni == nI - 1))
                 n0s = n1s = None
             else:
                 # Sinkhorn on the kept subsets: gather the projected descriptors of the kept tokens
@@ -76,7 +77,7 @@ class AdaGMN(GM):
                 eng.distance(st, Planes(yc.hi.view(-1, D), yc.lo.view(-1, D)), N0, N1, dist, ldd)
                 n0s, n1s = st.key_cnt[:B], st.key_cnt[B:]
                 _, i0c, _, m0c, _, sk = self._score_from_dist(dist, ldd, B, N0, N1, p, False, want_mass=update,
-                                                              n0s=n0s, n1s=n1s)
+                                                              n0s=n0s, n1s=n1s, write_scores=(ni == nI - 1))
                 i0 = torch.full((B, N0), -1, dtype=torch.int64, device=dev)
                 m0 = torch.zeros(B, N0, dtype=torch.float32, device=dev)
                 ops.scatter_matches(i0c, m0c, st.key_ids[:B], st.key_ids[B:], n0s, i0, m0)

@@ -143,7 +143,7 @@ class GM(nn.Module):
         ops.split_planes(desc.view(-1, D), out=ws.X, addend=ws.tok_f32)
         return RunState(ws, B, N0, N1, n_tok)
 
-    def _score(self, st: RunState, ni: int, p: float, keep_scores: bool, want_mass: bool = False):
+    def _score(self, st: RunState, ni: int, p: float, keep_scores: bool, want_mass: bool = False, write_scores=None):
         """final_proj -> dist -> Sinkhorn / dual-softmax -> mutual matches (nets/gm.py:290-320) on the full sets."""
         eng = self.engine()
         B, N0, N1 = st.B, st.N0, st.N1
@@ -152,7 +152,7 @@ class GM(nn.Module):
         ldd = (N1 + 7) // 8 * 8
         dist = self._dist_buffer(B, N0, ldd, dev)
         eng.distance(st, st.ws.Y, N0, N1, dist, ldd)
-        return self._score_from_dist(dist, ldd, B, N0, N1, p, keep_scores, want_mass)
+        return self._score_from_dist(dist, ldd, B, N0, N1, p, keep_scores, want_mass, write_scores=write_scores)
 
     def _dist_buffer(self, B, N0, ldd, dev):
         key = (B, N0, ldd, str(dev))
@@ -162,12 +162,16 @@ class GM(nn.Module):
         return self._dist
 
     def _score_from_dist(self, dist, ldd, B, N0, N1, p, keep_scores, want_mass=False, n0s=None, n1s=None,
-                         dist_batch_stride=None):
+                         dist_batch_stride=None, write_scores=None):
+        """keep_scores: the score matrix is handed to the caller (fresh buffer, final scaling written back);
+        otherwise the Sinkhorn only produces arg-max / masses and skips the write-back sweep."""
         dev = dist.device
+        if write_scores is None:
+            write_scores = keep_scores
         if self.with_sinkhorn:
             sk = self._sinkhorn_ws(B, N0, N1, dev, want_mass, fresh=keep_scores)
             ops.sinkhorn(dist, ldd, self.bin_score.data, self.sinkhorn_iterations, sk, n0s=n0s, n1s=n1s,
-                         dist_batch_stride=dist_batch_stride)
+                         dist_batch_stride=dist_batch_stride, write_scores=write_scores)
             i0, i1, m0, m1 = ops.matches(sk.row_max, sk.row_arg, sk.col_key, p, N0, N1, B, n0s=n0s, n1s=n1s)
             self._last_sk = sk
             return sk.scores(), i0, i1, m0, m1, sk

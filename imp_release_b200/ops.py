@@ -207,7 +207,7 @@ class SinkhornWorkspace:
 
 
 def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, ws: SinkhornWorkspace, n0s=None,
-             n1s=None, dist_batch_stride: Optional[int] = None):
+             n1s=None, dist_batch_stride: Optional[int] = None, write_scores: bool = True):
     a = SinkhornArgs()
     a.dist = ptr(dist)
     a.dist_batch_stride = dist_batch_stride if dist_batch_stride is not None else ws.N0max * ldd
@@ -219,9 +219,10 @@ def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, 
     a.row_mass, a.col_mass = ptr(ws.row_mass), ptr(ws.col_mass)
     a.n0s, a.n1s = ptr(n0s), ptr(n1s)
     a.N0max, a.N1max, a.batch = ws.N0max, ws.N1max, ws.batch
+    a.write_scores = int(write_scores)
     mat_bytes = 4.0 * ws.batch * (ws.N0max + 1) * (ws.N1max + 1)
     # algorithmic traffic: 2 sweeps per iteration + init (read dist, write p) + final (read, write)
-    with _Span('sinkhorn', 2 + max(iters - 1, 0), mat_bytes * (2 * iters + 4)):
+    with _Span('sinkhorn', 3 + max(iters - 1, 0), mat_bytes * (2 * iters + 4)):
         check(_lib.load().imp_sinkhorn(C.byref(a), stream_ptr()), 'imp_sinkhorn')
 
 

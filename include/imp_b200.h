@@ -98,7 +98,7 @@ IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const 
 
 /* ---- Sinkhorn optimal transport + fused arg-max, nets/layers.py:27-46 (sink_algorithm / sinkhorn) ----------- */
 typedef struct imp_sinkhorn_args {
-  const float* dist; /* [batch, N0max, ldd] */
+  const float* dist; /* [batch, N0max, ldd], 16-byte aligned, ldd and batch stride multiples of 4 floats */
   int64_t dist_batch_stride;
   int32_t ldd;
   int32_t iters;
@@ -115,7 +115,8 @@ typedef struct imp_sinkhorn_args {
   float* row_mass;   /* [batch, N0max] or NULL: sum_j scores[i, :N1] (pooling, nets/adgm.py:476) */
   float* col_mass;   /* [batch, N1max] or NULL */
   const int32_t *n0s, *n1s; /* per-sample sizes or NULL */
-  int32_t N0max, N1max, batch, _pad2;
+  int32_t N0max, N1max, batch;
+  int32_t write_scores; /* 1: store the final (p u) v into P; 0: P keeps softmax(M) and only arg-max / masses are produced */
 } imp_sinkhorn_args;
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
 

@@ -161,6 +161,12 @@ def test_sinkhorn_and_matches(B, N0, N1, iters):
     assert float((m0.cpu() - rm0).abs().max()) < 1e-5 and float((m1.cpu() - rm1).abs().max()) < 1e-5
     assert float((ws.row_mass.cpu() - ref[:, :-1, :-1].sum(-1)).abs().max()) < 1e-4
     assert float((ws.col_mass.cpu() - ref[:, :-1, :-1].sum(1)).abs().max()) < 1e-4
+    # arg-max only mode (no write-back of the scaled matrix): identical matches, P keeps softmax(M)
+    ws2 = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True)
+    ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws2, write_scores=False)
+    k0, k1, q0, q1 = ops.matches(ws2.row_max, ws2.row_arg, ws2.col_key, 0.2, N0, N1, B)
+    assert torch.equal(k0, i0) and torch.equal(k1, i1) and torch.equal(q0, m0)
+    assert float((ws2.row_mass - ws.row_mass).abs().max()) == 0.0
     # compute_matches on a caller-provided tensor
     rmx, rarg, ckey = ops.score_argmax(ws.scores(), N0, N1)
     j0, j1, n0, n1 = ops.matches(rmx, rarg, ckey, 0.1, N0, N1, B)
