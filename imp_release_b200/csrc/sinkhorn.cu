@@ -419,7 +419,10 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
   if (slots > 64) slots = 64;
   if (slots > rows_per_cta) slots = rows_per_cta;
-  IMP_REQUIRE(slots >= 2, "sinkhorn: a row of %d floats does not fit the shared-memory ring", a.ldp);
+  // Slot s must always be drained by the same consumer warp (row r -> warp r % 4, slot r % slots): otherwise a fast
+  // warp could run a whole lap ahead of a slow one and mis-read the phase parity of a barrier it has never seen.
+  slots = slots / SKR_CONSUMERS * SKR_CONSUMERS;
+  IMP_REQUIRE(slots >= SKR_CONSUMERS, "sinkhorn: a row of %d floats does not fit the shared-memory ring", a.ldp);
   p.ring_slots = slots;
   const size_t smem = (size_t)slots * row_bytes + fixed;
   static bool configured = false;

@@ -117,12 +117,13 @@ def test_full_size_properties():
     data = synth.make_pair_batch(seed=21, batch=2, n0=2000, n1=2000)
     with torch.no_grad():
         out = net.produce_matches(cuda(data), p=0.2, only_last=True)
-        st = net._last_sk
+        dist = torch.randn(2, 2000, 2000, device='cuda', generator=torch.Generator('cuda').manual_seed(5)) * 3
+        scores = net.compute_score(dist, net.bin_score, 20)
     i0 = out['indices0'][-1]
     valid = i0 >= 0
     assert int(valid.sum()) > 1000
-    cols = st.scores().sum(1)
-    assert float((cols[:, :-1] - 1).abs().max()) < 1e-4 and float((cols[:, -1] - 2001).abs().max()) < 1e-1
+    cols = scores.sum(1)
+    assert float((cols[:, :-1] - 1).abs().max()) < 1e-4 and float((cols[:, -1] - 2001).abs().max()) < 1e-1, "column marginals"
     for b in range(2):
         v = i0[b][i0[b] >= 0]
         assert v.numel() == v.unique().numel()                                                  # injective

@@ -137,7 +137,8 @@ def test_attention_self_cross_shared(Nq, Nk, nq, nk):
             assert abs(float(cs[img, :nk_i].sum()) - 4 * nq_i) / (4 * nq_i) < 1e-3
 
 
-@pytest.mark.parametrize('B,N0,N1,iters', [(1, 512, 512, 20), (2, 300, 260, 20), (1, 2000, 2000, 20), (3, 37, 1100, 5), (1, 130, 70, 0), (1, 2047, 2047, 100)])
+@pytest.mark.parametrize('B,N0,N1,iters', [(1, 512, 512, 20), (2, 300, 260, 20), (1, 2000, 2000, 20), (3, 37, 1100, 5), (1, 130, 70, 0), (1, 2047, 2047, 100),
+                                           (40, 700, 650, 20), (24, 1500, 1490, 3)])
 def test_sinkhorn_and_matches(B, N0, N1, iters):
     g = torch.Generator().manual_seed(100 + N0)
     dist = torch.randn(B, N0, N1, generator=g) * 3
@@ -165,8 +166,9 @@ def test_sinkhorn_and_matches(B, N0, N1, iters):
     ws2 = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True)
     ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws2, write_scores=False)
     k0, k1, q0, q1 = ops.matches(ws2.row_max, ws2.row_arg, ws2.col_key, 0.2, N0, N1, B)
-    assert torch.equal(k0, i0) and torch.equal(k1, i1) and torch.equal(q0, m0)
-    assert float((ws2.row_mass - ws.row_mass).abs().max()) == 0.0
+    # (column sums are accumulated with float atomics, so two runs agree to rounding, not bit-for-bit)
+    assert torch.equal(k0, i0) and torch.equal(k1, i1) and float((q0 - m0).abs().max()) < 1e-6
+    assert float((ws2.row_mass - ws.row_mass).abs().max()) < 1e-5
     # compute_matches on a caller-provided tensor
     rmx, rarg, ckey = ops.score_argmax(ws.scores(), N0, N1)
     j0, j1, n0, n1 = ops.matches(rmx, rarg, ckey, 0.1, N0, N1, B)
