@@ -1,8 +1,9 @@
-// tcgen05 split-precision GEMM (see gemm.cuh).  One 128 x BN output tile per CTA:
-//   warp 0  : TMA producer  (hi/lo planes of A and B, 64-wide K slabs, 128B swizzle)
-//   warp 1  : UMMA issuer   (one elected lane; accumulator 128 lanes x BN columns of TMEM)
+// tcgen05 split-precision GEMM (see gemm.cuh).  Persistent: one CTA per SM walks over 128 x BN output tiles.
+//   warp 0  : TMA producer  (hi/lo planes of A and B, 64-wide K slabs, 128B swizzle; the smem ring runs across tiles)
+//   warp 1  : UMMA issuer   (one elected lane; two accumulators of 128 lanes x BN TMEM columns, ping-pong)
 //   warp 2  : TMEM allocator
-//   warps 4-7: epilogue     (tcgen05.ld, bias / residual / hi-lo split, vectorised global stores)
+//   warps 4-7: epilogue     (tcgen05.ld, bias / residual / hi-lo split, vectorised global stores) -- drains
+//             accumulator t while the tensor core already works on tile t+1
 #include "gemm.cuh"
 
 #include "common.h"
@@ -16,6 +17,7 @@ static constexpr int GEMM_THREADS = 256;
 
 struct GemmKernelParams {
   int M, N, KB1, KB, b_batched, nsplit, out_mode;
+  int tiles_n, tiles_m, tiles_total;
   float alpha;
   const float* bias;
   void *out0, *out1;
@@ -37,17 +39,16 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                      const GemmKernelParams p) {
   using S = GemmSmem<BN>;
+  constexpr int ACC = (2 * BN <= 512) ? 2 : 1;  // accumulator buffers in TMEM
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * S::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [ACC]
+  uint64_t* tmem_empty_bar = tmem_full_bar + ACC;  // [ACC]
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
 
   const int warp = threadIdx.x >> 5;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * GEMM_BM;
-  const int z = blockIdx.z;
   const bool split = p.nsplit == 3;
 
   if (warp == 0 && elect_one()) {
@@ -63,11 +64,14 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < ACC; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_ptr_smem, BN);
+    tmem_alloc(tmem_ptr_smem, ACC * BN);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -75,160 +79,201 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
 
+  // tile t -> (n tile fastest, then m tile, then batch): CTAs running side by side share the A tile in L2
+  auto tile_coords = [&](int t, int& m0, int& n0, int& z) {
+    const int per_z = p.tiles_n * p.tiles_m;
+    z = t / per_z;
+    const int r = t - z * per_z;
+    m0 = (r / p.tiles_n) * GEMM_BM;
+    n0 = (r % p.tiles_n) * BN;
+  };
+
   if (warp == 0) {
     if (elect_one()) {
       const uint32_t tx = split ? S::STAGE_BYTES : (S::A_BYTES + S::B_BYTES);
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&empty_bar[s], ((kb / STAGES) & 1) ^ 1);
-        uint8_t* st = smem + s * S::STAGE_BYTES;
-        mbar_arrive_expect_tx(&full_bar[s], tx);
-        const bool seg2 = kb >= p.KB1;
-        const int ka = (seg2 ? kb - p.KB1 : kb) * GEMM_BK;
-        tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
-        tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * GEMM_BK, n0, p.b_batched ? z : 0);
-        if (split) {
-          tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
-          tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * GEMM_BK, n0,
-                      p.b_batched ? z : 0);
+      int it = 0;  // running k-block counter across tiles
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[s], tx);
+          const bool seg2 = kb >= p.KB1;
+          const int ka = (seg2 ? kb - p.KB1 : kb) * GEMM_BK;
+          tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
+          tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * GEMM_BK, n0, p.b_batched ? z : 0);
+          if (split) {
+            tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
+            tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * GEMM_BK, n0,
+                        p.b_batched ? z : 0);
+          }
         }
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
       constexpr uint32_t idesc = make_idesc(FMT_F16, GEMM_BM, BN, 0, 0);
-      for (int kb = 0; kb < p.KB; ++kb) {
-        const int s = kb % STAGES;
-        mbar_wait(&full_bar[s], (kb / STAGES) & 1);
+      int it = 0, lt = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++lt) {
+        const int a = lt % ACC;
+        mbar_wait(&tmem_empty_bar[a], ((lt / ACC) & 1) ^ 1);  // the epilogue has drained this accumulator
         tc_fence_after();
-        const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
-        const uint32_t a_lo = a_hi + S::A_BYTES;
-        const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
-        const uint32_t b_lo = b_hi + S::B_BYTES;
+        const uint32_t d_tmem = tmem_base + a * BN;
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
+          const uint32_t a_lo = a_hi + S::A_BYTES;
+          const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
+          const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-        for (int k = 0; k < GEMM_BK / 16; ++k) {
-          const uint32_t off = k * 32;  // 16 fp16 along K inside the swizzle span
-          const uint64_t dah = make_smem_desc_sw128(a_hi + off, 16, 1024);
-          const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 16, 1024);
-          umma_f16_ss(tmem_base, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-          if (split) {
-            const uint64_t dal = make_smem_desc_sw128(a_lo + off, 16, 1024);
-            const uint64_t dbl = make_smem_desc_sw128(b_lo + off, 16, 1024);
-            umma_f16_ss(tmem_base, dal, dbh, idesc, 1u);
-            umma_f16_ss(tmem_base, dah, dbl, idesc, 1u);
+          for (int k = 0; k < GEMM_BK / 16; ++k) {
+            const uint32_t off = k * 32;  // 16 fp16 along K inside the swizzle span
+            const uint64_t dah = make_smem_desc_sw128(a_hi + off, 16, 1024);
+            const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 16, 1024);
+            umma_f16_ss(d_tmem, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            if (split) {
+              const uint64_t dal = make_smem_desc_sw128(a_lo + off, 16, 1024);
+              const uint64_t dbl = make_smem_desc_sw128(b_lo + off, 16, 1024);
+              umma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
+              umma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
+            }
           }
+          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        umma_commit(&tmem_full_bar[a]);
       }
-      umma_commit(tmem_full_bar);
     }
   } else if (warp >= 4) {
     const int q = warp & 3;  // TMEM lane quarter this warp may touch
     const int row = q * 32 + lane_id();
-    const long long gm = m0 + row;
-    const bool row_ok = gm < p.M;
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t t_row = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const long long obase = (long long)z * p.out_batch_stride + gm * p.out_row_stride;
+    int lt = 0;
+    for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++lt) {
+      int m0, n0, z;
+      tile_coords(t, m0, n0, z);
+      const int a = lt % ACC;
+      const long long gm = m0 + row;
+      const bool row_ok = gm < p.M;
+      mbar_wait(&tmem_full_bar[a], (lt / ACC) & 1);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + a * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const long long obase = (long long)z * p.out_batch_stride + gm * p.out_row_stride;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      const int nc = n0 + c * 32;
-      if (nc >= p.N) break;  // warp-uniform
-      uint32_t r[32];
-      tmem_ld_x32(t_row + c * 32, r);
-      tmem_wait_ld();
-      float v[32];
+      for (int c = 0; c < BN / 32; ++c) {
+        const int nc = n0 + c * 32;
+        if (nc >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld_x32(t_row + c * 32, r);
+        tmem_wait_ld();
+        float v[32];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
-      const bool full = nc + 32 <= p.N;
-      if (p.bias != nullptr) {
+        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        const bool full = nc + 32 <= p.N;
+        if (p.bias != nullptr) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
-      }
-      if (!row_ok) continue;
-      if (p.out_mode == GEMM_OUT_F32) {
-        float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
-        if (full) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4)
-            *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        } else {
-          for (int j = 0; j < 32 && nc + j < p.N; ++j) o[j] = v[j];
+          for (int j = 0; j < 32; ++j)
+            if (full || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
         }
-      } else if (p.out_mode == GEMM_OUT_F16) {
-        __half* o = reinterpret_cast<__half*>(p.out0) + obase + nc;
-        if (full) {
+        if (!row_ok) continue;
+        if (p.out_mode == GEMM_OUT_F32) {
+          float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
+          if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 pk;
-            pk.x = pack_half2(v[j], v[j + 1]);
-            pk.y = pack_half2(v[j + 2], v[j + 3]);
-            pk.z = pack_half2(v[j + 4], v[j + 5]);
-            pk.w = pack_half2(v[j + 6], v[j + 7]);
-            *reinterpret_cast<uint4*>(o + j) = pk;
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) o[j] = v[j];
           }
-        } else {
-          for (int j = 0; j < 32 && nc + j < p.N; ++j) o[j] = __float2half_rn(v[j]);
-        }
-      } else {
-        __half* oh = reinterpret_cast<__half*>(p.out0) + obase + nc;
-        __half* ol = reinterpret_cast<__half*>(p.out1) + obase + nc;
-        if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
-          const __half* rh = p.res_hi + obase + nc;
-          const __half* rl = p.res_lo + obase + nc;
+        } else if (p.out_mode == GEMM_OUT_F16) {
+          __half* o = reinterpret_cast<__half*>(p.out0) + obase + nc;
           if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
-              const uint4 a = *reinterpret_cast<const uint4*>(rh + j);
-              const uint4 b = *reinterpret_cast<const uint4*>(rl + j);
-              const __half2* ah = reinterpret_cast<const __half2*>(&a);
-              const __half2* bh = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-              for (int t = 0; t < 4; ++t) {
-                const float2 fa = __half22float2(ah[t]);
-                const float2 fb = __half22float2(bh[t]);
-                v[j + 2 * t] += fa.x + fb.x;
-                v[j + 2 * t + 1] += fa.y + fb.y;
-              }
+              uint4 pk;
+              pk.x = pack_half2(v[j], v[j + 1]);
+              pk.y = pack_half2(v[j + 2], v[j + 3]);
+              pk.z = pack_half2(v[j + 4], v[j + 5]);
+              pk.w = pack_half2(v[j + 6], v[j + 7]);
+              *reinterpret_cast<uint4*>(o + j) = pk;
             }
           } else {
-            for (int j = 0; j < 32 && nc + j < p.N; ++j) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
-          }
-        }
-        if (full) {
 #pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint32_t hi[4], lo[4];
-#pragma unroll
-            for (int t = 0; t < 4; ++t) {
-              __half h0, l0, h1, l1;
-              split_f16x2(v[j + 2 * t], h0, l0);
-              split_f16x2(v[j + 2 * t + 1], h1, l1);
-              __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-              hi[t] = *reinterpret_cast<uint32_t*>(&hh);
-              lo[t] = *reinterpret_cast<uint32_t*>(&ll);
-            }
-            *reinterpret_cast<uint4*>(oh + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-            *reinterpret_cast<uint4*>(ol + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            for (int j = 0; j < 32; ++j)
+              if (nc + j < p.N) o[j] = __float2half_rn(v[j]);
           }
         } else {
-          for (int j = 0; j < 32 && nc + j < p.N; ++j) {
-            __half h, l;
-            split_f16x2(v[j], h, l);
-            oh[j] = h;
-            ol[j] = l;
+          __half* oh = reinterpret_cast<__half*>(p.out0) + obase + nc;
+          __half* ol = reinterpret_cast<__half*>(p.out1) + obase + nc;
+          if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
+            const __half* rh = p.res_hi + obase + nc;
+            const __half* rl = p.res_lo + obase + nc;
+            if (full) {
+              uint4 ra[4], rb[4];
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {  // issue all residual loads before using any
+                ra[j] = *reinterpret_cast<const uint4*>(rh + 8 * j);
+                rb[j] = *reinterpret_cast<const uint4*>(rl + 8 * j);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const __half2* ah = reinterpret_cast<const __half2*>(&ra[j]);
+                const __half2* bh = reinterpret_cast<const __half2*>(&rb[j]);
+#pragma unroll
+                for (int t2 = 0; t2 < 4; ++t2) {
+                  const float2 fa = __half22float2(ah[t2]);
+                  const float2 fb = __half22float2(bh[t2]);
+                  v[8 * j + 2 * t2] += fa.x + fb.x;
+                  v[8 * j + 2 * t2 + 1] += fa.y + fb.y;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (nc + j < p.N) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
+            }
+          }
+          if (full) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              uint32_t hi[4], lo[4];
+#pragma unroll
+              for (int t2 = 0; t2 < 4; ++t2) {
+                __half h0, l0, h1, l1;
+                split_f16x2(v[j + 2 * t2], h0, l0);
+                split_f16x2(v[j + 2 * t2 + 1], h1, l1);
+                __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+                hi[t2] = *reinterpret_cast<uint32_t*>(&hh);
+                lo[t2] = *reinterpret_cast<uint32_t*>(&ll);
+              }
+              *reinterpret_cast<uint4*>(oh + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(ol + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (nc + j < p.N) {
+                __half h, l;
+                split_f16x2(v[j], h, l);
+                oh[j] = h;
+                ol[j] = l;
+              }
+            }
           }
         }
       }
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[a]);  // 128 arrivals: the accumulator may be overwritten
     }
-    tc_fence_before();
   }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, BN);
+    tmem_dealloc(tmem_base, ACC * BN);
   }
 }
 
@@ -277,7 +322,10 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
     IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((g.N + BN - 1) / BN, (g.M + GEMM_BM - 1) / GEMM_BM, g.batch);
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_total = p.tiles_n * p.tiles_m * g.batch;
+  const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo, p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -25,7 +25,7 @@ namespace imp {
 static constexpr float SK_EPS = 1e-8f;
 static constexpr int SKR_CONSUMERS = 4;
 static constexpr int SKR_THREADS = (SKR_CONSUMERS + 1) * 32;  // + one producer warp
-static constexpr int SKR_SMEM_BUDGET = 110 * 1024;            // two CTAs per SM
+static constexpr int SKR_SMEM_BUDGET = 113 * 1024;            // two CTAs per SM (228 KB - 2 x 1 KB reserved)
 
 struct SkDims {
   int R, C;  // augmented rows / cols of this sample
