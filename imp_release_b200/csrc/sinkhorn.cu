@@ -16,6 +16,7 @@
 #include "sinkhorn.cuh"
 
 #include <float.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -389,42 +390,26 @@ __global__ void sk_matches_kernel(const float* __restrict__ row_max, const int* 
   }
 }
 
+// L2-resident chunking: a 2001 x 2004 fp32 matrix is 16 MB, the B200 L2 is 126 MB.  Sweeping all matrices of a big
+// batch in every launch streams the whole batch from HBM 22 times; instead the batch is cut into chunks that fit in
+// L2 and the whole 22-launch sequence runs per chunk, so that after the first sweep the matrices are re-read from L2.
+static int sk_chunk_matrices(size_t matrix_bytes, int batch) {
+  static long budget_mb = -1;
+  if (budget_mb < 0) {
+    const char* e = getenv("IMP_SK_L2_MB");
+    budget_mb = e ? atol(e) : 80;
+  }
+  if (budget_mb == 0) return batch;  // chunking disabled
+  long c = (long)((size_t)budget_mb * 1024 * 1024 / matrix_bytes);
+  if (c < 1) c = 1;
+  return c > batch ? batch : (int)c;
+}
+
 template <int NV>
 static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   const int R = a.N0max + 1;
-  SkParams p;
-  p.dist = a.dist;
-  p.dist_bs = a.dist_batch_stride;
-  p.ldd = a.ldd;
-  p.bin_score = a.bin_score;
-  p.P = a.P;
-  p.p_bs = a.p_batch_stride;
-  p.ldp = a.ldp;
-  p.u = a.u;
-  p.row_max = a.row_max;
-  p.row_arg = a.row_arg;
-  p.row_mass = a.row_mass;
-  p.col_mass = a.col_mass;
-  p.n0s = a.n0s;
-  p.n1s = a.n1s;
-  p.N0max = a.N0max;
-  p.N1max = a.N1max;
-  p.write_scores = a.write_scores;
-  // a CTA owns up to 128 consecutive rows of one matrix; shrink the blocks until there are >= 4 CTAs per SM
-  int rows_per_cta = 128;
-  while (rows_per_cta > 8 && (long long)a.batch * ((R + rows_per_cta - 1) / rows_per_cta) < 4LL * num_sms()) rows_per_cta >>= 1;
-  p.rows_per_cta = rows_per_cta;
   const size_t row_bytes = (size_t)a.ldp * sizeof(float);
   const size_t fixed = 2 * row_bytes + 2 * 64 * sizeof(uint64_t);
-  int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
-  if (slots > 64) slots = 64;
-  if (slots > rows_per_cta) slots = rows_per_cta;
-  // Slot s must always be drained by the same consumer warp (row r -> warp r % 4, slot r % slots): otherwise a fast
-  // warp could run a whole lap ahead of a slow one and mis-read the phase parity of a barrier it has never seen.
-  slots = slots / SKR_CONSUMERS * SKR_CONSUMERS;
-  IMP_REQUIRE(slots >= SKR_CONSUMERS, "sinkhorn: a row of %d floats does not fit the shared-memory ring", a.ldp);
-  p.ring_slots = slots;
-  const size_t smem = (size_t)slots * row_bytes + fixed;
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
@@ -432,32 +417,71 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
     configured = true;
   }
-  dim3 grid((R + rows_per_cta - 1) / rows_per_cta, a.batch);
-  float* col[3] = {a.colbuf, a.colbuf + (size_t)a.batch * a.ldp, a.colbuf + 2 * (size_t)a.batch * a.ldp};
+  const int chunk = sk_chunk_matrices((size_t)R * row_bytes, a.batch);
   const int iters = a.iters;
-  IMP_CUDA_OK(cudaMemsetAsync(col[0], 0, (size_t)a.batch * a.ldp * sizeof(float), st));
-  p.col_prev = nullptr;
-  p.col_acc = col[0];
-  p.col_zero = col[1];
-  p.do_iter = iters > 0 ? 1 : 0;
-  sk_ring_kernel<NV, SK_INIT><<<grid, SKR_THREADS, smem, st>>>(p);
-  for (int k = 1; k < iters; ++k) {
-    p.col_prev = col[(k - 1) % 3];
-    p.col_acc = col[k % 3];
-    p.col_zero = col[(k + 1) % 3];
-    sk_ring_kernel<NV, SK_ITER><<<grid, SKR_THREADS, smem, st>>>(p);
-  }
-  const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
   IMP_CUDA_OK(cudaMemsetAsync(a.col_key, 0, (size_t)a.batch * a.N1max * sizeof(unsigned long long), st));
   if (a.col_mass) IMP_CUDA_OK(cudaMemsetAsync(a.col_mass, 0, (size_t)a.batch * a.N1max * sizeof(float), st));
-  p.col_prev = col_last;
-  p.col_acc = nullptr;
-  p.col_zero = nullptr;
-  sk_ring_kernel<NV, SK_FINAL><<<grid, SKR_THREADS, smem, st>>>(p);
-  const int slab = 256;
-  sk_colmax_kernel<<<dim3((a.N1max + 127) / 128, (a.N0max + slab - 1) / slab, a.batch), 128, 0, st>>>(
-      a.P, a.p_batch_stride, a.ldp, a.u, col_last, a.write_scores, iters > 0 ? 1 : 0,
-      reinterpret_cast<unsigned long long*>(a.col_key), a.n0s, a.n1s, a.N0max, a.N1max, slab);
+  IMP_CUDA_OK(cudaMemsetAsync(a.colbuf, 0, (size_t)a.batch * a.ldp * sizeof(float), st));  // col[0]
+
+  for (int b0 = 0; b0 < a.batch; b0 += chunk) {
+    const int nb = (a.batch - b0 < chunk) ? a.batch - b0 : chunk;
+    SkParams p;
+    p.dist = a.dist + (long long)b0 * a.dist_batch_stride;
+    p.dist_bs = a.dist_batch_stride;
+    p.ldd = a.ldd;
+    p.bin_score = a.bin_score;
+    p.P = a.P + (long long)b0 * a.p_batch_stride;
+    p.p_bs = a.p_batch_stride;
+    p.ldp = a.ldp;
+    p.u = a.u + (long long)b0 * (a.N0max + 1);
+    p.row_max = a.row_max + (long long)b0 * a.N0max;
+    p.row_arg = a.row_arg + (long long)b0 * a.N0max;
+    p.row_mass = a.row_mass ? a.row_mass + (long long)b0 * a.N0max : nullptr;
+    p.col_mass = a.col_mass ? a.col_mass + (long long)b0 * a.N1max : nullptr;
+    p.n0s = a.n0s ? a.n0s + b0 : nullptr;
+    p.n1s = a.n1s ? a.n1s + b0 : nullptr;
+    p.N0max = a.N0max;
+    p.N1max = a.N1max;
+    p.write_scores = a.write_scores;
+    // rows per CTA: aim at one resident wave (2 CTAs per SM), a multiple of the consumer-warp count, 8..128 rows
+    int rows_per_cta = (int)(((long long)nb * R + 2LL * num_sms() - 1) / (2LL * num_sms()));
+    rows_per_cta = (rows_per_cta + SKR_CONSUMERS - 1) / SKR_CONSUMERS * SKR_CONSUMERS;
+    if (rows_per_cta < 8) rows_per_cta = 8;
+    if (rows_per_cta > 128) rows_per_cta = 128;
+    p.rows_per_cta = rows_per_cta;
+    int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
+    if (slots > 64) slots = 64;
+    if (slots > rows_per_cta) slots = rows_per_cta;
+    // Slot s must always be drained by the same consumer warp (row r -> warp r % 4, slot r % slots): otherwise a fast
+    // warp could run a whole lap ahead of a slow one and mis-read the phase parity of a barrier it has never seen.
+    slots = slots / SKR_CONSUMERS * SKR_CONSUMERS;
+    IMP_REQUIRE(slots >= SKR_CONSUMERS, "sinkhorn: a row of %d floats does not fit the shared-memory ring", a.ldp);
+    p.ring_slots = slots;
+    const size_t smem = (size_t)slots * row_bytes + fixed;
+    dim3 grid((R + rows_per_cta - 1) / rows_per_cta, nb);
+    float* col[3] = {a.colbuf + (size_t)b0 * a.ldp, a.colbuf + ((size_t)a.batch + b0) * a.ldp,
+                     a.colbuf + (2 * (size_t)a.batch + b0) * a.ldp};
+    p.col_prev = nullptr;
+    p.col_acc = col[0];
+    p.col_zero = col[1];
+    p.do_iter = iters > 0 ? 1 : 0;
+    sk_ring_kernel<NV, SK_INIT><<<grid, SKR_THREADS, smem, st>>>(p);
+    for (int k = 1; k < iters; ++k) {
+      p.col_prev = col[(k - 1) % 3];
+      p.col_acc = col[k % 3];
+      p.col_zero = col[(k + 1) % 3];
+      sk_ring_kernel<NV, SK_ITER><<<grid, SKR_THREADS, smem, st>>>(p);
+    }
+    const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
+    p.col_prev = col_last;
+    p.col_acc = nullptr;
+    p.col_zero = nullptr;
+    sk_ring_kernel<NV, SK_FINAL><<<grid, SKR_THREADS, smem, st>>>(p);
+    const int slab = 256;
+    sk_colmax_kernel<<<dim3((a.N1max + 127) / 128, (a.N0max + slab - 1) / slab, nb), 128, 0, st>>>(
+        p.P, a.p_batch_stride, a.ldp, p.u, col_last, a.write_scores, iters > 0 ? 1 : 0,
+        reinterpret_cast<unsigned long long*>(a.col_key) + (size_t)b0 * a.N1max, p.n0s, p.n1s, a.N0max, a.N1max, slab);
+  }
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
