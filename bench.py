@@ -91,6 +91,19 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
 
 
+def host_cores() -> int:
+    """Usable host cores: affinity mask capped by the cgroup CPU quota (os.cpu_count() over-reports in containers)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, 'sched_getaffinity') else (os.cpu_count() or 1)
+    try:
+        with open('/sys/fs/cgroup/cpu.max') as f:
+            q, per = f.read().split()
+        if q != 'max':
+            n = max(1, min(n, int(float(q) / float(per) + 0.5)))
+    except Exception:
+        pass
+    return max(1, n)
+
+
 def attention_flops_per_pair(n, iters):
     from oracle.imp_oracle import attention_flops
     return attention_flops(n, n, iters)
@@ -116,7 +129,7 @@ def cpu_reference_step(n_pairs=1, n=N_KPTS, iters=N_ITERS, repeats=1, seed=1):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     cores = torch.get_num_threads()
     for _ in range(min(args.warmup, 1)):
         cpu_reference_step()
@@ -270,7 +283,7 @@ def run_gpu(args, rank, world, local_rank):
             if r['kernel'] in t:
                 r['traffic'] = t[r['kernel']]
 
-    torch.set_num_threads(os.cpu_count() or 1)
+    torch.set_num_threads(host_cores())
     cpu_s = cpu_reference_step(repeats=2) if world == 1 and not args.no_cpu_baseline else None
     cpu_baseline = None
     if cpu_s is not None:
