@@ -1,13 +1,14 @@
 // Flash-style multi-head attention for sm_100a (see attention.cuh).  One CTA = 128 query rows of one head of one
 // image; keys stream through in tiles of 128.
 //   warp 0    : TMA producer (Q once; K/V tiles into a 4-deep ring, 128B swizzle)
-//   warp 1    : UMMA issuer  S = Q K^T (SS, fp16, fp32 accum in TMEM, two S buffers) and O += P V (P from TMEM,
-//               V consumed token-major as an MN-major B operand); also owns the TMEM allocation
+//   warp 1    : UMMA issuer  S = Q K^T (SS, fp16, fp32 accum in TMEM) and O += P V (P from TMEM, V consumed
+//               token-major as an MN-major B operand); also owns the TMEM allocation
 //   warps 2-5 : softmax.  TMEM lane == query row, so a thread owns a whole score row: row max / sum need no
 //               shuffles.  exp2 with the 1/8*log2(e) scale folded into one FFMA, lazy rescaling of O (only when the
 //               running max grows by > 2^8), P written back to TMEM as packed fp16 over the S columns.
-// S(j+1) is issued before P(j) is awaited, so the tensor core computes the next score tile while the softmax warps
-// work on the current one.
+// The kernel is bound by the softmax (MUFU ex2 + issue slots), not by the tensor pipe, so a CTA keeps ONE score
+// buffer (256 TMEM columns, 112 KB smem) and TWO CTAs share an SM: while one CTA's softmax warps work, the other
+// CTA's MMAs run, and each SM sub-partition always has two softmax warps to switch between.
 #include "attention.cuh"
 
 #include <math.h>
@@ -22,12 +23,12 @@ static constexpr int AT_BN = 128;
 static constexpr int AT_D = 64;
 static constexpr int AT_HEADS = 4;
 static constexpr int AT_C = AT_D * AT_HEADS;
-static constexpr int AT_STAGES = 4;
+static constexpr int AT_STAGES = 3;
 static constexpr int AT_THREADS = 192;
 static constexpr int AT_TILE_BYTES = AT_BN * AT_D * 2;  // 16 KB (Q, K and V tiles alike)
-static constexpr uint32_t AT_TMEM_COLS = 512;
-static constexpr uint32_t AT_COL_S = 0;    // two score buffers of 128 fp32 columns (P aliases the first 64)
-static constexpr uint32_t AT_COL_O = 256;  // 64 fp32 columns
+static constexpr uint32_t AT_TMEM_COLS = 256;
+static constexpr uint32_t AT_COL_S = 0;    // score tile, 128 fp32 columns (P aliases the first 64)
+static constexpr uint32_t AT_COL_O = 128;  // 64 fp32 columns
 static constexpr float AT_SCALE_LOG2 = 0.125f * 1.4426950408889634f;
 static constexpr float AT_RESCALE_TAU = 8.0f;
 
@@ -39,22 +40,22 @@ struct AttnKernelParams {
   long long out_img_stride;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 1)
+__global__ void __launch_bounds__(AT_THREADS, 2)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
   uint8_t* s_q = smem;
   uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K at +0, V at +16 KB
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + AT_STAGES * 2 * AT_TILE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES;  // [2]
-  uint64_t* p_full = s_full + 2;            // [2]
-  uint64_t* o_done = p_full + 2;
+  uint64_t* s_full = kv_empty + AT_STAGES;
+  uint64_t* p_full = s_full + 1;
+  uint64_t* o_done = p_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
 
+  if (smem_u32(smem) & 1023u) __trap();
   const int warp = threadIdx.x >> 5;
   const int q0 = blockIdx.x * AT_BM;
   const int h = blockIdx.y;
@@ -74,10 +75,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 128);
-    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
@@ -110,32 +109,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       constexpr uint32_t idesc_qk = make_idesc(FMT_F16, AT_BM, AT_BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(FMT_F16, AT_BM, AT_D, 0, 1);  // B = V, MN-major
       const uint32_t q_addr = smem_u32(s_q);
-      auto issue_qk = [&](int j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_full[s], (j / AT_STAGES) & 1);
+      mbar_wait(q_full, 0);
+      for (int j = 0; j < T; ++j) {
+        const int st = j % AT_STAGES;
+        mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + s * 2 * AT_TILE_BYTES);
-        const uint32_t d = tmem_base + AT_COL_S + (j & 1) * AT_BN;
+        const uint32_t k_addr = smem_u32(s_kv + st * 2 * AT_TILE_BYTES);
+        const uint32_t v_addr = k_addr + AT_TILE_BYTES;
+        // S = Q K^T.  The tensor pipe executes MMAs in issue order, so this overwrites the score columns only after
+        // O += P(j-1) V(j-1), which read P from the same columns, has drained.
 #pragma unroll
         for (int kk = 0; kk < AT_D / 16; ++kk)
-          umma_f16_ss(d, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
+          umma_f16_ss(tmem_base + AT_COL_S, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
                       make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-      };
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
+        umma_commit(s_full);
+        mbar_wait(p_full, j & 1);
         tc_fence_after();
-        const int s = j % AT_STAGES;
-        const uint32_t v_addr = smem_u32(s_kv + s * 2 * AT_TILE_BYTES + AT_TILE_BYTES);
-        const uint32_t a_tmem = tmem_base + AT_COL_S + (j & 1) * AT_BN;
 #pragma unroll
         for (int kk = 0; kk < AT_BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
-          umma_f16_ts(tmem_base + AT_COL_O, a_tmem + kk * 8, make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024),
-                      idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[s]);
+          umma_f16_ts(tmem_base + AT_COL_O, tmem_base + AT_COL_S + kk * 8,
+                      make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(&kv_empty[st]);
         umma_commit(o_done);
       }
     }
@@ -150,27 +144,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     float lse_in = 0.f;
     if (p.shared && row_ok) lse_in = p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow];
 
+    const uint32_t s_addr = tmem_base + lane_off + AT_COL_S;
     for (int j = 0; j < T; ++j) {
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
+      mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const uint32_t s_addr = tmem_base + lane_off + AT_COL_S + (j & 1) * AT_BN;
-      uint32_t r[AT_BN];
-      tmem_ld_x32(s_addr, r);
-      tmem_ld_x32(s_addr + 32, r + 32);
-      tmem_ld_x32(s_addr + 64, r + 64);
-      tmem_ld_x32(s_addr + 96, r + 96);
-      tmem_wait_ld();
       const int kbase = j * AT_BN;
-      if (kbase + AT_BN > nk) {  // ragged last tile: keys beyond nk do not exist
-#pragma unroll
-        for (int c = 0; c < AT_BN; ++c)
-          if (kbase + c >= nk) r[c] = 0xff800000u;  // -inf
-      }
+      const int nvalid = nk - kbase;  // keys of this tile that exist (>= 128 except for the ragged last tile)
       float neg_ref;
       if (!p.shared) {
+        // pass 1: row max (the score row is re-read from TMEM in pass 2 instead of living in 128 registers)
         float mx = -INFINITY;
 #pragma unroll
-        for (int c = 0; c < AT_BN; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+        for (int cb = 0; cb < AT_BN; cb += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(s_addr + cb, r);
+          tmem_wait_ld();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (cb + c < nvalid) ? __uint_as_float(r[c]) : -INFINITY);
+        }
         const float m_new = fmaxf(m_run, mx * AT_SCALE_LOG2);
         const bool need = m_new > m_run + AT_RESCALE_TAU;  // first tile: m_run = -inf
         const bool any = __any_sync(0xffffffffu, need);
@@ -185,15 +176,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             m_run = m_new;
           }
           if (j > 0) {
-            uint32_t o[AT_D];
             const uint32_t o_addr = tmem_base + lane_off + AT_COL_O;
-            tmem_ld_x32(o_addr, o);
-            tmem_ld_x32(o_addr + 32, o + 32);
-            tmem_wait_ld();
 #pragma unroll
-            for (int c = 0; c < AT_D; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-            tmem_st_x32(o_addr, o);
-            tmem_st_x32(o_addr + 32, o + 32);
+            for (int cb = 0; cb < AT_D; cb += 32) {
+              uint32_t o[32];
+              tmem_ld_x32(o_addr + cb, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
+              tmem_st_x32(o_addr + cb, o);
+            }
           }
         }
         neg_ref = -m_run;
@@ -204,21 +196,30 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         neg_ref = -lse_in;
       }
-      uint32_t pk[AT_BN / 2];
+      // pass 2: p = exp2(s * c - ref), packed fp16 written over the score columns (chunk cb lands in columns
+      // [cb/2, cb/2+16), which this thread has already consumed)
       float lsum = 0.f;
 #pragma unroll
-      for (int c = 0; c < AT_BN; c += 2) {
-        const float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
-        const float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
-        lsum += p0 + p1;
-        pk[c >> 1] = pack_half2(p0, p1);
+      for (int cb = 0; cb < AT_BN; cb += 32) {
+        uint32_t r[32];
+        tmem_ld_x32(s_addr + cb, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+          p0 = (cb + c < nvalid) ? p0 : 0.f;
+          p1 = (cb + c + 1 < nvalid) ? p1 : 0.f;
+          lsum += p0 + p1;
+          pk[c >> 1] = pack_half2(p0, p1);
+        }
+        tmem_st_x16(s_addr + (cb >> 1), pk);
       }
       l_run += lsum;
-      tmem_st_x32(s_addr, pk);
-      tmem_st_x32(s_addr + 32, pk + 32);
       tmem_wait_st();
       tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
+      mbar_arrive(p_full);
     }
 
     // epilogue: O / l -> fp16 hi/lo planes; LSE for the sharing layers / column sums
@@ -286,7 +287,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   p.out_hi = reinterpret_cast<__half*>(a.out_hi);
   p.out_lo = reinterpret_cast<__half*>(a.out_lo);
   p.out_img_stride = a.out_img_stride;
-  const size_t smem = AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + 1024 + 256;
+  const size_t smem = AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + 256;
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

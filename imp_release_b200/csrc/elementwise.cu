@@ -113,10 +113,103 @@ instnorm_relu_split_kernel(const float* __restrict__ H, long long h_bs, int ldh,
   }
 }
 
+// Slab variant for the wide MLP hidden layer: one CTA owns 16 channels of one image and keeps the whole [N, 16] slab
+// (128 KB at N = 2000) in shared memory, so H is read from HBM exactly once (stats and normalisation both run out of
+// smem) and the hi/lo planes are written once: 12 B per element, the minimum for a stand-alone pass.
+static constexpr int INS_CH = 16;
+static constexpr int INS_THREADS = 512;
+
+__global__ void __launch_bounds__(INS_THREADS, 1)
+instnorm_slab_kernel(const float* __restrict__ H, long long h_bs, int ldh, const int* __restrict__ ns, int Nmax, float eps,
+                     __half* __restrict__ out_hi, __half* __restrict__ out_lo, long long o_bs, int ldo, int relu) {
+  extern __shared__ __align__(16) float slab[];  // [n][16]
+  __shared__ float s_part[INS_THREADS / 32][2][INS_CH];
+  __shared__ float s_mean[INS_CH], s_rstd[INS_CH];
+  const int b = blockIdx.y;
+  const int c0 = blockIdx.x * INS_CH;
+  const int n = ns ? ns[b] : Nmax;
+  const int q = threadIdx.x & 3;  // which float4 of the 16 channels this thread always handles
+  const float* h = H + b * h_bs + c0;
+  const float4 shift = n > 0 ? *reinterpret_cast<const float4*>(h + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), sq = s;
+  const int total = n * 4;
+#pragma unroll 8
+  for (int i = threadIdx.x; i < total; i += INS_THREADS) {
+    const int t = i >> 2;
+    const float4 v = *reinterpret_cast<const float4*>(h + (long long)t * ldh + 4 * q);
+    *reinterpret_cast<float4*>(slab + t * INS_CH + 4 * q) = v;
+    const float4 d = make_float4(v.x - shift.x, v.y - shift.y, v.z - shift.z, v.w - shift.w);
+    s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
+    sq.x += d.x * d.x; sq.y += d.y * d.y; sq.z += d.z * d.z; sq.w += d.w * d.w;
+  }
+  // lanes with equal q: xor 4, 8, 16
+#pragma unroll
+  for (int o = 4; o < 32; o <<= 1) {
+    s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
+    s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
+    sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
+    sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane < 4) {
+    float* ps = &s_part[warp][0][4 * lane];
+    float* pq = &s_part[warp][1][4 * lane];
+    ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
+    pq[0] = sq.x; pq[1] = sq.y; pq[2] = sq.z; pq[3] = sq.w;
+  }
+  __syncthreads();
+  if (threadIdx.x < INS_CH) {
+    float ts = 0.f, tq = 0.f;
+#pragma unroll
+    for (int w = 0; w < INS_THREADS / 32; ++w) {
+      ts += s_part[w][0][threadIdx.x];
+      tq += s_part[w][1][threadIdx.x];
+    }
+    const float inv_n = n > 0 ? 1.f / (float)n : 0.f;
+    const float m = ts * inv_n;
+    const float var = fmaxf(tq * inv_n - m * m, 0.f);  // biased variance of the shifted data
+    const float sh = n > 0 ? h[threadIdx.x] : 0.f;
+    s_mean[threadIdx.x] = m + sh;
+    s_rstd[threadIdx.x] = 1.f / sqrtf(var + eps);
+  }
+  __syncthreads();
+  const float4 mean = *reinterpret_cast<const float4*>(&s_mean[4 * q]);
+  const float4 rstd = *reinterpret_cast<const float4*>(&s_rstd[4 * q]);
+  __half* oh = out_hi + b * o_bs + c0 + 4 * q;
+  __half* ol = out_lo + b * o_bs + c0 + 4 * q;
+#pragma unroll 4
+  for (int i = threadIdx.x; i < total; i += INS_THREADS) {
+    const int t = i >> 2;
+    const float4 v = *reinterpret_cast<const float4*>(slab + t * INS_CH + 4 * q);
+    float y[4] = {(v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z, (v.w - mean.w) * rstd.w};
+    __half hh[4], ll[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (relu) y[k] = fmaxf(y[k], 0.f);
+      split_f16x2(y[k], hh[k], ll[k]);
+    }
+    *reinterpret_cast<uint2*>(oh + (long long)t * ldo) = *reinterpret_cast<uint2*>(hh);
+    *reinterpret_cast<uint2*>(ol + (long long)t * ldo) = *reinterpret_cast<uint2*>(ll);
+  }
+}
+
 int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const int* ns, int Nmax, int C, int batch,
                                float eps, int relu, void* out_hi, void* out_lo, float* out_f32, long long o_bs,
                                int ldo, cudaStream_t st) {
   if (batch == 0 || Nmax == 0) return 0;
+  const size_t slab_bytes = (size_t)Nmax * INS_CH * sizeof(float);
+  if (out_f32 == nullptr && C % INS_CH == 0 && C >= 256 && ldh % 4 == 0 && ldo % 4 == 0 && h_bs % 4 == 0 && o_bs % 4 == 0 &&
+      slab_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+    static bool configured = false;
+    if (!configured) {
+      IMP_CUDA_OK(cudaFuncSetAttribute(instnorm_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    instnorm_slab_kernel<<<dim3(C / INS_CH, batch), INS_THREADS, slab_bytes, st>>>(
+        H, h_bs, ldh, ns, Nmax, eps, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), o_bs, ldo, relu);
+    IMP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   dim3 grid((C + IN_CH - 1) / IN_CH, batch);
   instnorm_relu_split_kernel<<<grid, IN_THREADS, 0, st>>>(H, h_bs, ldh, ns, Nmax, C, eps,
                                                           reinterpret_cast<__half*>(out_hi),
@@ -132,8 +225,11 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
 __global__ void small_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,
                                     const float* __restrict__ bias, float* __restrict__ Y, int ldy, long long rows,
                                     int Cin, int Cout) {
-  extern __shared__ float s_w[];  // [Cout][Cin] + [Cout]
-  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) s_w[i] = W[i];
+  extern __shared__ float s_w[];  // transposed [Cin][Cout] (lanes = consecutive outputs -> conflict-free) + [Cout]
+  for (int i = threadIdx.x; i < Cout * Cin; i += blockDim.x) {
+    const int o = i / Cin, c = i - o * Cin;
+    s_w[c * Cout + o] = W[i];
+  }
   for (int i = threadIdx.x; i < Cout; i += blockDim.x) s_w[Cout * Cin + i] = bias[i];
   __syncthreads();
   const long long total = rows * Cout;
@@ -142,9 +238,9 @@ __global__ void small_linear_kernel(const float* __restrict__ X, int ldx, const 
     const long long t = idx / Cout;
     const int o = (int)(idx - t * Cout);
     const float* x = X + t * ldx;
-    const float* w = s_w + o * Cin;
     float acc = s_w[Cout * Cin + o];
-    for (int cidx = 0; cidx < Cin; ++cidx) acc = fmaf(x[cidx], w[cidx], acc);
+#pragma unroll 4
+    for (int cidx = 0; cidx < Cin; ++cidx) acc = fmaf(__ldg(x + cidx), s_w[cidx * Cout + o], acc);
     Y[t * ldy + o] = acc;
   }
 }
@@ -155,7 +251,7 @@ int launch_small_linear(const float* X, int ldx, const float* W, const float* bi
   const size_t smem = (size_t)(Cout * Cin + Cout) * sizeof(float);
   IMP_REQUIRE(smem <= 48 * 1024, "small_linear: weight does not fit in shared memory");
   const long long total = rows * Cout;
-  const int blocks = (int)((total + 255) / 256 < 148 * 8 ? (total + 255) / 256 : 148 * 8);
+  const int blocks = (int)((total + 255) / 256 < 148 * 16 ? (total + 255) / 256 : 148 * 16);
   small_linear_kernel<<<blocks, 256, smem, st>>>(X, ldx, W, bias, Y, ldy, rows, Cin, Cout);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -47,6 +47,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC;  // [ACC]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [ACC][BN] bias slice of the tile being drained
 
   const int warp = threadIdx.x >> 5;
   const bool split = p.nsplit == 3;
@@ -157,26 +158,27 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       const int a = lt % ACC;
       const long long gm = m0 + row;
       const bool row_ok = gm < p.M;
+      // stage this tile's bias slice in shared memory (one coalesced load instead of 256 broadcast LDGs per thread)
+      float* bias_t = s_bias + a * BN;
+      for (int j = threadIdx.x - 128; j < BN; j += 128)
+        bias_t[j] = (p.bias != nullptr && n0 + j < p.N) ? __ldg(p.bias + n0 + j) : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
       mbar_wait(&tmem_full_bar[a], (lt / ACC) & 1);
       tc_fence_after();
       const uint32_t t_row = tmem_base + a * BN + (static_cast<uint32_t>(q * 32) << 16);
       const long long obase = (long long)z * p.out_batch_stride + gm * p.out_row_stride;
+      const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
+      uint32_t r[32];
+      tmem_ld_x32(t_row, r);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = 0; c < nchunks; ++c) {
         const int nc = n0 + c * 32;
-        if (nc >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld_x32(t_row + c * 32, r);
         tmem_wait_ld();
         float v[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]) * p.alpha;
+        for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias_t[c * 32 + j]);
+        if (c + 1 < nchunks) tmem_ld_x32(t_row + (c + 1) * 32, r);  // next chunk's TMEM read overlaps this chunk's stores
         const bool full = nc + 32 <= p.N;
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (full || nc + j < p.N) v[j] += __ldg(p.bias + nc + j);
-        }
         if (!row_ok) continue;
         if (p.out_mode == GEMM_OUT_F32) {
           float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
@@ -315,7 +317,7 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.out_row_stride = g.out_row_stride;
   p.out_batch_stride = g.out_batch_stride;
 
-  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256;
+  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float);
   auto kern = gemm_f16split_kernel<BN, STAGES>;
   static bool configured = false;
   if (!configured) {
