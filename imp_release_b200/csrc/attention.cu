@@ -291,6 +291,8 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // two CTAs per SM need the full shared-memory carve-out (the default heuristic may leave room for one only)
+    IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   dim3 grid((a.Nq_max + AT_BM - 1) / AT_BM, AT_HEADS, a.n_img);

@@ -415,6 +415,10 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
+    // two CTAs per SM need the full shared-memory carve-out
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_ITER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int chunk = sk_chunk_matrices((size_t)R * row_bytes, a.batch);
