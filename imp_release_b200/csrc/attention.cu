@@ -151,6 +151,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const int kbase = j * AT_BN;
       const int nvalid = nk - kbase;  // keys of this tile that exist (>= 128 except for the ragged last tile)
       float neg_ref;
+      const bool ragged = nvalid < AT_BN;  // warp-uniform: only the last tile of a ragged key set needs masking
       if (!p.shared) {
         // pass 1: row max (the score row is re-read from TMEM in pass 2 instead of living in 128 registers)
         float mx = -INFINITY;
@@ -159,8 +160,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           uint32_t r[32];
           tmem_ld_x32(s_addr + cb, r);
           tmem_wait_ld();
+          if (!ragged) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (cb + c < nvalid) ? __uint_as_float(r[c]) : -INFINITY);
+            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (cb + c < nvalid) ? __uint_as_float(r[c]) : -INFINITY);
+          }
         }
         const float m_new = fmaxf(m_run, mx * AT_SCALE_LOG2);
         const bool need = m_new > m_run + AT_RESCALE_TAU;  // first tile: m_run = -inf
@@ -205,14 +211,24 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld_x32(s_addr + cb, r);
         tmem_wait_ld();
         uint32_t pk[16];
+        if (!ragged) {
 #pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
-          float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
-          p0 = (cb + c < nvalid) ? p0 : 0.f;
-          p1 = (cb + c + 1 < nvalid) ? p1 : 0.f;
-          lsum += p0 + p1;
-          pk[c >> 1] = pack_half2(p0, p1);
+          for (int c = 0; c < 32; c += 2) {
+            const float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+            const float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+            lsum += p0 + p1;
+            pk[c >> 1] = pack_half2(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < 32; c += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+            p0 = (cb + c < nvalid) ? p0 : 0.f;
+            p1 = (cb + c + 1 < nvalid) ? p1 : 0.f;
+            lsum += p0 + p1;
+            pk[c >> 1] = pack_half2(p0, p1);
+          }
         }
         tmem_st_x16(s_addr + (cb >> 1), pk);
       }
