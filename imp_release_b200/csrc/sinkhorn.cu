@@ -82,6 +82,15 @@ __device__ __forceinline__ float4 v_from_colsum(const float* __restrict__ colsum
 
 enum { SK_INIT = 0, SK_ITER = 1, SK_FINAL = 2 };
 
+// exp(x) for x <= 0 with ~3e-7 relative error in 6 instructions: x*log2(e) is split into a rounded product t and its
+// exact residual e (FMA), 2^t comes from the MUFU and the residual is applied to first order.  (expf() costs ~20
+// instructions and made the softmax pass compute-bound: 1.28 ms per launch instead of the ~0.33 ms its traffic needs.)
+__device__ __forceinline__ float sk_exp(float x) {
+  const float t = x * 1.4426950408889634f;
+  const float e = fmaf(x, 1.4426950408889634f, -t) + x * 1.925963033500235e-8f;
+  return fast_exp2(t) * fmaf(e, 0.6931471805599453f, 1.0f);
+}
+
 // MODE: SK_INIT  P = softmax_rows(pad(dist)) (+ first half-iteration: u with v = 1, column sums with that u)
 //       SK_ITER  one full Sinkhorn iteration (u, then column sums) in a single sweep over P
 //       SK_FINAL out = (p u) v, row arg-max / masses over the non-dustbin block
@@ -181,15 +190,16 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
         const int c0 = 4 * (lane_id() + 32 * k);
         if (c0 < d.C) {
           float4 t = *reinterpret_cast<const float4*>(srow + c0);
-          t.x = (c0 + 0 < d.C) ? expf(t.x - m) : 0.f;
-          t.y = (c0 + 1 < d.C) ? expf(t.y - m) : 0.f;
-          t.z = (c0 + 2 < d.C) ? expf(t.z - m) : 0.f;
-          t.w = (c0 + 3 < d.C) ? expf(t.w - m) : 0.f;
+          t.x = (c0 + 0 < d.C) ? sk_exp(t.x - m) : 0.f;
+          t.y = (c0 + 1 < d.C) ? sk_exp(t.y - m) : 0.f;
+          t.z = (c0 + 2 < d.C) ? sk_exp(t.z - m) : 0.f;
+          t.w = (c0 + 3 < d.C) ? sk_exp(t.w - m) : 0.f;
           *reinterpret_cast<float4*>(srow + c0) = t;
           sum += (t.x + t.y) + (t.z + t.w);
         }
       }
       sum = warp_sum(sum);
+      const float inv_sum = 1.0f / sum;  // one division per row; p = e * (1/sum) differs from e / sum by <= 1 ulp
       float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
       float rs = 0.f;
 #pragma unroll
@@ -197,10 +207,10 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
         const int c0 = 4 * (lane_id() + 32 * k);
         if (c0 < d.C) {
           float4 t = *reinterpret_cast<const float4*>(srow + c0);
-          t.x = t.x / sum;
-          t.y = t.y / sum;
-          t.z = t.z / sum;
-          t.w = t.w / sum;
+          t.x *= inv_sum;
+          t.y *= inv_sum;
+          t.z *= inv_sum;
+          t.w *= inv_sum;
           *reinterpret_cast<float4*>(srow + c0) = t;
           *reinterpret_cast<float4*>(prow + c0) = t;
           rs += (t.x + t.y) + (t.z + t.w);
@@ -253,8 +263,9 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
       const float ui = p.do_iter ? p.u[(long long)b * (p.N0max + 1) + i] : 1.f;
       const bool inner_row = i < d.R - 1;
       float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
-      float best = -1.f, mass = 0.f;
-      int best_j = 0x7fffffff;
+      // four independent (value, column) trackers -- one per float4 component -- keep the compare/select chains short
+      float bv[4] = {-1.f, -1.f, -1.f, -1.f}, ms[4] = {0.f, 0.f, 0.f, 0.f};
+      int bj[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c0 = 4 * (lane_id() + 32 * k);
@@ -266,12 +277,12 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
         if (inner_row) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            if (c0 + q < d.C - 1) {
-              mass += o[q];
-              if (o[q] > best) {  // strict: keeps the lowest column among equal values in this lane
-                best = o[q];
-                best_j = c0 + q;
-              }
+            const bool in = c0 + q < d.C - 1;
+            const float oq = in ? o[q] : -1.f;  // columns grow with k, so a strict > keeps the lowest column per tracker
+            ms[q] += in ? o[q] : 0.f;
+            if (oq > bv[q]) {
+              bv[q] = oq;
+              bj[q] = c0 + q;
             }
           }
           if (want_col) {
@@ -282,6 +293,14 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
           }
         }
       }
+      float best = bv[0], mass = (ms[0] + ms[1]) + (ms[2] + ms[3]);
+      int best_j = bj[0];
+#pragma unroll
+      for (int q = 1; q < 4; ++q)
+        if (bv[q] > best || (bv[q] == best && bj[q] < best_j)) {
+          best = bv[q];
+          best_j = bj[q];
+        }
       if (inner_row) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {  // warp arg-max, lowest index wins ties
