@@ -12,6 +12,7 @@
 #include "attention.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -19,16 +20,13 @@
 namespace imp {
 
 static constexpr int AT_BM = 128;
-static constexpr int AT_BN = 128;
+static constexpr int CS_BN = 128;  // key rows per CTA in the column-sum kernel
 static constexpr int AT_D = 64;
 static constexpr int AT_HEADS = 4;
 static constexpr int AT_C = AT_D * AT_HEADS;
-static constexpr int AT_STAGES = 3;
 static constexpr int AT_THREADS = 192;
-static constexpr int AT_TILE_BYTES = AT_BN * AT_D * 2;  // 16 KB (Q, K and V tiles alike)
-static constexpr uint32_t AT_TMEM_COLS = 256;
-static constexpr uint32_t AT_COL_S = 0;    // score tile, 128 fp32 columns (P aliases the first 64)
-static constexpr uint32_t AT_COL_O = 128;  // 64 fp32 columns
+static constexpr int AT_TILE_BYTES = AT_BM * AT_D * 2;  // 16 KB: a 128-row tile of one head
+static constexpr uint32_t AT_COL_S = 0;  // score tile at TMEM column 0 (packed fp16 P aliases its first half), O behind it
 static constexpr float AT_SCALE_LOG2 = 0.125f * 1.4426950408889634f;
 static constexpr float AT_RESCALE_TAU = 8.0f;
 
@@ -40,17 +38,21 @@ struct AttnKernelParams {
   long long out_img_stride;
 };
 
-__global__ void __launch_bounds__(AT_THREADS, 2)
+template <int BN, int STG, int MINB>
+__global__ void __launch_bounds__(AT_THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
+  constexpr int KV_BYTES = BN * AT_D * 2;                  // one K (or V) tile
+  constexpr uint32_t TMEM_COLS = (BN + AT_D <= 128) ? 128 : 256;  // score tile (BN fp32 columns) + O (64)
+  constexpr uint32_t COL_O = BN;
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
   uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K at +0, V at +16 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + AT_STAGES * 2 * AT_TILE_BYTES);
+  uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K at +0, V at +KV_BYTES
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + STG * 2 * KV_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + AT_STAGES;
-  uint64_t* s_full = kv_empty + AT_STAGES;
+  uint64_t* kv_empty = kv_full + STG;
+  uint64_t* s_full = kv_empty + STG;
   uint64_t* p_full = s_full + 1;
   uint64_t* o_done = p_full + 1;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
@@ -64,14 +66,14 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   const int nq = p.nq ? p.nq[img] : p.Nq_max;
   const int nk = p.nk ? p.nk[src] : p.Nk_max;
   if (q0 >= nq) return;
-  const int T = (nk + AT_BN - 1) / AT_BN;
+  const int T = (nk + BN - 1) / BN;
 
   if (warp == 0 && elect_one()) {
     tma_prefetch_desc(&tm_q);
     tma_prefetch_desc(&tm_k);
     tma_prefetch_desc(&tm_v);
     mbar_init(q_full, 1);
-    for (int s = 0; s < AT_STAGES; ++s) {
+    for (int s = 0; s < STG; ++s) {
       mbar_init(&kv_full[s], 1);
       mbar_init(&kv_empty[s], 1);
     }
@@ -81,7 +83,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, AT_TMEM_COLS);
+    tmem_alloc(tmem_ptr_smem, TMEM_COLS);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -95,27 +97,27 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
       tma_load_3d(s_q, &tm_q, q_full, h * AT_D, q0, img);
       for (int j = 0; j < T; ++j) {
-        const int s = j % AT_STAGES;
-        mbar_wait(&kv_empty[s], ((j / AT_STAGES) & 1) ^ 1);
-        uint8_t* st = s_kv + s * 2 * AT_TILE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[s], 2 * AT_TILE_BYTES);
-        tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * AT_BN, src);
-        tma_load_3d(st + AT_TILE_BYTES, &tm_v, &kv_full[s], h * AT_D, j * AT_BN, src);
+        const int s = j % STG;
+        mbar_wait(&kv_empty[s], ((j / STG) & 1) ^ 1);
+        uint8_t* st = s_kv + s * 2 * KV_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * BN, src);
+        tma_load_3d(st + KV_BYTES, &tm_v, &kv_full[s], h * AT_D, j * BN, src);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ UMMA issuer
     if (elect_one() && T > 0) {
-      constexpr uint32_t idesc_qk = make_idesc(FMT_F16, AT_BM, AT_BN, 0, 0);
+      constexpr uint32_t idesc_qk = make_idesc(FMT_F16, AT_BM, BN, 0, 0);
       constexpr uint32_t idesc_pv = make_idesc(FMT_F16, AT_BM, AT_D, 0, 1);  // B = V, MN-major
       const uint32_t q_addr = smem_u32(s_q);
       mbar_wait(q_full, 0);
       for (int j = 0; j < T; ++j) {
-        const int st = j % AT_STAGES;
-        mbar_wait(&kv_full[st], (j / AT_STAGES) & 1);
+        const int st = j % STG;
+        mbar_wait(&kv_full[st], (j / STG) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * 2 * AT_TILE_BYTES);
-        const uint32_t v_addr = k_addr + AT_TILE_BYTES;
+        const uint32_t k_addr = smem_u32(s_kv + st * 2 * KV_BYTES);
+        const uint32_t v_addr = k_addr + KV_BYTES;
         // S = Q K^T.  The tensor pipe executes MMAs in issue order, so this overwrites the score columns only after
         // O += P(j-1) V(j-1), which read P from the same columns, has drained.
 #pragma unroll
@@ -126,8 +128,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < AT_BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
-          umma_f16_ts(tmem_base + AT_COL_O, tmem_base + AT_COL_S + kk * 8,
+        for (int kk = 0; kk < BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
+          umma_f16_ts(tmem_base + COL_O, tmem_base + AT_COL_S + kk * 8,
                       make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
         umma_commit(&kv_empty[st]);
         umma_commit(o_done);
@@ -148,15 +150,15 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int j = 0; j < T; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      const int kbase = j * AT_BN;
+      const int kbase = j * BN;
       const int nvalid = nk - kbase;  // keys of this tile that exist (>= 128 except for the ragged last tile)
       float neg_ref;
-      const bool ragged = nvalid < AT_BN;  // warp-uniform: only the last tile of a ragged key set needs masking
+      const bool ragged = nvalid < BN;  // warp-uniform: only the last tile of a ragged key set needs masking
       if (!p.shared) {
         // pass 1: row max (the score row is re-read from TMEM in pass 2 instead of living in 128 registers)
         float mx = -INFINITY;
 #pragma unroll
-        for (int cb = 0; cb < AT_BN; cb += 32) {
+        for (int cb = 0; cb < BN; cb += 32) {
           uint32_t r[32];
           tmem_ld_x32(s_addr + cb, r);
           tmem_wait_ld();
@@ -182,7 +184,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             m_run = m_new;
           }
           if (j > 0) {
-            const uint32_t o_addr = tmem_base + lane_off + AT_COL_O;
+            const uint32_t o_addr = tmem_base + lane_off + COL_O;
 #pragma unroll
             for (int cb = 0; cb < AT_D; cb += 32) {
               uint32_t o[32];
@@ -206,7 +208,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // [cb/2, cb/2+16), which this thread has already consumed)
       float lsum = 0.f;
 #pragma unroll
-      for (int cb = 0; cb < AT_BN; cb += 32) {
+      for (int cb = 0; cb < BN; cb += 32) {
         uint32_t r[32];
         tmem_ld_x32(s_addr + cb, r);
         tmem_wait_ld();
@@ -246,7 +248,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       mbar_wait(o_done, (T - 1) & 1);
       tc_fence_after();
       uint32_t o[AT_D];
-      const uint32_t o_addr = tmem_base + lane_off + AT_COL_O;
+      const uint32_t o_addr = tmem_base + lane_off + COL_O;
       tmem_ld_x32(o_addr, o);
       tmem_ld_x32(o_addr + 32, o + 32);
       tmem_wait_ld();
@@ -280,17 +282,16 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, AT_TMEM_COLS);
+    tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
-int launch_attention(const AttnArgs& a, cudaStream_t st) {
-  IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
-  IMP_REQUIRE(a.q_row_stride >= AT_C && a.kv_row_stride >= AT_C, "attention: row strides must be >= 256");
+template <int BN, int STG, int MINB>
+static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   CUtensorMap tq, tk, tv;
   if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
-  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
-  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
   AttnKernelParams p;
   p.n_img = a.n_img;
   p.src_offset = a.src_offset;
@@ -303,18 +304,36 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   p.out_hi = reinterpret_cast<__half*>(a.out_hi);
   p.out_lo = reinterpret_cast<__half*>(a.out_lo);
   p.out_img_stride = a.out_img_stride;
-  const size_t smem = AT_TILE_BYTES + AT_STAGES * 2 * AT_TILE_BYTES + 256;
+  const size_t smem = AT_TILE_BYTES + STG * 2 * (BN * AT_D * 2) + 256;
+  auto kern = attention_kernel<BN, STG, MINB>;
   static bool configured = false;
   if (!configured) {
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    // two CTAs per SM need the full shared-memory carve-out (the default heuristic may leave room for one only)
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // several CTAs per SM need the full shared-memory carve-out
+    IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   dim3 grid((a.Nq_max + AT_BM - 1) / AT_BM, AT_HEADS, a.n_img);
-  attention_kernel<<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  kern<<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
+}
+
+int launch_attention(const AttnArgs& a, cudaStream_t st) {
+  IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
+  IMP_REQUIRE(a.q_row_stride >= AT_C && a.kv_row_stride >= AT_C, "attention: row strides must be >= 256");
+  // The kernel is bound by the serial QK -> softmax -> PV chain of a CTA, not by a throughput limit, so more (smaller)
+  // CTAs per SM win: 64-key tiles need 128 TMEM columns and 48 KB of smem -> up to 4 CTAs/SM; 128-key tiles -> 2.
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("IMP_ATTN_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  switch (variant) {
+    case 1: return launch_attention_impl<128, 3, 2>(a, st);
+    case 2: return launch_attention_impl<64, 2, 3>(a, st);
+    default: return launch_attention_impl<64, 2, 4>(a, st);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -338,7 +357,7 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint8_t* s_k = smem;                   // the CTA's 128 keys (A operand)
   uint8_t* s_q = smem + AT_TILE_BYTES;   // ring of query tiles (B operand)
   float* s_lse = reinterpret_cast<float*>(s_q + CS_STAGES * AT_TILE_BYTES);  // [CS_STAGES][128]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lse + CS_STAGES * AT_BN);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_lse + CS_STAGES * CS_BN);
   uint64_t* k_full = bars;
   uint64_t* q_full = bars + 1;
   uint64_t* q_empty = q_full + CS_STAGES;
@@ -347,7 +366,7 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(s_free + 2);
 
   const int warp = threadIdx.x >> 5;
-  const int k0 = blockIdx.x * AT_BN;
+  const int k0 = blockIdx.x * CS_BN;
   const int h = blockIdx.y;
   const int img = blockIdx.z;  // query image; keys come from src
   const int src = (img + p.src_offset) % p.n_img;
@@ -390,7 +409,7 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
     }
   } else if (warp == 1) {
     if (elect_one() && T > 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_F16, AT_BN, AT_BM, 0, 0);
+      constexpr uint32_t idesc = make_idesc(FMT_F16, CS_BN, AT_BM, 0, 0);
       const uint32_t k_addr = smem_u32(s_k);
       mbar_wait(k_full, 0);
       for (int j = 0; j < T; ++j) {
@@ -418,7 +437,7 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       const int s = j % CS_STAGES;
       if (j >= CS_STAGES) mbar_wait(&q_empty[s], ((j / CS_STAGES) & 1) ^ 1);
       const int qi = j * AT_BM + t128;
-      s_lse[s * AT_BN + t128] = (qi < nq) ? p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qi] : INFINITY;
+      s_lse[s * CS_BN + t128] = (qi < nq) ? p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qi] : INFINITY;
       mbar_arrive(&q_full[s]);
     };
     for (int j = 0; j < T && j < CS_STAGES - 1; ++j) stage_lse(j);
@@ -428,7 +447,7 @@ attention_colsum_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_c
       mbar_wait(&s_full[j & 1], (j >> 1) & 1);
       tc_fence_after();
       const uint32_t s_addr = tmem_base + lane_off + (j & 1) * AT_BM;
-      const float* lse_t = s_lse + s * AT_BN;
+      const float* lse_t = s_lse + s * CS_BN;
 #pragma unroll
       for (int cb = 0; cb < AT_BM; cb += 32) {
         uint32_t r[32];
@@ -456,7 +475,7 @@ int launch_attention_colsum(const AttnColsumArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention_colsum: empty problem");
   CUtensorMap tq, tk;
   if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
-  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, AT_BN)) return 3;
+  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, CS_BN)) return 3;
   ColsumKernelParams p;
   p.n_img = a.n_img;
   p.src_offset = a.src_offset;
@@ -467,13 +486,13 @@ int launch_attention_colsum(const AttnColsumArgs& a, cudaStream_t st) {
   p.lse = a.lse;
   p.colsum = a.colsum;
   IMP_CUDA_OK(cudaMemsetAsync(a.colsum, 0, (size_t)a.n_img * a.Nk_max * sizeof(float), st));
-  const size_t smem = AT_TILE_BYTES + CS_STAGES * AT_TILE_BYTES + CS_STAGES * AT_BN * 4 + 1024 + 256;
+  const size_t smem = AT_TILE_BYTES + CS_STAGES * AT_TILE_BYTES + CS_STAGES * CS_BN * 4 + 1024 + 256;
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(attention_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  dim3 grid((a.Nk_max + AT_BN - 1) / AT_BN, AT_HEADS, a.n_img);
+  dim3 grid((a.Nk_max + CS_BN - 1) / CS_BN, AT_HEADS, a.n_img);
   attention_colsum_kernel<<<grid, CS_THREADS, smem, st>>>(tq, tk, p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;

@@ -1,0 +1,11 @@
+#!/bin/bash
+# Round evidence: ncu --set full of the top kernels inside the bench workload + a launch list.  usage: ncu_capture.sh <tag>
+tag=${1:-cur}
+mkdir -p gpurun_out
+for spec in "attention_kernel:3" "sk_ring_kernel:6" "gemm_f16split:40" "instnorm_slab:3"; do
+  k=${spec%%:*}; skip=${spec##*:}
+  timeout 500 ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c 2 -f -o gpurun_out/${tag}_$k python bench.py --ncu --warmup 1 > gpurun_out/${tag}_ncu_$k.log 2>&1
+  tail -1 gpurun_out/${tag}_ncu_$k.log
+done
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 400 -c 900 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --ncu --warmup 1 > gpurun_out/${tag}_ncu_launches.log 2>&1
+wc -l gpurun_out/${tag}_launches.csv
