@@ -86,6 +86,7 @@ enum { SK_INIT = 0, SK_ITER = 1, SK_FINAL = 2 };
 // exact residual e (FMA), 2^t comes from the MUFU and the residual is applied to first order.  (expf() costs ~20
 // instructions and made the softmax pass compute-bound: 1.28 ms per launch instead of the ~0.33 ms its traffic needs.)
 __device__ __forceinline__ float sk_exp(float x) {
+  x = fmaxf(x, -200.f);  // exp(-200) underflows to 0 in fp32; also keeps the residual finite for the -FLT_MAX pad
   const float t = x * 1.4426950408889634f;
   const float e = fmaf(x, 1.4426950408889634f, -t) + x * 1.925963033500235e-8f;
   return fast_exp2(t) * fmaf(e, 0.6931471805599453f, 1.0f);
@@ -168,40 +169,52 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
     // spills); each lane only ever touches its own float4 groups, so in-place updates of the slot are race-free.
     if (MODE == SK_INIT) {
       const bool bin_row = (i == d.R - 1);
+      // pass 1: materialise the padded row in the slot (dustbin column / row, -FLT_MAX beyond C) and take its max.
+      // Interior float4 groups (all four columns < C-1) need no per-element masking.
       float m = -FLT_MAX;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c0 = 4 * (lane_id() + 32 * k);
         if (c0 < d.C) {
-          float4 t = make_float4(bin, bin, bin, bin);
-          if (!bin_row && c0 < d.C - 1) t = *reinterpret_cast<const float4*>(srow + c0);
-          t.x = (c0 + 0 < d.C) ? ((bin_row || c0 + 0 == d.C - 1) ? bin : t.x) : -FLT_MAX;
-          t.y = (c0 + 1 < d.C) ? ((bin_row || c0 + 1 == d.C - 1) ? bin : t.y) : -FLT_MAX;
-          t.z = (c0 + 2 < d.C) ? ((bin_row || c0 + 2 == d.C - 1) ? bin : t.z) : -FLT_MAX;
-          t.w = (c0 + 3 < d.C) ? ((bin_row || c0 + 3 == d.C - 1) ? bin : t.w) : -FLT_MAX;
-          *reinterpret_cast<float4*>(srow + c0) = t;
+          float4 t;
+          if (!bin_row && c0 + 3 < d.C - 1) {
+            t = *reinterpret_cast<const float4*>(srow + c0);
+          } else {
+            t = make_float4(bin, bin, bin, bin);
+            if (!bin_row && c0 < d.C - 1) t = *reinterpret_cast<const float4*>(srow + c0);
+            t.x = (c0 + 0 < d.C) ? ((bin_row || c0 + 0 == d.C - 1) ? bin : t.x) : -FLT_MAX;
+            t.y = (c0 + 1 < d.C) ? ((bin_row || c0 + 1 == d.C - 1) ? bin : t.y) : -FLT_MAX;
+            t.z = (c0 + 2 < d.C) ? ((bin_row || c0 + 2 == d.C - 1) ? bin : t.z) : -FLT_MAX;
+            t.w = (c0 + 3 < d.C) ? ((bin_row || c0 + 3 == d.C - 1) ? bin : t.w) : -FLT_MAX;
+            *reinterpret_cast<float4*>(srow + c0) = t;
+          }
           m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
         }
       }
       m = warp_max(m);
+      // pass 2: e = exp(x - max) in place, row sum  (sk_exp(-FLT_MAX - m) underflows to exactly 0 for the pad columns)
       float sum = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c0 = 4 * (lane_id() + 32 * k);
         if (c0 < d.C) {
           float4 t = *reinterpret_cast<const float4*>(srow + c0);
-          t.x = (c0 + 0 < d.C) ? sk_exp(t.x - m) : 0.f;
-          t.y = (c0 + 1 < d.C) ? sk_exp(t.y - m) : 0.f;
-          t.z = (c0 + 2 < d.C) ? sk_exp(t.z - m) : 0.f;
-          t.w = (c0 + 3 < d.C) ? sk_exp(t.w - m) : 0.f;
+          t.x = sk_exp(t.x - m);
+          t.y = sk_exp(t.y - m);
+          t.z = sk_exp(t.z - m);
+          t.w = sk_exp(t.w - m);
           *reinterpret_cast<float4*>(srow + c0) = t;
           sum += (t.x + t.y) + (t.z + t.w);
         }
       }
       sum = warp_sum(sum);
       const float inv_sum = 1.0f / sum;  // one division per row; p = e * (1/sum) differs from e / sum by <= 1 ulp
+      // first half-iteration with v = 1: sum_j p_ij = sum * inv_sum (the reference adds the rounded p's; the two agree
+      // to ~1e-7 relative)
+      const float ui = p.do_iter ? (bin_row ? (float)d.R : 1.f) / (sum * inv_sum + SK_EPS) : 0.f;
+      if (p.do_iter && lane_id() == 0) p.u[(long long)b * (p.N0max + 1) + i] = ui;
+      // pass 3: normalise, store, and fold p * u into the column accumulators
       float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
-      float rs = 0.f;
 #pragma unroll
       for (int k = 0; k < NV; ++k) {
         const int c0 = 4 * (lane_id() + 32 * k);
@@ -211,27 +224,13 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
           t.y *= inv_sum;
           t.z *= inv_sum;
           t.w *= inv_sum;
-          *reinterpret_cast<float4*>(srow + c0) = t;
           *reinterpret_cast<float4*>(prow + c0) = t;
-          rs += (t.x + t.y) + (t.z + t.w);
+          acc[k].x += t.x * ui;
+          acc[k].y += t.y * ui;
+          acc[k].z += t.z * ui;
+          acc[k].w += t.w * ui;
         } else if (c0 < p.ldp) {
           *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-      }
-      if (p.do_iter) {
-        rs = warp_sum(rs);  // sum_j p_ij * v_j with v = 1
-        const float ui = (bin_row ? (float)d.R : 1.f) / (rs + SK_EPS);
-        if (lane_id() == 0) p.u[(long long)b * (p.N0max + 1) + i] = ui;
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-          const int c0 = 4 * (lane_id() + 32 * k);
-          if (c0 < d.C) {
-            const float4 t = *reinterpret_cast<const float4*>(srow + c0);
-            acc[k].x += t.x * ui;
-            acc[k].y += t.y * ui;
-            acc[k].z += t.z * ui;
-            acc[k].w += t.w * ui;
-          }
         }
       }
     } else if (MODE == SK_ITER) {
@@ -275,14 +274,25 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
         const float o[4] = {(t.x * ui) * v.x, (t.y * ui) * v.y, (t.z * ui) * v.z, (t.w * ui) * v.w};
         if (p.write_scores) *reinterpret_cast<float4*>(prow + c0) = make_float4(o[0], o[1], o[2], o[3]);
         if (inner_row) {
+          if (c0 + 3 < d.C - 1) {  // interior group: no column masking needed
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const bool in = c0 + q < d.C - 1;
-            const float oq = in ? o[q] : -1.f;  // columns grow with k, so a strict > keeps the lowest column per tracker
-            ms[q] += in ? o[q] : 0.f;
-            if (oq > bv[q]) {
-              bv[q] = oq;
-              bj[q] = c0 + q;
+            for (int q = 0; q < 4; ++q) {
+              ms[q] += o[q];
+              if (o[q] > bv[q]) {
+                bv[q] = o[q];
+                bj[q] = c0 + q;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool in = c0 + q < d.C - 1;
+              const float oq = in ? o[q] : -1.f;  // columns grow with k, so a strict > keeps the lowest column per tracker
+              ms[q] += in ? o[q] : 0.f;
+              if (oq > bv[q]) {
+                bv[q] = oq;
+                bj[q] = c0 + q;
+              }
             }
           }
           if (want_col) {
@@ -466,11 +476,23 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     p.N0max = a.N0max;
     p.N1max = a.N1max;
     p.write_scores = a.write_scores;
-    // rows per CTA: aim at one resident wave (2 CTAs per SM), a multiple of the consumer-warp count, 8..128 rows
-    int rows_per_cta = (int)(((long long)nb * R + 2LL * num_sms() - 1) / (2LL * num_sms()));
-    rows_per_cta = (rows_per_cta + SKR_CONSUMERS - 1) / SKR_CONSUMERS * SKR_CONSUMERS;
-    if (rows_per_cta < 8) rows_per_cta = 8;
-    if (rows_per_cta > 128) rows_per_cta = 128;
+    // rows per CTA (multiple of the consumer-warp count, 8..128): pick the block height whose CTA count fills whole
+    // waves of 2 CTAs/SM best -- e.g. 64 x 2001 rows: 128-row blocks give 1024 CTAs = 3.46 waves, 88-row blocks
+    // 1472 CTAs = 4.97 waves.  Larger blocks win ties (fewer column-sum flushes).
+    const long long wave = 2LL * num_sms();
+    int rows_per_cta = 8;
+    double best_eff = -1.0;
+    for (int r = 128; r >= 8; r -= SKR_CONSUMERS) {
+      const long long ctas = (long long)nb * ((R + r - 1) / r);
+      const long long waves = (ctas + wave - 1) / wave;
+      const double eff = (double)ctas / (double)(waves * wave) * ((R % r == 0 || r <= R) ? 1.0 : 1.0);
+      const double balance = (double)R / (double)(((R + r - 1) / r) * r);  // ragged last block of each matrix
+      const double score = eff * balance;
+      if (score > best_eff + 1e-3) {
+        best_eff = score;
+        rows_per_cta = r;
+      }
+    }
     p.rows_per_cta = rows_per_cta;
     int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
     if (slots > 64) slots = 64;
