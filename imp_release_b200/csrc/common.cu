@@ -36,7 +36,8 @@ static EncodeTiledFn encode_fn() {
 }
 
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
-                     uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows) {
+                     uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows,
+                     int swizzle_bytes) {
   EncodeTiledFn fn = encode_fn();
   IMP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
   IMP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base not 16-byte aligned");
@@ -47,7 +48,8 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   cuuint32_t box[3] = {box_inner, box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), gdim, gstr, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE,
+                  swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   IMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (%d): dims %llu x %llu x %llu stride %llu/%llu box %u x %u",
               (int)r, (unsigned long long)inner, (unsigned long long)rows, (unsigned long long)batch,

@@ -27,10 +27,11 @@ const char* last_error();
     }                                 \
   } while (0)
 
-// 3-D fp16 tensor map {inner = k elements, rows, batch}, 128-byte swizzle, zero OOB fill.
-// row_stride / batch_stride in elements.  box = {box_inner (64 -> 128 B), box_rows, 1}.
+// 3-D fp16 tensor map {inner = k elements, rows, batch}, 128- or 64-byte swizzle, zero OOB fill.
+// row_stride / batch_stride in elements.  box = {box_inner (= swizzle span: 64 or 32 elements), box_rows, 1}.
 int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch,
-                     uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows);
+                     uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows,
+                     int swizzle_bytes = 128);
 
 int num_sms();
 

@@ -9,10 +9,11 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace imp {
 
 static constexpr int GEMM_BM = 128;
-static constexpr int GEMM_BK = 64;  // fp16 elements = one 128-byte swizzle span
 static constexpr int GEMM_THREADS = 256;
 
 struct GemmKernelParams {
@@ -25,20 +26,23 @@ struct GemmKernelParams {
   long long out_row_stride, out_batch_stride;
 };
 
-template <int BN>
+// BK = K elements per pipeline stage = one swizzle span (64 fp16 = 128 B, or 32 fp16 = 64 B).  The mainloop is bound by
+// the latency of the TMA fetches, not by their bandwidth, so four 48 KB stages (BK = 32) beat two 96 KB stages (BK = 64).
+template <int BN, int BK>
 struct GemmSmem {
-  static constexpr int A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB per plane
-  static constexpr int B_BYTES = BN * GEMM_BK * 2;
+  static constexpr int A_BYTES = GEMM_BM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int SBO = 8 * BK * 2;  // bytes between 8-row groups
 };
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
                      const GemmKernelParams p) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, BK>;
   constexpr int ACC = (2 * BN <= 512) ? 2 : 1;  // accumulator buffers in TMEM
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -102,12 +106,12 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           uint8_t* st = smem + s * S::STAGE_BYTES;
           mbar_arrive_expect_tx(&full_bar[s], tx);
           const bool seg2 = kb >= p.KB1;
-          const int ka = (seg2 ? kb - p.KB1 : kb) * GEMM_BK;
+          const int ka = (seg2 ? kb - p.KB1 : kb) * BK;
           tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
-          tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * GEMM_BK, n0, p.b_batched ? z : 0);
+          tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * BK, n0, p.b_batched ? z : 0);
           if (split) {
             tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
-            tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * GEMM_BK, n0,
+            tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * BK, n0,
                         p.b_batched ? z : 0);
           }
         }
@@ -131,14 +135,15 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           const uint32_t b_hi = a_hi + 2 * S::A_BYTES;
           const uint32_t b_lo = b_hi + S::B_BYTES;
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
+          for (int k = 0; k < BK / 16; ++k) {
             const uint32_t off = k * 32;  // 16 fp16 along K inside the swizzle span
-            const uint64_t dah = make_smem_desc_sw128(a_hi + off, 16, 1024);
-            const uint64_t dbh = make_smem_desc_sw128(b_hi + off, 16, 1024);
+            constexpr uint32_t LT = (BK == 64) ? 2u : 4u;  // SWIZZLE_128B : SWIZZLE_64B
+            const uint64_t dah = make_smem_desc(a_hi + off, 16, S::SBO, LT);
+            const uint64_t dbh = make_smem_desc(b_hi + off, 16, S::SBO, LT);
             umma_f16_ss(d_tmem, dah, dbh, idesc, (kb > 0 || k > 0) ? 1u : 0u);
             if (split) {
-              const uint64_t dal = make_smem_desc_sw128(a_lo + off, 16, 1024);
-              const uint64_t dbl = make_smem_desc_sw128(b_lo + off, 16, 1024);
+              const uint64_t dal = make_smem_desc(a_lo + off, 16, S::SBO, LT);
+              const uint64_t dbl = make_smem_desc(b_lo + off, 16, S::SBO, LT);
               umma_f16_ss(d_tmem, dal, dbh, idesc, 1u);
               umma_f16_ss(d_tmem, dah, dbl, idesc, 1u);
             }
@@ -279,32 +284,33 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   }
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int BK>
 static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, BK>;
+  constexpr int SWZ = BK * 2;
   const bool split = g.nsplit == 3;
   CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo;
   const int Kt = g.K1 + g.K2;
-  if (make_tmap_f16_3d(&ta_hi, g.a_hi, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+  if (make_tmap_f16_3d(&ta_hi, g.a_hi, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
   ta_lo = ta_hi;
-  if (split && make_tmap_f16_3d(&ta_lo, g.a_lo, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+  if (split && make_tmap_f16_3d(&ta_lo, g.a_lo, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
   ta2_hi = ta_hi;
   ta2_lo = ta_lo;
   if (g.K2 > 0) {
-    if (make_tmap_f16_3d(&ta2_hi, g.a2_hi, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+    if (make_tmap_f16_3d(&ta2_hi, g.a2_hi, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, BK, GEMM_BM, SWZ)) return 3;
     ta2_lo = ta2_hi;
-    if (split && make_tmap_f16_3d(&ta2_lo, g.a2_lo, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, GEMM_BK, GEMM_BM)) return 3;
+    if (split && make_tmap_f16_3d(&ta2_lo, g.a2_lo, g.K2, g.M, g.batch, g.a2_row_stride, g.a2_batch_stride, BK, GEMM_BM, SWZ)) return 3;
   }
   const int bb = g.b_batched ? g.batch : 1;
-  if (make_tmap_f16_3d(&tb_hi, g.b_hi, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, GEMM_BK, BN)) return 3;
+  if (make_tmap_f16_3d(&tb_hi, g.b_hi, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, BK, BN, SWZ)) return 3;
   tb_lo = tb_hi;
-  if (split && make_tmap_f16_3d(&tb_lo, g.b_lo, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, GEMM_BK, BN)) return 3;
+  if (split && make_tmap_f16_3d(&tb_lo, g.b_lo, Kt, g.N, bb, g.b_row_stride, g.b_batch_stride, BK, BN, SWZ)) return 3;
 
   GemmKernelParams p;
   p.M = g.M;
   p.N = g.N;
-  p.KB1 = g.K1 / GEMM_BK;
-  p.KB = Kt / GEMM_BK;
+  p.KB1 = g.K1 / BK;
+  p.KB = Kt / BK;
   p.b_batched = g.b_batched;
   p.nsplit = g.nsplit;
   p.out_mode = g.out_mode;
@@ -318,7 +324,7 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.out_batch_stride = g.out_batch_stride;
 
   const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float);
-  auto kern = gemm_f16split_kernel<BN, STAGES>;
+  auto kern = gemm_f16split_kernel<BN, STAGES, BK>;
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -335,11 +341,16 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
 
 int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   IMP_REQUIRE(g.nsplit == 1 || g.nsplit == 3, "gemm: nsplit must be 1 or 3");
-  IMP_REQUIRE(g.K1 > 0 && g.K1 % GEMM_BK == 0 && g.K2 % GEMM_BK == 0, "gemm: K segments must be multiples of 64 (got %d, %d)", g.K1, g.K2);
+  IMP_REQUIRE(g.K1 > 0 && g.K1 % 64 == 0 && g.K2 % 64 == 0, "gemm: K segments must be multiples of 64 (got %d, %d)", g.K1, g.K2);
   IMP_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0, "gemm: empty problem");
   IMP_REQUIRE(g.out_row_stride % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
-  if (g.N > 128) return launch_impl<256, 2>(g, stream);
-  return launch_impl<128, 3>(g, stream);
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("IMP_GEMM_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  if (g.N > 128) return variant == 1 ? launch_impl<256, 2, 64>(g, stream) : launch_impl<256, 4, 32>(g, stream);
+  return launch_impl<128, 3, 64>(g, stream);
 }
 
 }  // namespace imp

@@ -158,15 +158,23 @@ __host__ __device__ constexpr uint32_t make_idesc(uint32_t fmt_ab, uint32_t m, u
 // K-major tile (rows of 128 B = one swizzle span along K): SBO = 1024 (8 rows), LBO unused.
 // MN-major tile (128-B lines along MN, one line per k): SBO = 1024 (8 k), LBO = byte offset between
 // consecutive 128-B blocks along MN.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
-                                                         uint32_t sbo_bytes) {
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
   d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= static_cast<uint64_t>(1) << 46;
-  d |= static_cast<uint64_t>(2) << 61;
+  d |= static_cast<uint64_t>(layout_type) << 61;
   return d;
+}
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                         uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 2);
+}
+// 64-byte swizzle, K-major: rows of 64 B (32 fp16), 8-row atoms of 512 B -> SBO = 512
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return make_smem_desc(smem_addr, lbo_bytes, sbo_bytes, 4);
 }
 
 // TMEM -> registers: 32 lanes x 32 bit, N consecutive columns (thread i of the warp reads lane base+i).
