@@ -23,6 +23,9 @@ for name, N, K1, K2, mode in (('qkv n768 k256 f16', 768, 256, 0, ops.OUT_F16), (
     res = ops.Planes(o0, o1) if mode == ops.OUT_SPLIT_RESID else None
     ms = t(lambda: ops.gemm(a, W, M=T, N=N, K1=K1, K2=K2, a2=(A if K2 else None), a_row_stride=K1, a2_row_stride=K2, b_row_stride=K1 + K2,
                             bias=bias, out_mode=mode, out0=o0, out1=o1, out_row_stride=N, res=res))
+    ms1 = t(lambda: ops.gemm(a, W, M=T, N=N, K1=K1, K2=K2, a2=(A if K2 else None), a_row_stride=K1, a2_row_stride=K2, b_row_stride=K1 + K2,
+                            bias=bias, out_mode=mode, out0=o0, out1=o1, out_row_stride=N, res=res, nsplit=1))
+    print(f'    nsplit=1: {ms1:.3f} ms')
     fl = 2.0 * T * N * (K1 + K2)
     print(f'{name:28s} {ms:.3f} ms  useful {fl/ms/1e9:7.1f} TF/s  (x3 MMA {3*fl/ms/1e9:7.1f})')
 B, N = 64, 2000
