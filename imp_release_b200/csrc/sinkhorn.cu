@@ -15,6 +15,7 @@
 // torch.max on CPU).
 #include "sinkhorn.cuh"
 
+#include <cooperative_groups.h>
 #include <float.h>
 #include <stdlib.h>
 
@@ -419,6 +420,215 @@ __global__ void sk_matches_kernel(const float* __restrict__ row_max, const int* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Resident variant for small batches (one pair at N ~ 2000: the B = 1 latency path and the 2048^2 x 100-iteration
+// micro-benchmark): the whole matrix (16 MB) fits in the aggregate shared memory of one cooperative grid (2 CTAs/SM x
+// 8 rows x 8 KB), so it is read from HBM exactly once, all Sinkhorn iterations run out of shared memory inside ONE
+// launch with a grid-wide barrier per iteration, and only the final scores are written back.
+namespace cg = cooperative_groups;
+static constexpr int SKS_THREADS = 128;
+static constexpr int SKS_WARPS = 4;
+
+template <int NV>
+__global__ void __launch_bounds__(SKS_THREADS, 2) sk_resident_kernel(const SkParams p, float* col0, float* col1, float* col2,
+                                                                     unsigned long long* col_key, int iters) {
+  extern __shared__ __align__(16) float sk_smem[];
+  cg::grid_group grid = cg::this_grid();
+  const int ctas_per_mat = (p.N0max + 1 + p.rows_per_cta - 1) / p.rows_per_cta;
+  const int b = blockIdx.x / ctas_per_mat;
+  const SkDims d = sk_dims(p.n0s, p.n1s, b, p.N0max, p.N1max);
+  const int row0 = (blockIdx.x % ctas_per_mat) * p.rows_per_cta;
+  const int nrows = max(0, min(p.rows_per_cta, d.R - row0));
+  float* rows = sk_smem;                                  // [rows_per_cta][ldp]
+  float* s_v = rows + (size_t)p.rows_per_cta * p.ldp;     // [ldp]
+  float* s_col = s_v + p.ldp;                             // [ldp]
+  float* s_u = s_col + p.ldp;                             // [rows_per_cta]
+  const int warp = threadIdx.x >> 5;
+  const int C4 = (d.C + 3) & ~3;
+  const float bin = *p.bin_score;
+  float* cols[3] = {col0 + (long long)b * p.ldp, col1 + (long long)b * p.ldp, col2 + (long long)b * p.ldp};
+
+  // ---- load + softmax (same arithmetic as the streaming init pass)
+  for (int r = warp; r < nrows; r += SKS_WARPS) {
+    const int i = row0 + r;
+    const bool bin_row = (i == d.R - 1);
+    float* srow = rows + (size_t)r * p.ldp;
+    const float* drow = p.dist + b * p.dist_bs + (long long)i * p.ldd;
+    float m = -FLT_MAX;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane_id() + 32 * k);
+      if (c0 < C4) {
+        float4 t = make_float4(bin, bin, bin, bin);
+        if (!bin_row && c0 < d.C - 1) t = *reinterpret_cast<const float4*>(drow + c0);  // ldd >= roundup4(N1)
+        t.x = (c0 + 0 < d.C) ? ((bin_row || c0 + 0 == d.C - 1) ? bin : t.x) : -FLT_MAX;
+        t.y = (c0 + 1 < d.C) ? ((bin_row || c0 + 1 == d.C - 1) ? bin : t.y) : -FLT_MAX;
+        t.z = (c0 + 2 < d.C) ? ((bin_row || c0 + 2 == d.C - 1) ? bin : t.z) : -FLT_MAX;
+        t.w = (c0 + 3 < d.C) ? ((bin_row || c0 + 3 == d.C - 1) ? bin : t.w) : -FLT_MAX;
+        *reinterpret_cast<float4*>(srow + c0) = t;
+        m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+      }
+    }
+    m = warp_max(m);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane_id() + 32 * k);
+      if (c0 < C4) {
+        float4 t = *reinterpret_cast<const float4*>(srow + c0);
+        t.x = sk_exp(t.x - m);
+        t.y = sk_exp(t.y - m);
+        t.z = sk_exp(t.z - m);
+        t.w = sk_exp(t.w - m);
+        *reinterpret_cast<float4*>(srow + c0) = t;
+        sum += (t.x + t.y) + (t.z + t.w);
+      }
+    }
+    sum = warp_sum(sum);
+    const float inv_sum = 1.0f / sum;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane_id() + 32 * k);
+      if (c0 < C4) {
+        float4 t = *reinterpret_cast<const float4*>(srow + c0);
+        t.x *= inv_sum;
+        t.y *= inv_sum;
+        t.z *= inv_sum;
+        t.w *= inv_sum;
+        *reinterpret_cast<float4*>(srow + c0) = t;
+      }
+    }
+    if (lane_id() == 0) s_u[r] = 1.f;
+  }
+  __syncthreads();
+
+  // ---- Sinkhorn iterations out of shared memory
+  for (int it = 0; it < iters; ++it) {
+    const float* prev = cols[(it + 2) % 3];
+    float* accg = cols[it % 3];
+    float* zero = cols[(it + 1) % 3];
+    if (blockIdx.x % ctas_per_mat == 0)
+      for (int j = threadIdx.x; j < p.ldp; j += SKS_THREADS) zero[j] = 0.f;
+    for (int c0 = 4 * threadIdx.x; c0 < C4; c0 += 4 * SKS_THREADS) {
+      *reinterpret_cast<float4*>(s_v + c0) = (it == 0) ? make_float4(c0 + 0 < d.C ? 1.f : 0.f, c0 + 1 < d.C ? 1.f : 0.f,
+                                                                     c0 + 2 < d.C ? 1.f : 0.f, c0 + 3 < d.C ? 1.f : 0.f)
+                                                       : v_from_colsum(prev, c0, d.C);
+      *reinterpret_cast<float4*>(s_col + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    float4 acc[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = warp; r < nrows; r += SKS_WARPS) {
+      const int i = row0 + r;
+      const float* srow = rows + (size_t)r * p.ldp;
+      float rs = 0.f;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
+          rs += (t.x * v.x + t.y * v.y) + (t.z * v.z + t.w * v.w);
+        }
+      }
+      rs = warp_sum(rs);
+      const float ui = ((i == d.R - 1) ? (float)d.R : 1.f) / (rs + SK_EPS);
+      if (lane_id() == 0) s_u[r] = ui;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C) {
+          const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+          acc[k].x += t.x * ui;
+          acc[k].y += t.y * ui;
+          acc[k].z += t.z * ui;
+          acc[k].w += t.w * ui;
+        }
+      }
+    }
+    if (nrows > 0) {
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        const int c0 = 4 * (lane_id() + 32 * k);
+        if (c0 < d.C && warp < nrows) {
+          atomicAdd(s_col + c0 + 0, acc[k].x);
+          atomicAdd(s_col + c0 + 1, acc[k].y);
+          atomicAdd(s_col + c0 + 2, acc[k].z);
+          atomicAdd(s_col + c0 + 3, acc[k].w);
+        }
+      }
+    }
+    __syncthreads();
+    if (nrows > 0)
+      for (int j = threadIdx.x; j < d.C; j += SKS_THREADS) atomicAdd(accg + j, s_col[j]);
+    grid.sync();
+  }
+
+  // ---- final scaling, row arg-max / masses, column arg-max, optional write-back
+  const float* last = cols[(iters + 2) % 3];
+  for (int c0 = 4 * threadIdx.x; c0 < C4; c0 += 4 * SKS_THREADS)
+    *reinterpret_cast<float4*>(s_v + c0) = iters > 0 ? v_from_colsum(last, c0, d.C)
+                                                     : make_float4(c0 + 0 < d.C ? 1.f : 0.f, c0 + 1 < d.C ? 1.f : 0.f,
+                                                                   c0 + 2 < d.C ? 1.f : 0.f, c0 + 3 < d.C ? 1.f : 0.f);
+  __syncthreads();
+  for (int r = warp; r < nrows; r += SKS_WARPS) {
+    const int i = row0 + r;
+    const float* srow = rows + (size_t)r * p.ldp;
+    const float ui = iters > 0 ? s_u[r] : 1.f;
+    const bool inner_row = i < d.R - 1;
+    float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
+    if (lane_id() == 0) p.u[(long long)b * (p.N0max + 1) + i] = ui;
+    float best = -1.f, mass = 0.f;
+    int best_j = 0x7fffffff;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+      const int c0 = 4 * (lane_id() + 32 * k);
+      if (c0 >= d.C) {
+        if (c0 < p.ldp && p.write_scores) *reinterpret_cast<float4*>(prow + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
+        continue;
+      }
+      const float4 t = *reinterpret_cast<const float4*>(srow + c0);
+      const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
+      const float o[4] = {(t.x * ui) * v.x, (t.y * ui) * v.y, (t.z * ui) * v.z, (t.w * ui) * v.w};
+      // the resident path never materialised softmax(M) in HBM: P receives either the final scores or the plain p
+      *reinterpret_cast<float4*>(prow + c0) = p.write_scores ? make_float4(o[0], o[1], o[2], o[3]) : t;
+      if (inner_row) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (c0 + q < d.C - 1) {
+            mass += o[q];
+            if (o[q] > best) {
+              best = o[q];
+              best_j = c0 + q;
+            }
+            atomicMax(col_key + (long long)b * p.N1max + c0 + q,
+                      (static_cast<unsigned long long>(__float_as_uint(o[q])) << 32) | (0xFFFFFFFFu - (unsigned)i));
+            if (p.col_mass) atomicAdd(p.col_mass + (long long)b * p.N1max + c0 + q, o[q]);
+          }
+        }
+      }
+    }
+    if (inner_row) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
+        if (ob > best || (ob == best && oj < best_j)) {
+          best = ob;
+          best_j = oj;
+        }
+      }
+      mass = warp_sum(mass);
+      if (lane_id() == 0) {
+        p.row_max[(long long)b * p.N0max + i] = best;
+        p.row_arg[(long long)b * p.N0max + i] = best_j;
+        if (p.row_mass) p.row_mass[(long long)b * p.N0max + i] = mass;
+      }
+    }
+  }
+}
+
 // Optional L2-resident chunking (IMP_SK_L2_MB=<MB>): cut a big batch into chunks that fit in the 126 MB L2 and run the
 // whole 22-launch sequence per chunk.  Measured on B200 at B=64, N=2000: 5.29 ms streaming vs 9.5 / 7.1 / 6.6 ms with
 // 48 / 80 / 100 MB chunks (small launches + per-launch overhead lose more than the L2 hits win), so it is OFF by default.
@@ -455,6 +665,47 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   IMP_CUDA_OK(cudaMemsetAsync(a.col_key, 0, (size_t)a.batch * a.N1max * sizeof(unsigned long long), st));
   if (a.col_mass) IMP_CUDA_OK(cudaMemsetAsync(a.col_mass, 0, (size_t)a.batch * a.N1max * sizeof(float), st));
   IMP_CUDA_OK(cudaMemsetAsync(a.colbuf, 0, (size_t)a.batch * a.ldp * sizeof(float), st));  // col[0]
+
+  {  // small problems: everything resident in shared memory, one cooperative launch
+    static int use_resident = -1;
+    if (use_resident < 0) {
+      const char* e = getenv("IMP_SK_RESIDENT");
+      use_resident = e ? atoi(e) : 1;
+    }
+    const long long wave = 2LL * num_sms();
+    int rpc = (int)(((long long)a.batch * R + wave - 1) / wave);
+    rpc = (rpc + SKS_WARPS - 1) / SKS_WARPS * SKS_WARPS;
+    const int ctas_per_mat = (R + rpc - 1) / rpc;
+    const size_t smem_res = ((size_t)rpc + 2) * row_bytes + (size_t)rpc * sizeof(float) + 16;
+    if (use_resident && (long long)a.batch * ctas_per_mat <= wave && smem_res <= (size_t)SKR_SMEM_BUDGET) {
+      static bool conf = false;
+      if (!conf) {
+        IMP_CUDA_OK(cudaFuncSetAttribute(sk_resident_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
+        IMP_CUDA_OK(cudaFuncSetAttribute(sk_resident_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        conf = true;
+      }
+      int max_blocks = 0;
+      IMP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, sk_resident_kernel<NV>, SKS_THREADS, smem_res));
+      if ((long long)max_blocks * num_sms() >= (long long)a.batch * ctas_per_mat) {
+        SkParams p;
+        p.dist = a.dist; p.dist_bs = a.dist_batch_stride; p.ldd = a.ldd; p.bin_score = a.bin_score;
+        p.P = a.P; p.p_bs = a.p_batch_stride; p.ldp = a.ldp; p.u = a.u;
+        p.col_prev = nullptr; p.col_acc = nullptr; p.col_zero = nullptr;
+        p.row_max = a.row_max; p.row_arg = a.row_arg; p.row_mass = a.row_mass; p.col_mass = a.col_mass;
+        p.n0s = a.n0s; p.n1s = a.n1s; p.N0max = a.N0max; p.N1max = a.N1max;
+        p.rows_per_cta = rpc; p.ring_slots = 0; p.do_iter = iters > 0; p.write_scores = a.write_scores;
+        float* c0 = a.colbuf;
+        float* c1 = a.colbuf + (size_t)a.batch * a.ldp;
+        float* c2 = a.colbuf + 2 * (size_t)a.batch * a.ldp;
+        unsigned long long* ck = reinterpret_cast<unsigned long long*>(a.col_key);
+        int it = iters;
+        void* args[] = {&p, &c0, &c1, &c2, &ck, &it};
+        IMP_CUDA_OK(cudaLaunchCooperativeKernel((void*)sk_resident_kernel<NV>, dim3(a.batch * ctas_per_mat), dim3(SKS_THREADS),
+                                                args, smem_res, st));
+        return 0;
+      }
+    }
+  }
 
   for (int b0 = 0; b0 < a.batch; b0 += chunk) {
     const int nb = (a.batch - b0 < chunk) ? a.batch - b0 : chunk;

@@ -68,10 +68,23 @@ class GM(nn.Module):
         self._last_sk = None
 
     # ------------------------------------------------------------------ engine / packing
+    def _apply(self, fn, *a, **kw):            # .cuda() / .to() / .float(): parameters move -> repack lazily
+        self._engine = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):       # new weights -> repack lazily
+        self._engine = None
+        return super().load_state_dict(*a, **kw)
+
+    def invalidate_packed_weights(self):
+        """Call after modifying parameters in place (load_state_dict / .to() are tracked automatically)."""
+        self._engine = None
+
     def engine(self) -> Engine:
-        params = list(self.parameters())
-        key = (str(params[0].device), tuple(p._version for p in params), tuple(p.data_ptr() for p in params[:4]))
+        # cheap staleness check on the hot path; the full per-parameter scan only runs when (re)packing
+        key = (self.bin_score.device, self.bin_score.data_ptr(), self.kenc.encoder[0].weight._version)
         if self._engine is None or key != self._engine_key:
+            params = list(self.parameters())
             if not params[0].is_cuda:
                 raise ops._lib.ImpLibraryError('move the model to a CUDA device first (net.cuda()); the B200 path has '
                                                'no CPU implementation')
@@ -123,6 +136,7 @@ class GM(nn.Module):
     def _begin(self, desc0, desc1, nk0, nk1, sc0, sc1) -> RunState:
         """Stack both images token-major, run the keypoint encoder, x = desc + enc (nets/gms.py:158-172)."""
         eng = self.engine()
+        self._io = None            # the workspace state is about to be overwritten
         B, N0, N1 = desc0.shape[0], desc0.shape[1], desc1.shape[1]
         dev = desc0.device
         Np = max(N0, N1)
@@ -235,7 +249,13 @@ class GM(nn.Module):
         return enc[:B, :N0].transpose(1, 2), enc[B:, :N1].transpose(1, 2)
 
     def _load_state(self, desc0, desc1) -> RunState:
-        """Channels-first caller tensors -> token-major planes in the workspace (boundary conversion)."""
+        """Channels-first caller tensors -> token-major planes in the workspace (boundary conversion).  If the caller
+        hands back exactly the tensors the previous call returned (eval/matching.py:51-58 does), the planes already in
+        the workspace are the full-precision state and the conversion is skipped."""
+        io = getattr(self, '_io', None)
+        if (io is not None and desc0 is io[0] and desc1 is io[1] and desc0._version == io[2] and desc1._version == io[3]
+                and self._st is not None and self._engine is not None):
+            return self._st
         eng = self.engine()
         B, N0, N1 = desc0.shape[0], desc0.shape[2], desc1.shape[2]
         dev = desc0.device
@@ -254,7 +274,9 @@ class GM(nn.Module):
 
     def _export_state(self, st: RunState):
         x = st.ws.X.float().view(2 * st.B, st.ws.Np, D)
-        return x[:st.B, :st.N0].transpose(1, 2), x[st.B:, :st.N1].transpose(1, 2)
+        o0, o1 = x[:st.B, :st.N0].transpose(1, 2), x[st.B:, :st.N1].transpose(1, 2)
+        self._io = (o0, o1, o0._version, o1._version)
+        return o0, o1
 
     def forward_one_layer(self, desc0, desc1, M0, M1, layer_i):
         """nets/gms.py:260-282 / nets/adgm.py:528-550: one self or cross layer on both images; stateful (the stashed
