@@ -700,9 +700,11 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
         unsigned long long* ck = reinterpret_cast<unsigned long long*>(a.col_key);
         int it = iters;
         void* args[] = {&p, &c0, &c1, &c2, &ck, &it};
-        IMP_CUDA_OK(cudaLaunchCooperativeKernel((void*)sk_resident_kernel<NV>, dim3(a.batch * ctas_per_mat), dim3(SKS_THREADS),
-                                                args, smem_res, st));
-        return 0;
+        if (cudaLaunchCooperativeKernel((void*)sk_resident_kernel<NV>, dim3(a.batch * ctas_per_mat), dim3(SKS_THREADS), args,
+                                        smem_res, st) == cudaSuccess)
+          return 0;
+        (void)cudaGetLastError();  // cooperative launch unavailable (e.g. under a profiler / MPS): use the streaming path
+        use_resident = 0;
       }
     }
   }

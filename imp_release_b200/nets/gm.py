@@ -152,10 +152,20 @@ class GM(nn.Module):
             desc[:B, :N0], desc[B:, :N1] = desc0, desc1
             nk[:B, :N0], nk[B:, :N1] = nk0, nk1
             sc[:B, :N0], sc[B:, :N1] = sc0, sc1
-        n_tok = torch.tensor([N0] * B + [N1] * B, dtype=torch.int32, device=dev)
+        n_tok = self._n_tok(B, N0, N1, dev)
         eng.encode_keypoints(ws, nk, sc, n_tok, ws.tok_f32)
         ops.split_planes(desc.view(-1, D), out=ws.X, addend=ws.tok_f32)
         return RunState(ws, B, N0, N1, n_tok)
+
+    def _n_tok(self, B, N0, N1, dev) -> torch.Tensor:
+        """Per-image token counts [2B] (cached: no host-to-device copy on the hot path, CUDA-graph capturable)."""
+        key = (B, N0, N1, str(dev))
+        cache = self.__dict__.setdefault('_n_tok_cache', {})
+        if key not in cache:
+            if len(cache) > 64:
+                cache.clear()
+            cache[key] = torch.tensor([N0] * B + [N1] * B, dtype=torch.int32, device=dev)
+        return cache[key]
 
     def _score(self, st: RunState, ni: int, p: float, keep_scores: bool, want_mass: bool = False, write_scores=None):
         """final_proj -> dist -> Sinkhorn / dual-softmax -> mutual matches (nets/gm.py:290-320) on the full sets."""
@@ -242,7 +252,7 @@ class GM(nn.Module):
         sc = norm_kpts0.new_zeros(2 * B, Np, dtype=torch.float32)
         nk[:B, :N0], nk[B:, :N1] = norm_kpts0, norm_kpts1
         sc[:B, :N0], sc[B:, :N1] = scores0, scores1
-        n_tok = torch.tensor([N0] * B + [N1] * B, dtype=torch.int32, device=dev)
+        n_tok = self._n_tok(B, N0, N1, dev)
         enc = torch.empty(2 * B * Np, D, dtype=torch.float32, device=dev)
         eng.encode_keypoints(ws, nk, sc, n_tok, enc)
         enc = enc.view(2 * B, Np, D)
@@ -267,8 +277,7 @@ class GM(nn.Module):
         ops.split_planes(x.view(-1, D), out=ws.X)
         st = self._st
         if st is None or st.ws is not ws or st.B != B or st.N0 != N0 or st.N1 != N1:
-            n_tok = torch.tensor([N0] * B + [N1] * B, dtype=torch.int32, device=dev)
-            st = RunState(ws, B, N0, N1, n_tok)
+            st = RunState(ws, B, N0, N1, self._n_tok(B, N0, N1, dev))
             self._st = st
         return st
 

@@ -167,7 +167,7 @@ def test_sinkhorn_and_matches(B, N0, N1, iters):
     ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws2, write_scores=False)
     k0, k1, q0, q1 = ops.matches(ws2.row_max, ws2.row_arg, ws2.col_key, 0.2, N0, N1, B)
     # (column sums are accumulated with float atomics, so two runs agree to rounding, not bit-for-bit)
-    assert torch.equal(k0, i0) and torch.equal(k1, i1) and float((q0 - m0).abs().max()) < 1e-6
+    assert torch.equal(k0, i0) and torch.equal(k1, i1) and float((q0 - m0).abs().max()) < 1e-5
     assert float((ws2.row_mass - ws.row_mass).abs().max()) < 1e-5
     # compute_matches on a caller-provided tensor
     rmx, rarg, ckey = ops.score_argmax(ws.scores(), N0, N1)

@@ -75,3 +75,23 @@ def test_adagmn_batched_pruning(N0, N1, B, seed):
     assert min(kept) < min(N0, N1), 'test vector must actually prune'
     compare(out, ref)
     assert out['scores'][0].shape == ref['scores'][0].shape
+
+
+def test_cuda_graph_replay_matches_eager():
+    from imp_release_b200.graphed import GraphedMatcher
+    c = cfg(9)
+    sd = synth.make_state_dict('DGNNS', 9, seed=7)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    d1 = to_cuda(synth.make_pair_batch(seed=31, batch=1, n0=700, n1=640))
+    d2 = to_cuda(synth.make_pair_batch(seed=32, batch=1, n0=700, n1=640))
+    g = GraphedMatcher(net, d1, p=0.2, only_last=True)
+    for d in (d2, d1, d2):
+        with torch.no_grad():
+            eager = net.produce_matches(d, p=0.2, only_last=True)
+            i_e, m_e = eager['indices0'][-1].clone(), eager['mscores0'][-1].clone()
+        out = g(d)
+        torch.cuda.synchronize()
+        assert torch.equal(out['indices0'][-1], i_e)
+        assert float((out['mscores0'][-1] - m_e).abs().max()) < 1e-5
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches({k: v.cpu() for k, v in d2.items()}, only_last=True)
+    assert torch.equal(out['indices0'][-1].cpu(), ref['indices0'][-1])

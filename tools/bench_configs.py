@@ -33,6 +33,10 @@ data = {k: v.to(dev) for k, v in synth.make_pair_batch(seed=5, batch=1, n0=1987,
 with torch.no_grad():
     ms = timed(lambda: net.produce_matches(data, p=0.2, only_last=True), warm=3, n=10)
 out['imp_b1_15it_only_last'] = {'ms_per_pair': ms, 'pairs_per_s': 1e3 / ms}
+from imp_release_b200.graphed import GraphedMatcher
+g = GraphedMatcher(net, data, p=0.2, only_last=True)
+ms = timed(lambda: g(data), warm=3, n=20)
+out['imp_b1_15it_only_last_cuda_graph'] = {'ms_per_pair': ms, 'pairs_per_s': 1e3 / ms}
 # per-layer API (eval/matching.py sequence without the host RANSAC): encode + 15 x (self, cross) + 7 scorings
 def layer_api():
     nk0 = normalize_keypoints(data['keypoints0'], data['image0'].shape); nk1 = normalize_keypoints(data['keypoints1'], data['image1'].shape)
