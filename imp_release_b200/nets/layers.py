@@ -13,8 +13,13 @@ SHARING_LAYERS = [False, False] * 2 + [False, False, True, True] * 21   # nets/g
 def normalize_keypoints(kpts: torch.Tensor, image_shape) -> torch.Tensor:
     """nets/layers.py:49-56.  Boundary helper (2N floats); called by eval/matching.py:24 on the caller's device."""
     _, _, height, width = image_shape
-    size = kpts.new_tensor([float(width), float(height)])
-    return (kpts - size / 2) / (size.max() * 0.7)
+    # same fp32 arithmetic as the reference (centre = size/2, scale = fp32(max(W,H)) * 0.7) but with host scalars, so
+    # that no host->device copy happens here (keeps the forward CUDA-graph capturable)
+    scale = float(torch.tensor(float(max(width, height)), dtype=torch.float32) * 0.7)
+    out = kpts.clone()
+    out[..., 0].sub_(float(width) / 2)
+    out[..., 1].sub_(float(height) / 2)
+    return out.div_(scale)
 
 
 def _conv(cin: int, cout: int) -> nn.Conv1d:
