@@ -147,7 +147,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -310,12 +310,29 @@ def run_gpu(args, rank, world, local_rank):
         'kernels': kernels,
         'cpu_baseline': cpu_baseline,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The driver parses ONE JSON line from stdout: everything else (NCCL banners, warnings) goes to stderr."""
+    data = (json.dumps(line) + '\n').encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)            # library chatter printed to fd 1 (e.g. "NCCL version ...") lands on stderr
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=5)

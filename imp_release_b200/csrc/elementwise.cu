@@ -5,6 +5,8 @@
 #include "common.h"
 #include "ptx.cuh"
 
+#include <stdlib.h>
+
 namespace imp {
 
 // x[n] (fp32) (+ optional addend y[n]) -> hi/lo fp16 planes.  4 elements per thread, 16 B loads.
@@ -116,10 +118,10 @@ instnorm_relu_split_kernel(const float* __restrict__ H, long long h_bs, int ldh,
 // Slab variant for the wide MLP hidden layer: one CTA owns 16 channels of one image and keeps the whole [N, 16] slab
 // (128 KB at N = 2000) in shared memory, so H is read from HBM exactly once (stats and normalisation both run out of
 // smem) and the hi/lo planes are written once: 12 B per element, the minimum for a stand-alone pass.
-static constexpr int INS_CH = 16;
 static constexpr int INS_THREADS = 512;
 
-__global__ void __launch_bounds__(INS_THREADS, 1)
+template <int INS_CH, int MINB>
+__global__ void __launch_bounds__(INS_THREADS, MINB)
 instnorm_slab_kernel(const float* __restrict__ H, long long h_bs, int ldh, const int* __restrict__ ns, int Nmax, float eps,
                      __half* __restrict__ out_hi, __half* __restrict__ out_lo, long long o_bs, int ldo, int relu) {
   extern __shared__ __align__(16) float slab[];  // [n][16]
@@ -128,30 +130,32 @@ instnorm_slab_kernel(const float* __restrict__ H, long long h_bs, int ldh, const
   const int b = blockIdx.y;
   const int c0 = blockIdx.x * INS_CH;
   const int n = ns ? ns[b] : Nmax;
-  const int q = threadIdx.x & 3;  // which float4 of the 16 channels this thread always handles
+  constexpr int QPT = INS_CH / 4;           // float4 groups per token
+  constexpr int QSH = (QPT == 4) ? 2 : 1;   // log2(QPT)
+  const int q = threadIdx.x & (QPT - 1);    // which float4 of the slab's channels this thread always handles
   const float* h = H + b * h_bs + c0;
   const float4 shift = n > 0 ? *reinterpret_cast<const float4*>(h + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f), sq = s;
-  const int total = n * 4;
+  const int total = n * QPT;
 #pragma unroll 8
   for (int i = threadIdx.x; i < total; i += INS_THREADS) {
-    const int t = i >> 2;
+    const int t = i >> QSH;
     const float4 v = *reinterpret_cast<const float4*>(h + (long long)t * ldh + 4 * q);
     *reinterpret_cast<float4*>(slab + t * INS_CH + 4 * q) = v;
     const float4 d = make_float4(v.x - shift.x, v.y - shift.y, v.z - shift.z, v.w - shift.w);
     s.x += d.x; s.y += d.y; s.z += d.z; s.w += d.w;
     sq.x += d.x * d.x; sq.y += d.y * d.y; sq.z += d.z * d.z; sq.w += d.w * d.w;
   }
-  // lanes with equal q: xor 4, 8, 16
+  // lanes with equal q: xor QPT, 2 QPT, ...
 #pragma unroll
-  for (int o = 4; o < 32; o <<= 1) {
+  for (int o = QPT; o < 32; o <<= 1) {
     s.x += __shfl_xor_sync(0xffffffffu, s.x, o); s.y += __shfl_xor_sync(0xffffffffu, s.y, o);
     s.z += __shfl_xor_sync(0xffffffffu, s.z, o); s.w += __shfl_xor_sync(0xffffffffu, s.w, o);
     sq.x += __shfl_xor_sync(0xffffffffu, sq.x, o); sq.y += __shfl_xor_sync(0xffffffffu, sq.y, o);
     sq.z += __shfl_xor_sync(0xffffffffu, sq.z, o); sq.w += __shfl_xor_sync(0xffffffffu, sq.w, o);
   }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (lane < 4) {
+  if (lane < QPT) {
     float* ps = &s_part[warp][0][4 * lane];
     float* pq = &s_part[warp][1][4 * lane];
     ps[0] = s.x; ps[1] = s.y; ps[2] = s.z; ps[3] = s.w;
@@ -179,7 +183,7 @@ instnorm_slab_kernel(const float* __restrict__ H, long long h_bs, int ldh, const
   __half* ol = out_lo + b * o_bs + c0 + 4 * q;
 #pragma unroll 4
   for (int i = threadIdx.x; i < total; i += INS_THREADS) {
-    const int t = i >> 2;
+    const int t = i >> QSH;
     const float4 v = *reinterpret_cast<const float4*>(slab + t * INS_CH + 4 * q);
     float y[4] = {(v.x - mean.x) * rstd.x, (v.y - mean.y) * rstd.y, (v.z - mean.z) * rstd.z, (v.w - mean.w) * rstd.w};
     __half hh[4], ll[4];
@@ -197,15 +201,36 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
                                float eps, int relu, void* out_hi, void* out_lo, float* out_f32, long long o_bs,
                                int ldo, cudaStream_t st) {
   if (batch == 0 || Nmax == 0) return 0;
-  const size_t slab_bytes = (size_t)Nmax * INS_CH * sizeof(float);
-  if (out_f32 == nullptr && C % INS_CH == 0 && C >= 256 && ldh % 4 == 0 && ldo % 4 == 0 && h_bs % 4 == 0 && o_bs % 4 == 0 &&
-      slab_bytes <= 200 * 1024 && (reinterpret_cast<uintptr_t>(H) & 15) == 0) {
+  const bool aligned = out_f32 == nullptr && C % 16 == 0 && C >= 256 && ldh % 4 == 0 && ldo % 4 == 0 && h_bs % 4 == 0 &&
+                       o_bs % 4 == 0 && (reinterpret_cast<uintptr_t>(H) & 15) == 0;
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("IMP_IN_VARIANT");
+    variant = e ? atoi(e) : 0;
+  }
+  // 8-channel slabs (64 KB at N = 2000): two CTAs per SM, so one CTA's load/statistics phase overlaps the other's
+  // normalise/store phase; 16-channel slabs (one CTA per SM) for longer images
+  if (aligned && variant == 0 && (size_t)Nmax * 8 * sizeof(float) <= 100 * 1024) {
+    auto kern = instnorm_slab_kernel<8, 2>;
     static bool configured = false;
     if (!configured) {
-      IMP_CUDA_OK(cudaFuncSetAttribute(instnorm_slab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       configured = true;
     }
-    instnorm_slab_kernel<<<dim3(C / INS_CH, batch), INS_THREADS, slab_bytes, st>>>(
+    kern<<<dim3(C / 8, batch), INS_THREADS, (size_t)Nmax * 8 * sizeof(float), st>>>(
+        H, h_bs, ldh, ns, Nmax, eps, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), o_bs, ldo, relu);
+    IMP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
+  if (aligned && (size_t)Nmax * 16 * sizeof(float) <= 200 * 1024) {
+    auto kern = instnorm_slab_kernel<16, 1>;
+    static bool configured = false;
+    if (!configured) {
+      IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      configured = true;
+    }
+    kern<<<dim3(C / 16, batch), INS_THREADS, (size_t)Nmax * 16 * sizeof(float), st>>>(
         H, h_bs, ldh, ns, Nmax, eps, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), o_bs, ldo, relu);
     IMP_CUDA_OK(cudaGetLastError());
     return 0;
