@@ -206,10 +206,11 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("IMP_IN_VARIANT");
-    variant = e ? atoi(e) : 0;
+    variant = e ? atoi(e) : 1;
   }
-  // 8-channel slabs (64 KB at N = 2000): two CTAs per SM, so one CTA's load/statistics phase overlaps the other's
-  // normalise/store phase; 16-channel slabs (one CTA per SM) for longer images
+  // Measured on B200 (tools/in_probe.py, 128 x 2000 x 512): 16-channel slabs, one CTA/SM: 0.315 ms (3.3 TB/s);
+  // 8-channel slabs, two CTAs/SM: 0.523 ms -- 32-byte accesses per token waste half of every DRAM burst.  So the
+  // 8-channel variant is opt-in (IMP_IN_VARIANT=0) only.
   if (aligned && variant == 0 && (size_t)Nmax * 8 * sizeof(float) <= 100 * 1024) {
     auto kern = instnorm_slab_kernel<8, 2>;
     static bool configured = false;
