@@ -52,6 +52,8 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC;  // [ACC]
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [ACC][BN] bias slice of the tile being drained
+  // per-epilogue-warp staging tile: 32 rows x 128 B payload, 144 B pitch (conflict-free for 16-byte accesses)
+  uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + ACC * BN);
 
   const int warp = threadIdx.x >> 5;
   const bool split = p.nsplit == 3;
@@ -184,21 +186,56 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         for (int j = 0; j < 32; ++j) v[j] = fmaf(__uint_as_float(r[j]), p.alpha, bias_t[c * 32 + j]);
         if (c + 1 < nchunks) tmem_ld_x32(t_row + (c + 1) * 32, r);  // next chunk's TMEM read overlaps this chunk's stores
         const bool full = nc + 32 <= p.N;
-        if (!row_ok) continue;
-        if (p.out_mode == GEMM_OUT_F32) {
-          float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
-          if (full) {
+        if (full) {
+          // Coalesced path: the warp's 32 x 32 sub-tile goes through a warp-private shared-memory tile so that
+          // global memory sees whole 64/128-byte row segments instead of 32 scattered 16-byte pieces per instruction.
+          uint8_t* stg = s_stage + q * (32 * 144);
+          const int l = lane_id();
+          const long long wrow0 = (long long)z * p.out_batch_stride + (long long)(m0 + q * 32) * p.out_row_stride + nc;
+          const int rows_ok = min(32, p.M - (m0 + q * 32));  // rows of this warp that exist (may be <= 0)
+          if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {  // 8 rows x (64 B hi + 64 B lo) per pass
+              const int r = it * 8 + (l >> 2), seg = l & 3;
+              uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
+              if (r < rows_ok) {
+                hv = *reinterpret_cast<const uint4*>(p.res_hi + wrow0 + (long long)r * p.out_row_stride + seg * 8);
+                lv = *reinterpret_cast<const uint4*>(p.res_lo + wrow0 + (long long)r * p.out_row_stride + seg * 8);
+              }
+              *reinterpret_cast<uint4*>(stg + r * 144 + seg * 16) = hv;
+              *reinterpret_cast<uint4*>(stg + r * 144 + 64 + seg * 16) = lv;
+            }
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const uint4 ra = *reinterpret_cast<const uint4*>(stg + l * 144 + j * 16);
+              const uint4 rb = *reinterpret_cast<const uint4*>(stg + l * 144 + 64 + j * 16);
+              const __half2* ah = reinterpret_cast<const __half2*>(&ra);
+              const __half2* bh = reinterpret_cast<const __half2*>(&rb);
+#pragma unroll
+              for (int t2 = 0; t2 < 4; ++t2) {
+                const float2 fa = __half22float2(ah[t2]);
+                const float2 fb = __half22float2(bh[t2]);
+                v[8 * j + 2 * t2] += fa.x + fb.x;
+                v[8 * j + 2 * t2 + 1] += fa.y + fb.y;
+              }
+            }
+            __syncwarp();
+          }
+          if (p.out_mode == GEMM_OUT_F32) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
+              *reinterpret_cast<float4*>(stg + l * 144 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            __syncwarp();
+            float* o = reinterpret_cast<float*>(p.out0) + wrow0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) o[j] = v[j];
-          }
-        } else if (p.out_mode == GEMM_OUT_F16) {
-          __half* o = reinterpret_cast<__half*>(p.out0) + obase + nc;
-          if (full) {
+            for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per pass
+              const int r = it * 4 + (l >> 3), seg = l & 7;
+              if (r < rows_ok)
+                *reinterpret_cast<float4*>(o + (long long)r * p.out_row_stride + seg * 4) =
+                    *reinterpret_cast<const float4*>(stg + r * 144 + seg * 16);
+            }
+          } else if (p.out_mode == GEMM_OUT_F16) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint4 pk;
@@ -206,45 +243,18 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
               pk.y = pack_half2(v[j + 2], v[j + 3]);
               pk.z = pack_half2(v[j + 4], v[j + 5]);
               pk.w = pack_half2(v[j + 6], v[j + 7]);
-              *reinterpret_cast<uint4*>(o + j) = pk;
+              *reinterpret_cast<uint4*>(stg + l * 144 + j * 2) = pk;
+            }
+            __syncwarp();
+            __half* o = reinterpret_cast<__half*>(p.out0) + wrow0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {  // 8 rows x 64 B per pass
+              const int r = it * 8 + (l >> 2), seg = l & 3;
+              if (r < rows_ok)
+                *reinterpret_cast<uint4*>(o + (long long)r * p.out_row_stride + seg * 8) =
+                    *reinterpret_cast<const uint4*>(stg + r * 144 + seg * 16);
             }
           } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nc + j < p.N) o[j] = __float2half_rn(v[j]);
-          }
-        } else {
-          __half* oh = reinterpret_cast<__half*>(p.out0) + obase + nc;
-          __half* ol = reinterpret_cast<__half*>(p.out1) + obase + nc;
-          if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
-            const __half* rh = p.res_hi + obase + nc;
-            const __half* rl = p.res_lo + obase + nc;
-            if (full) {
-              uint4 ra[4], rb[4];
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {  // issue all residual loads before using any
-                ra[j] = *reinterpret_cast<const uint4*>(rh + 8 * j);
-                rb[j] = *reinterpret_cast<const uint4*>(rl + 8 * j);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __half2* ah = reinterpret_cast<const __half2*>(&ra[j]);
-                const __half2* bh = reinterpret_cast<const __half2*>(&rb[j]);
-#pragma unroll
-                for (int t2 = 0; t2 < 4; ++t2) {
-                  const float2 fa = __half22float2(ah[t2]);
-                  const float2 fb = __half22float2(bh[t2]);
-                  v[8 * j + 2 * t2] += fa.x + fb.x;
-                  v[8 * j + 2 * t2 + 1] += fa.y + fb.y;
-                }
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j)
-                if (nc + j < p.N) v[j] += __half2float(rh[j]) + __half2float(rl[j]);
-            }
-          }
-          if (full) {
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               uint32_t hi[4], lo[4];
@@ -257,18 +267,50 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
                 hi[t2] = *reinterpret_cast<uint32_t*>(&hh);
                 lo[t2] = *reinterpret_cast<uint32_t*>(&ll);
               }
-              *reinterpret_cast<uint4*>(oh + j) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-              *reinterpret_cast<uint4*>(ol + j) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+              *reinterpret_cast<uint4*>(stg + l * 144 + j * 2) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+              *reinterpret_cast<uint4*>(stg + l * 144 + 64 + j * 2) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
             }
-          } else {
+            __syncwarp();
+            __half* oh = reinterpret_cast<__half*>(p.out0) + wrow0;
+            __half* ol = reinterpret_cast<__half*>(p.out1) + wrow0;
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (nc + j < p.N) {
-                __half h, l;
-                split_f16x2(v[j], h, l);
-                oh[j] = h;
-                ol[j] = l;
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + (l >> 2), seg = l & 3;
+              if (r < rows_ok) {
+                *reinterpret_cast<uint4*>(oh + (long long)r * p.out_row_stride + seg * 8) =
+                    *reinterpret_cast<const uint4*>(stg + r * 144 + seg * 16);
+                *reinterpret_cast<uint4*>(ol + (long long)r * p.out_row_stride + seg * 8) =
+                    *reinterpret_cast<const uint4*>(stg + r * 144 + 64 + seg * 16);
               }
+            }
+          }
+          __syncwarp();  // staging tile is reused by the next chunk
+          continue;
+        }
+        // ragged last chunk (N not a multiple of 32): per-thread scalar path
+        if (!row_ok) continue;
+        if (p.out_mode == GEMM_OUT_F32) {
+          float* o = reinterpret_cast<float*>(p.out0) + obase + nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < p.N) o[j] = v[j];
+        } else if (p.out_mode == GEMM_OUT_F16) {
+          __half* o = reinterpret_cast<__half*>(p.out0) + obase + nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j)
+            if (nc + j < p.N) o[j] = __float2half_rn(v[j]);
+        } else {
+          __half* oh = reinterpret_cast<__half*>(p.out0) + obase + nc;
+          __half* ol = reinterpret_cast<__half*>(p.out1) + obase + nc;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            if (nc + j < p.N) {
+              float x = v[j];
+              if (p.out_mode == GEMM_OUT_SPLIT_RESID) x += __half2float(p.res_hi[obase + nc + j]) + __half2float(p.res_lo[obase + nc + j]);
+              __half h, lw;
+              split_f16x2(x, h, lw);
+              oh[j] = h;
+              ol[j] = lw;
             }
           }
         }
@@ -323,7 +365,7 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.out_row_stride = g.out_row_stride;
   p.out_batch_stride = g.out_batch_stride;
 
-  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float);
+  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float) + 4 * 32 * 144;
   auto kern = gemm_f16split_kernel<BN, STAGES, BK>;
   static bool configured = false;
   if (!configured) {
