@@ -177,6 +177,24 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       const int nchunks = min(BN / 32, (p.N - n0 + 31) / 32);
       uint32_t r[32];
       tmem_ld_x32(t_row, r);
+      // residual planes of the warp's 32 x 32 sub-tile, prefetched one chunk ahead (coalesced: 8 rows x 64 B per pass)
+      const bool resid = p.out_mode == GEMM_OUT_SPLIT_RESID;
+      const int rows_ok_w = min(32, p.M - (m0 + q * 32));
+      const long long wbase = (long long)z * p.out_batch_stride + (long long)(m0 + q * 32) * p.out_row_stride;
+      uint4 rh[4], rl[4];
+      auto load_resid = [&](int nc_) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int rr = it * 8 + (lane_id() >> 2), seg = lane_id() & 3;
+          rh[it] = make_uint4(0, 0, 0, 0);
+          rl[it] = rh[it];
+          if (rr < rows_ok_w && nc_ + 32 <= p.N) {
+            rh[it] = *reinterpret_cast<const uint4*>(p.res_hi + wbase + nc_ + (long long)rr * p.out_row_stride + seg * 8);
+            rl[it] = *reinterpret_cast<const uint4*>(p.res_lo + wbase + nc_ + (long long)rr * p.out_row_stride + seg * 8);
+          }
+        }
+      };
+      if (resid) load_resid(n0);
 #pragma unroll 1
       for (int c = 0; c < nchunks; ++c) {
         const int nc = n0 + c * 32;
@@ -193,19 +211,15 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           const int l = lane_id();
           const long long wrow0 = (long long)z * p.out_batch_stride + (long long)(m0 + q * 32) * p.out_row_stride + nc;
           const int rows_ok = min(32, p.M - (m0 + q * 32));  // rows of this warp that exist (may be <= 0)
-          if (p.out_mode == GEMM_OUT_SPLIT_RESID) {
+          if (resid) {
 #pragma unroll
-            for (int it = 0; it < 4; ++it) {  // 8 rows x (64 B hi + 64 B lo) per pass
-              const int r = it * 8 + (l >> 2), seg = l & 3;
-              uint4 hv = make_uint4(0, 0, 0, 0), lv = hv;
-              if (r < rows_ok) {
-                hv = *reinterpret_cast<const uint4*>(p.res_hi + wrow0 + (long long)r * p.out_row_stride + seg * 8);
-                lv = *reinterpret_cast<const uint4*>(p.res_lo + wrow0 + (long long)r * p.out_row_stride + seg * 8);
-              }
-              *reinterpret_cast<uint4*>(stg + r * 144 + seg * 16) = hv;
-              *reinterpret_cast<uint4*>(stg + r * 144 + 64 + seg * 16) = lv;
+            for (int it = 0; it < 4; ++it) {  // the prefetched 8 rows x (64 B hi + 64 B lo) per pass
+              const int rr = it * 8 + (l >> 2), seg = l & 3;
+              *reinterpret_cast<uint4*>(stg + rr * 144 + seg * 16) = rh[it];
+              *reinterpret_cast<uint4*>(stg + rr * 144 + 64 + seg * 16) = rl[it];
             }
             __syncwarp();
+            if (c + 1 < nchunks) load_resid(nc + 32);  // next chunk's residual is in flight during this chunk's stores
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const uint4 ra = *reinterpret_cast<const uint4*>(stg + l * 144 + j * 16);
@@ -391,7 +405,8 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     const char* e = getenv("IMP_GEMM_VARIANT");
     variant = e ? atoi(e) : 0;
   }
-  if (g.N > 128) return variant == 1 ? launch_impl<256, 2, 64>(g, stream) : launch_impl<256, 4, 32>(g, stream);
+  // two 96 KB stages (BK = 64) and four 48 KB stages (BK = 32) measure the same on B200 (tools/gemm_probe.py)
+  if (g.N > 128) return variant == 0 ? launch_impl<256, 2, 64>(g, stream) : launch_impl<256, 4, 32>(g, stream);
   return launch_impl<128, 3, 64>(g, stream);
 }
 
