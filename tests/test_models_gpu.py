@@ -95,3 +95,49 @@ def test_cuda_graph_replay_matches_eager():
         assert float((out['mscores0'][-1] - m_e).abs().max()) < 1e-5
     ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches({k: v.cpu() for k, v in d2.items()}, only_last=True)
     assert torch.equal(out['indices0'][-1].cpu(), ref['indices0'][-1])
+
+
+@pytest.mark.parametrize('N0,N1,B,nl', [(5, 9, 1, 3), (129, 64, 3, 4), (2300, 2210, 1, 3)])
+def test_dgnns_edge_sizes(N0, N1, B, nl):
+    """Tiny, odd-batch and > 2048-keypoint pairs (longest Sinkhorn row variant, > 16 key tiles)."""
+    c = cfg(nl)
+    sd = synth.make_state_dict('DGNNS', nl, seed=13)
+    data = synth.make_pair_batch(seed=17, batch=B, n0=N0, n1=N1)
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches(data, p=0.2, only_last=False)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net.produce_matches(to_cuda(data), p=0.2, only_last=False)
+    compare(out, ref)
+
+
+def test_dual_softmax_model_path():
+    """with_sinkhorn=False (eval_imp.py --use_dual_softmax): dual-softmax scorer through the model API."""
+    c = cfg(3, with_sinkhorn=False)
+    sd = synth.make_state_dict('DGNNS', 3, seed=5)
+    data = synth.make_pair_batch(seed=6, batch=2, n0=150, n1=170)
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches(data, p=0.2)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net.produce_matches(to_cuda(data), p=0.2)
+    compare(out, ref)
+
+
+def test_run_adapters_and_weight_reload():
+    """mode=1 `run` adapters (eval/eval_yfcc_full.py:54) and repacking after load_state_dict."""
+    c = cfg(3)
+    data = synth.make_pair_batch(seed=9, batch=1, n0=200, n1=180)
+    nk0 = imp_oracle.normalize_keypoints(data['keypoints0'], data['image0'].shape)
+    nk1 = imp_oracle.normalize_keypoints(data['keypoints1'], data['image1'].shape)
+    rd = {'desc1': data['descriptors0'], 'desc2': data['descriptors1'],
+          'x1': torch.cat([nk0, data['scores0'][..., None]], -1), 'x2': torch.cat([nk1, data['scores1'][..., None]], -1)}
+    net = DGNNS(c).cuda().eval()
+    for seed in (3, 4):                      # second pass: new weights must be repacked
+        sd = synth.make_state_dict('DGNNS', 3, seed=seed)
+        net.load_state_dict(sd, strict=True)
+        ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches(
+            {**data, 'norm_keypoints0': nk0, 'norm_keypoints1': nk1}, p=0.2, only_last=True)
+        with torch.no_grad():
+            out = net(to_cuda(rd), mode=1)
+        ri = ref['indices0'][-1][0]
+        idx0 = torch.where(ri >= 0)[0]
+        assert torch.equal(out['index0'].cpu(), idx0) and torch.equal(out['index1'].cpu(), ri[idx0])
