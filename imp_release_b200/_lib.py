@@ -80,6 +80,8 @@ SIGNATURES = {
     'imp_kenc_input': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'imp_small_linear': (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp]),
     'imp_sinkhorn': (C.c_int, [C.POINTER(SinkhornArgs), c_vp]),
+    'imp_set_profiling': (C.c_int, [c_i32]),
+    'imp_sinkhorn_iter_ms': (C.c_float, []),
     'imp_matches': (C.c_int, [C.POINTER(MatchArgs), c_vp]),
     'imp_dual_softmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),

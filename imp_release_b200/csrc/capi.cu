@@ -17,6 +17,8 @@ int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max,
                         cudaStream_t st);
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
                         int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st);
+void sinkhorn_set_profiling(int on);
+float sinkhorn_iter_ms();
 }  // namespace imp
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -51,6 +53,11 @@ IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const 
   return imp::launch_small_linear(X, ldx, W, bias, Y, ldy, rows, Cin, Cout, ST(stream));
 }
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream) { return imp::launch_sinkhorn(*args, ST(stream)); }
+IMP_API int imp_set_profiling(int32_t on) {
+  imp::sinkhorn_set_profiling(on);
+  return 0;
+}
+IMP_API float imp_sinkhorn_iter_ms(void) { return imp::sinkhorn_iter_ms(); }
 IMP_API int imp_matches(const imp_match_args* args, void* stream) { return imp::launch_matches(*args, ST(stream)); }
 IMP_API int imp_dual_softmax(const float* dist, int64_t d_bs, int32_t ldd, const float* bin_score, float* P, int64_t p_bs,
                      int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1, int32_t batch, void* stream) {

@@ -644,6 +644,18 @@ static int sk_chunk_matrices(size_t matrix_bytes, int batch) {
   return c > batch ? batch : (int)c;
 }
 
+static int g_profile = 0;
+static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
+static int g_ev_iters = 0;
+void sinkhorn_set_profiling(int on) { g_profile = on; }
+float sinkhorn_iter_ms() {
+  if (g_ev_iters <= 0 || g_ev0 == nullptr) return -1.f;
+  if (cudaEventSynchronize(g_ev1) != cudaSuccess) return -1.f;
+  float ms = 0.f;
+  if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
+  return ms / (float)g_ev_iters;
+}
+
 template <int NV>
 static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   const int R = a.N0max + 1;
@@ -764,11 +776,23 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     p.col_zero = col[1];
     p.do_iter = iters > 0 ? 1 : 0;
     sk_ring_kernel<NV, SK_INIT><<<grid, SKR_THREADS, smem, st>>>(p);
+    const bool prof = g_profile && b0 == 0 && nb == a.batch && iters > 1;
+    if (prof) {
+      if (g_ev0 == nullptr) {
+        cudaEventCreate(&g_ev0);
+        cudaEventCreate(&g_ev1);
+      }
+      cudaEventRecord(g_ev0, st);
+    }
     for (int k = 1; k < iters; ++k) {
       p.col_prev = col[(k - 1) % 3];
       p.col_acc = col[k % 3];
       p.col_zero = col[(k + 1) % 3];
       sk_ring_kernel<NV, SK_ITER><<<grid, SKR_THREADS, smem, st>>>(p);
+    }
+    if (prof) {
+      cudaEventRecord(g_ev1, st);
+      g_ev_iters = iters - 1;
     }
     const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
     p.col_prev = col_last;

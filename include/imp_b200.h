@@ -119,6 +119,11 @@ typedef struct imp_sinkhorn_args {
   int32_t write_scores; /* 1: store the final (p u) v into P; 0: P keeps softmax(M) and only arg-max / masses are produced */
 } imp_sinkhorn_args;
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
+/* Measurement aid for bench.py: with profiling on, imp_sinkhorn brackets its iteration launches with CUDA events on the
+ * launching stream; imp_sinkhorn_iter_ms() waits for them and returns the mean duration of one iteration kernel of the
+ * most recent call (< 0 if none was recorded). */
+IMP_API int imp_set_profiling(int32_t on);
+IMP_API float imp_sinkhorn_iter_ms(void);
 
 /* mutual-NN matches, GM.compute_matches nets/gm.py:305-320 (int64 indices like torch) */
 typedef struct imp_match_args {
