@@ -235,6 +235,7 @@ def run_gpu(args, rank, world, local_rank):
 
     # per-kernel breakdown with CUDA events on the launching stream (separate pass so `value` is unperturbed)
     ops.PROFILE = {}
+    net.overlap_scoring = False      # serialise the two streams so that per-kernel event times are uncontended
     from imp_release_b200 import _lib as implib
     implib.load().imp_set_profiling(1)
     barrier()
@@ -247,6 +248,7 @@ def run_gpu(args, rank, world, local_rank):
         work = sum(w for _, _, w in spans)
         prof[name] = (tot, len(spans), work)
     ops.PROFILE = None
+    net.overlap_scoring = True
     sk_iter_ms = float(implib.load().imp_sinkhorn_iter_ms())
     implib.load().imp_set_profiling(0)
     total_prof = sum(v[0] for v in prof.values()) or 1.0
