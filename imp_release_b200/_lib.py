@@ -37,7 +37,8 @@ class AttnArgs(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('v', c_vp), ('q_img_stride', c_i64), ('kv_img_stride', c_i64),
                 ('q_row_stride', c_i32), ('kv_row_stride', c_i32), ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
                 ('nq', c_vp), ('nk', c_vp), ('shared', c_i32), ('_pad', c_i32), ('lse', c_vp),
-                ('out_hi', c_vp), ('out_lo', c_vp), ('out_img_stride', c_i64)]
+                ('out_hi', c_vp), ('out_lo', c_vp), ('out_img_stride', c_i64),
+                ('q_lo', c_vp), ('k_lo', c_vp), ('v_lo', c_vp)]
 
 
 class AttnColsumArgs(C.Structure):

@@ -38,17 +38,25 @@ struct AttnKernelParams {
   long long out_img_stride;
 };
 
-template <int BN, int STG, int MINB>
+// SPLIT = true: "high precision" mode.  Q, K, V arrive as fp16 hi/lo planes and P is split into hi/lo as well; both
+// contractions issue the 3-product scheme of the GEMMs (hi.hi + lo.hi + hi.lo), which tracks an fp32 attention to ~1e-5
+// (needed when the attention is sharply peaked; costs 3x the tensor work, so the kernel becomes tensor-bound).
+template <int BN, int STG, int MINB, bool SPLIT>
 __global__ void __launch_bounds__(AT_THREADS, MINB)
 attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                 const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
-  constexpr int KV_BYTES = BN * AT_D * 2;                  // one K (or V) tile
+                 const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_ql,
+                 const __grid_constant__ CUtensorMap tm_kl, const __grid_constant__ CUtensorMap tm_vl,
+                 const AttnKernelParams p) {
+  static_assert(!SPLIT || BN == 64, "split mode stores P_hi | P_lo in the 64 score columns");
+  constexpr int NP = SPLIT ? 2 : 1;                        // planes per operand
+  constexpr int KV_BYTES = BN * AT_D * 2;                  // one K (or V) tile plane
   constexpr uint32_t TMEM_COLS = (BN + AT_D <= 128) ? 128 : 256;  // score tile (BN fp32 columns) + O (64)
   constexpr uint32_t COL_O = BN;
   extern __shared__ __align__(1024) uint8_t smem[];  // 128B-swizzled tiles need 1024-byte alignment
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K at +0, V at +KV_BYTES
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + STG * 2 * KV_BYTES);
+  uint8_t* s_q = smem;                        // Q_hi [, Q_lo]
+  uint8_t* s_kv = smem + NP * AT_TILE_BYTES;  // stage s: K_hi, V_hi [, K_lo, V_lo], KV_BYTES each
+  constexpr int STAGE_BYTES = 2 * NP * KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + STG * STAGE_BYTES);
   uint64_t* q_full = bars;
   uint64_t* kv_full = bars + 1;
   uint64_t* kv_empty = kv_full + STG;
@@ -94,15 +102,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (elect_one() && T > 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
+      mbar_arrive_expect_tx(q_full, NP * AT_TILE_BYTES);
       tma_load_3d(s_q, &tm_q, q_full, h * AT_D, q0, img);
+      if (SPLIT) tma_load_3d(s_q + AT_TILE_BYTES, &tm_ql, q_full, h * AT_D, q0, img);
       for (int j = 0; j < T; ++j) {
         const int s = j % STG;
         mbar_wait(&kv_empty[s], ((j / STG) & 1) ^ 1);
-        uint8_t* st = s_kv + s * 2 * KV_BYTES;
-        mbar_arrive_expect_tx(&kv_full[s], 2 * KV_BYTES);
+        uint8_t* st = s_kv + s * STAGE_BYTES;
+        mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
         tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * BN, src);
         tma_load_3d(st + KV_BYTES, &tm_v, &kv_full[s], h * AT_D, j * BN, src);
+        if (SPLIT) {
+          tma_load_3d(st + 2 * KV_BYTES, &tm_kl, &kv_full[s], h * AT_D, j * BN, src);
+          tma_load_3d(st + 3 * KV_BYTES, &tm_vl, &kv_full[s], h * AT_D, j * BN, src);
+        }
       }
     }
   } else if (warp == 1) {
@@ -116,21 +129,33 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int st = j % STG;
         mbar_wait(&kv_full[st], (j / STG) & 1);
         tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * 2 * KV_BYTES);
+        const uint32_t k_addr = smem_u32(s_kv + st * STAGE_BYTES);
         const uint32_t v_addr = k_addr + KV_BYTES;
         // S = Q K^T.  The tensor pipe executes MMAs in issue order, so this overwrites the score columns only after
         // O += P(j-1) V(j-1), which read P from the same columns, has drained.
 #pragma unroll
-        for (int kk = 0; kk < AT_D / 16; ++kk)
-          umma_f16_ss(tmem_base + AT_COL_S, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024),
-                      make_smem_desc_sw128(k_addr + kk * 32, 16, 1024), idesc_qk, kk > 0 ? 1u : 0u);
+        for (int kk = 0; kk < AT_D / 16; ++kk) {
+          const uint64_t dq = make_smem_desc_sw128(q_addr + kk * 32, 16, 1024);
+          const uint64_t dk = make_smem_desc_sw128(k_addr + kk * 32, 16, 1024);
+          umma_f16_ss(tmem_base + AT_COL_S, dq, dk, idesc_qk, kk > 0 ? 1u : 0u);
+          if (SPLIT) {
+            umma_f16_ss(tmem_base + AT_COL_S, make_smem_desc_sw128(q_addr + AT_TILE_BYTES + kk * 32, 16, 1024), dk, idesc_qk, 1u);
+            umma_f16_ss(tmem_base + AT_COL_S, dq, make_smem_desc_sw128(k_addr + 2 * KV_BYTES + kk * 32, 16, 1024), idesc_qk, 1u);
+          }
+        }
         umma_commit(s_full);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
 #pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
-          umma_f16_ts(tmem_base + COL_O, tmem_base + AT_COL_S + kk * 8,
-                      make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024), idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+        for (int kk = 0; kk < BN / 16; ++kk) {  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
+          const uint64_t dv = make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024);
+          umma_f16_ts(tmem_base + COL_O, tmem_base + AT_COL_S + kk * 8, dv, idesc_pv, (j > 0 || kk > 0) ? 1u : 0u);
+          if (SPLIT) {  // P_lo lives in score columns [BN/2, BN)
+            umma_f16_ts(tmem_base + COL_O, tmem_base + AT_COL_S + BN / 2 + kk * 8, dv, idesc_pv, 1u);
+            umma_f16_ts(tmem_base + COL_O, tmem_base + AT_COL_S + kk * 8,
+                        make_smem_desc_sw128(v_addr + 2 * KV_BYTES + kk * 2048, 1024, 1024), idesc_pv, 1u);
+          }
+        }
         umma_commit(&kv_empty[st]);
         umma_commit(o_done);
       }
@@ -204,9 +229,35 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         neg_ref = -lse_in;
       }
+      float lsum = 0.f;
+      if (SPLIT) {
+        // high-precision mode: the whole 64-column score row is read first (P_hi | P_lo overwrite all of it), then
+        // p is split into an fp16 pair p = hi + lo (~22 bits)
+        uint32_t r[BN];
+        tmem_ld_x32(s_addr, r);
+        tmem_ld_x32(s_addr + 32, r + 32);
+        tmem_wait_ld();
+        uint32_t ph[BN / 2], pl[BN / 2];
+#pragma unroll
+        for (int c = 0; c < BN; c += 2) {
+          float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+          float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+          if (ragged) {
+            p0 = (c < nvalid) ? p0 : 0.f;
+            p1 = (c + 1 < nvalid) ? p1 : 0.f;
+          }
+          lsum += p0 + p1;
+          const __half2 hh = __floats2half2_rn(p0, p1);
+          const float2 hf = __half22float2(hh);
+          const __half2 ll = __floats2half2_rn(p0 - hf.x, p1 - hf.y);
+          ph[c >> 1] = *reinterpret_cast<const uint32_t*>(&hh);
+          pl[c >> 1] = *reinterpret_cast<const uint32_t*>(&ll);
+        }
+        tmem_st_x32(s_addr, ph);
+        tmem_st_x32(s_addr + BN / 2, pl);
+      } else {
       // pass 2: p = exp2(s * c - ref), packed fp16 written over the score columns (chunk cb lands in columns
       // [cb/2, cb/2+16), which this thread has already consumed)
-      float lsum = 0.f;
 #pragma unroll
       for (int cb = 0; cb < BN; cb += 32) {
         uint32_t r[32];
@@ -233,6 +284,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           }
         }
         tmem_st_x16(s_addr + (cb >> 1), pk);
+      }
       }
       l_run += lsum;
       tmem_wait_st();
@@ -286,12 +338,20 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   }
 }
 
-template <int BN, int STG, int MINB>
+template <int BN, int STG, int MINB, bool SPLIT>
 static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq, tk, tv, tql, tkl, tvl;
   if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
   if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
   if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+  tql = tq;
+  tkl = tk;
+  tvl = tv;
+  if (SPLIT) {
+    if (make_tmap_f16_3d(&tql, a.q_lo, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
+    if (make_tmap_f16_3d(&tkl, a.k_lo, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+    if (make_tmap_f16_3d(&tvl, a.v_lo, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+  }
   AttnKernelParams p;
   p.n_img = a.n_img;
   p.src_offset = a.src_offset;
@@ -304,8 +364,9 @@ static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   p.out_hi = reinterpret_cast<__half*>(a.out_hi);
   p.out_lo = reinterpret_cast<__half*>(a.out_lo);
   p.out_img_stride = a.out_img_stride;
-  const size_t smem = AT_TILE_BYTES + STG * 2 * (BN * AT_D * 2) + 256;
-  auto kern = attention_kernel<BN, STG, MINB>;
+  constexpr int NP = SPLIT ? 2 : 1;
+  const size_t smem = NP * AT_TILE_BYTES + STG * 2 * NP * (BN * AT_D * 2) + 256;
+  auto kern = attention_kernel<BN, STG, MINB, SPLIT>;
   static bool configured = false;
   if (!configured) {
     IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -314,7 +375,7 @@ static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
     configured = true;
   }
   dim3 grid((a.Nq_max + AT_BM - 1) / AT_BM, AT_HEADS, a.n_img);
-  kern<<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
+  kern<<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, tql, tkl, tvl, p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -322,6 +383,10 @@ static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
   IMP_REQUIRE(a.q_row_stride >= AT_C && a.kv_row_stride >= AT_C, "attention: row strides must be >= 256");
+  if (a.q_lo != nullptr || a.k_lo != nullptr || a.v_lo != nullptr) {
+    IMP_REQUIRE(a.q_lo != nullptr && a.k_lo != nullptr && a.v_lo != nullptr, "attention: high-precision mode needs q_lo, k_lo and v_lo");
+    return launch_attention_impl<64, 2, 2, true>(a, st);  // 96 KB smem, 128 TMEM columns -> 2 CTAs/SM
+  }
   // The kernel is bound by the serial QK -> softmax -> PV chain of a CTA, not by a throughput limit, so more (smaller)
   // CTAs per SM win: 64-key tiles need 128 TMEM columns and 48 KB of smem -> up to 4 CTAs/SM; 128-key tiles -> 2.
   static int variant = -1;
@@ -330,9 +395,9 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
     variant = e ? atoi(e) : 0;
   }
   switch (variant) {
-    case 1: return launch_attention_impl<128, 3, 2>(a, st);
-    case 2: return launch_attention_impl<64, 2, 3>(a, st);
-    default: return launch_attention_impl<64, 2, 4>(a, st);
+    case 1: return launch_attention_impl<128, 3, 2, false>(a, st);
+    case 2: return launch_attention_impl<64, 2, 3, false>(a, st);
+    default: return launch_attention_impl<64, 2, 4, false>(a, st);
   }
 }
 

@@ -92,6 +92,9 @@ class Workspace:
         self.lse = {'self': torch.zeros(n_img, HEADS, Np, **f32), 'cross': torch.zeros(n_img, HEADS, Np, **f32)}
         # EIMP: compacted [K | V] rows of the kept tokens, one stash per layer type
         self.kvc: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
+        # high-precision attention: "lo" planes of the Q|K|V projections (and of the compacted K|V)
+        self.qkv_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
+        self.kvc_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
         # keypoint encoder scratch
         self.k_in = torch.zeros(T, 4, **f32)
         self.k_a = torch.zeros(T, 64, **f32)
@@ -100,10 +103,16 @@ class Workspace:
         self.k_p = Planes.empty((T, D), device)
         self.tok_f32 = torch.zeros(T, D, **f32)
 
-    def kv_compact(self, name: str) -> torch.Tensor:
-        if self.kvc[name] is None:
-            self.kvc[name] = torch.zeros(self.n_img * self.Np, 2 * D, dtype=torch.float16, device=self.H.device)
-        return self.kvc[name]
+    def kv_compact(self, name: str, lo: bool = False) -> torch.Tensor:
+        store = self.kvc_lo if lo else self.kvc
+        if store[name] is None:
+            store[name] = torch.zeros(self.n_img * self.Np, 2 * D, dtype=torch.float16, device=self.H.device)
+        return store[name]
+
+    def qkv_lo_buf(self, name: str) -> torch.Tensor:
+        if self.qkv_lo[name] is None:
+            self.qkv_lo[name] = torch.zeros(self.n_img * self.Np, 3 * D, dtype=torch.float16, device=self.H.device)
+        return self.qkv_lo[name]
 
 
 class RunState:
@@ -118,9 +127,10 @@ class RunState:
 
 
 class Engine:
-    def __init__(self, pk: PackedModel, names: List[str]):
+    def __init__(self, pk: PackedModel, names: List[str], high_precision_attention: bool = False):
         self.pk = pk
         self.names = names
+        self.hp = high_precision_attention
         self._ws: Dict[tuple, Workspace] = {}
 
     def workspace(self, n_img: int, Np: int, device) -> Workspace:
@@ -171,29 +181,42 @@ class Engine:
         buf = ws.qkv[name]
         lse = ws.lse[name]
         base = buf.data_ptr()
+        hp = self.hp
+        buf_lo = ws.qkv_lo_buf(name) if hp else None
+        base_lo = buf_lo.data_ptr() if hp else None
+        mode = ops.OUT_SPLIT if hp else ops.OUT_F16
         if not L['sharing']:
             ops.gemm(ws.X, L['Wqkv'], M=T, N=3 * D, K1=D, a_row_stride=D, b_row_stride=D, bias=L['bqkv'],
-                     out_mode=ops.OUT_F16, out0=buf, out_row_stride=3 * D)
+                     out_mode=mode, out0=buf, out1=buf_lo, out_row_stride=3 * D)
         else:
             ops.gemm(ws.X, L['Wv'], M=T, N=D, K1=D, a_row_stride=D, b_row_stride=D, bias=L['bv'],
-                     out_mode=ops.OUT_F16, out0=buf, out_row_stride=3 * D, out_offset=2 * D)
+                     out_mode=mode, out0=buf, out1=buf_lo, out_row_stride=3 * D, out_offset=2 * D)
+        k_lo = v_lo = None
         if st.key_ids is None:
             k_ptr, v_ptr, kv_rs, nk = base + 2 * D, base + 2 * 2 * D, 3 * D, st.n_tok
+            if hp:
+                k_lo, v_lo = base_lo + 2 * D, base_lo + 2 * 2 * D
         else:
-            kvc = ws.kv_compact(name)
-            src3 = buf.view(n_img, Np, 3 * D)
-            dst3 = kvc.view(n_img, Np, 2 * D)
+            planes = [(buf, ws.kv_compact(name))] + ([(buf_lo, ws.kv_compact(name, lo=True))] if hp else [])
+            for src, kvc in planes:
+                src3 = src.view(n_img, Np, 3 * D)
+                dst3 = kvc.view(n_img, Np, 2 * D)
+                if not L['sharing']:
+                    ops.gather_rows(src3[:, :, D:], st.key_ids, st.key_cnt, dst3, Np)          # K | V of the kept tokens
+                else:
+                    ops.gather_rows(src3[:, :, 2 * D:], st.key_ids, st.key_cnt, dst3[:, :, D:], Np)  # new V, same key set
             if not L['sharing']:
-                ops.gather_rows(src3[:, :, D:], st.key_ids, st.key_cnt, dst3, Np)          # K | V of the kept tokens
                 st.stash_cnt[name] = st.key_cnt
-            else:
-                ops.gather_rows(src3[:, :, 2 * D:], st.key_ids, st.key_cnt, dst3[:, :, D:], Np)  # new V, same key set
+            kvc = ws.kv_compact(name)
             k_ptr, v_ptr, kv_rs, nk = kvc.data_ptr(), kvc.data_ptr() + 2 * D, 2 * D, st.key_cnt
+            if hp:
+                kl = ws.kv_compact(name, lo=True)
+                k_lo, v_lo = kl.data_ptr(), kl.data_ptr() + 2 * D
         pairs_qk = st.B * (2 * st.N0 * st.N1 if cross else st.N0 * st.N0 + st.N1 * st.N1)
         ops.ATTN_WORK_HINT = (2.0 if L['sharing'] else 4.0) * D * pairs_qk   # algorithmic FLOPs
         ops.attention(base, k_ptr, v_ptr, n_img=n_img, src_offset=(st.B if cross else 0), Nq_max=Np, Nk_max=Np,
                       nq=st.n_tok, nk=nk, shared=L['sharing'], lse=lse, out=ws.A, q_row_stride=3 * D,
-                      kv_row_stride=kv_rs)
+                      kv_row_stride=kv_rs, q_lo=base_lo, k_lo=k_lo, v_lo=v_lo)
         ops.ATTN_WORK_HINT = None
         ops.gemm(ws.X, L['W0'], M=T, N=2 * D, K1=D, K2=D, a2=ws.A, a_row_stride=D, a2_row_stride=D, b_row_stride=2 * D,
                  bias=L['b0'], out_mode=ops.OUT_F32, out0=ws.H, out_row_stride=2 * D)

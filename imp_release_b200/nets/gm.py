@@ -59,6 +59,11 @@ class GM(nn.Module):
         self.gnn = GNNParams(D, self.config['GNN_layers'], self._sharing)
         self.final_proj = nn.ModuleList([_conv(D, D) for _ in range(self.n_layers)])
         self.register_parameter('bin_score', nn.Parameter(torch.tensor(1.)))
+        # B200-specific knob (not a reference config key): 'fp16' = single fp16 attention operands (default, fastest);
+        # 'high' = 3-product split for QK^T and PV (fp32-level attention; use when the attention is sharply peaked)
+        self.attention_precision = self.config.get('attention_precision', 'fp16')
+        if self.attention_precision not in ('fp16', 'high'):
+            raise ValueError("attention_precision must be 'fp16' or 'high'")
         self.self_prob0 = self.self_prob1 = self.cross_prob0 = self.cross_prob1 = None
         self._engine: Optional[Engine] = None
         self._engine_key = None
@@ -90,7 +95,8 @@ class GM(nn.Module):
                                                'no CPU implementation')
             sd = {k: v for k, v in self.state_dict().items()}
             n_gnn = len(self.gnn.layers)
-            self._engine = Engine(PackedModel(sd, self.n_layers, self.gnn.sharing_layers), self.gnn.names)
+            self._engine = Engine(PackedModel(sd, self.n_layers, self.gnn.sharing_layers), self.gnn.names,
+                                  high_precision_attention=(self.attention_precision == 'high'))
             assert n_gnn >= 2 * self.n_layers
             self._engine_key = key
         return self._engine

@@ -129,7 +129,7 @@ def _p(t):
 
 def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, shared: bool, lse,
               out: Planes, q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
-              kv_img_stride: Optional[int] = None):
+              kv_img_stride: Optional[int] = None, q_lo=None, k_lo=None, v_lo=None):
     """q/k/v: fp16 tensors or raw device addresses (slices of a fused projection buffer).
     ``work_hint``: algorithmic FLOPs of this call (QK^T + PV = 4*d per score element), for the profiler only."""
     attn_work = ATTN_WORK_HINT if ATTN_WORK_HINT is not None else 4.0 * 64 * 4 * n_img * Nq_max * Nk_max
@@ -144,6 +144,7 @@ def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int,
     a.lse = ptr(lse)
     a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
     a.out_img_stride = Nq_max * 256
+    a.q_lo, a.k_lo, a.v_lo = _p(q_lo), _p(k_lo), _p(v_lo)
     with _Span('attention_shared' if shared else 'attention', 1, attn_work):
         check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
 

@@ -70,6 +70,9 @@ typedef struct imp_attn_args {
   float* lse;            /* [n_img, 4, Nq_max] log2-domain LSE; written if !shared, read if shared */
   void *out_hi, *out_lo; /* [n_img, Nq_max, 256] fp16 planes */
   int64_t out_img_stride;
+  /* optional "lo" planes of Q, K, V (same strides).  All three non-NULL selects the high-precision mode: 3-product
+   * split contractions for QK^T and PV (fp32-level attention, ~1.6x the time); NULL = single fp16 operands */
+  const void *q_lo, *k_lo, *v_lo;
 } imp_attn_args;
 IMP_API int imp_attention(const imp_attn_args* args, void* stream);
 

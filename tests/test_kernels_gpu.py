@@ -289,3 +289,39 @@ def test_scatter_matches():
     assert oi[0].tolist() == [-1, -1, 11, -1, -1, -1, 10, -1, -1, -1, -1, -1]
     assert oi[1].tolist() == [-1, 7, -1, 8] + [-1] * 8
     assert abs(float(om[0, 2]) - .5) < 1e-7 and abs(float(om[0, 6]) - .7) < 1e-7 and float(om[0, 9]) == 0
+
+
+def test_attention_high_precision_mode():
+    """Split-precision attention (hi/lo planes for Q, K, V and P) tracks an fp64 attention to ~1e-5 even for peaky
+    softmax rows, where the single-fp16 mode is ~1e-3 off."""
+    n_img, N = 2, 500
+    g = torch.Generator().manual_seed(3)
+    q = torch.randn(n_img, N, 256, generator=g) * 3      # large logits -> sharply peaked attention
+    k = torch.randn(n_img, N, 256, generator=g) * 3
+    v = torch.randn(n_img, N, 256, generator=g)
+    pq, pk, pv = ops.split_planes(q.to(DEV)), ops.split_planes(k.to(DEV)), ops.split_planes(v.to(DEV))
+    nqs = torch.tensor([500, 437], dtype=torch.int32, device=DEV)
+    errs = {}
+    for mode in ('fp16', 'high'):
+        lse = torch.zeros(n_img, 4, N, device=DEV)
+        out = ops.Planes.empty((n_img, N, 256), DEV)
+        lo = dict(q_lo=pq.lo, k_lo=pk.lo, v_lo=pv.lo) if mode == 'high' else {}
+        ops.attention(pq.hi, pk.hi, pv.hi, n_img=n_img, src_offset=1, Nq_max=N, Nk_max=N, nq=nqs, nk=nqs, shared=False, lse=lse,
+                      out=out, **lo)
+        o = out.float()
+        err = 0.0
+        for img in range(n_img):
+            src = (img + 1) % n_img
+            nq_i, nk_i = int(nqs[img]), int(nqs[src])
+            ref, lref = _ref_attention(q[img, :nq_i].to(DEV), k[src].to(DEV), v[src].to(DEV), nk_i)
+            err = max(err, float((o[img, :nq_i].double() - ref).abs().max()))
+            if mode == 'high':
+                assert float((lse[img, :, :nq_i].double() - lref).abs().max()) < 1e-3
+                # shared mode with the same precision reproduces the same probabilities
+                out2 = ops.Planes.empty((n_img, N, 256), DEV)
+                ops.attention(pq.hi, pk.hi, pv.hi, n_img=n_img, src_offset=1, Nq_max=N, Nk_max=N, nq=nqs, nk=nqs, shared=True,
+                              lse=lse, out=out2, **lo)
+                assert float((out2.float()[img, :nq_i].double() - ref).abs().max()) < 2e-4
+        errs[mode] = err
+    assert errs['high'] < 1e-4, errs
+    assert errs['high'] < errs['fp16'] / 5, errs
