@@ -160,7 +160,7 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = model_config()
+    cfg = {**model_config(), 'attention_precision': args.attention_precision}
     net = DGNNS(cfg)
     net.load_state_dict(synth.make_state_dict('DGNNS', N_ITERS, seed=7), strict=True)
     net = net.to(dev).eval()
@@ -311,7 +311,9 @@ def run_gpu(args, rank, world, local_rank):
     line = {
         'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-        'dtype': 'f16x3 split (fp32-equivalent) projections/scores, f16 attention operands, f32 accumulate/softmax/Sinkhorn',
+        'dtype': 'f16x3 split (fp32-equivalent) projections/scores, '
+                 + ('f16x3 split' if args.attention_precision == 'high' else 'f16') +
+                 ' attention operands, f32 accumulate/softmax/Sinkhorn',
         'data': 'synthetic',
         'config': {'workload': f'BASELINE.json configs[1]: DGNNS.forward (IMP), batch={BATCH} pairs/GPU, N={N_KPTS}, D=256, '
                                f'{N_ITERS} iters, Sinkhorn(20)+matches every iteration',
@@ -356,6 +358,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--attention-precision', default='fp16', choices=['fp16', 'high'],
+                    help="'high' = split-precision attention (DESIGN.md section 2); default = the fast fp16 mode")
     ap.add_argument('--ncu', action='store_true', help='profiling aid: 1 warm-up + 1 resident step, nothing else (numbers invalid)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))
