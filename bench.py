@@ -160,7 +160,8 @@ def run_gpu(args, rank, world, local_rank):
     dev = torch.device('cuda', local_rank)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
-    cfg = {**model_config(), 'attention_precision': args.attention_precision}
+    sk_storage = args.sinkhorn_storage or ops.default_sk_storage()
+    cfg = {**model_config(), 'attention_precision': args.attention_precision, 'sinkhorn_storage': sk_storage}
     net = DGNNS(cfg)
     net.load_state_dict(synth.make_state_dict('DGNNS', N_ITERS, seed=7), strict=True)
     net = net.to(dev).eval()
@@ -273,11 +274,17 @@ def run_gpu(args, rank, world, local_rank):
             # traffic is ONE sweep of the [B, N0+1, N1+1] fp32 matrix per launch (the reference
             # formulation, SURVEY.md 8(d), counts two sweeps per iteration; this kernel fuses them).
             mat = 4.0 * BATCH * (N_KPTS + 1) * (N_KPTS + 1)
+            sk_bytes = {'fp32': 4, 'fp24': 3, 'fp16': 2}[sk_storage]
             it_s = (sk_iter_ms if sk_iter_ms > 0 else (tot / n) / 23.0) / 1e3
             ach = mat / it_s / 1e9
-            return {'kernel': 'sk_ring_kernel<ITER> (one Sinkhorn iteration, %d of the %d launches of a scoring)' % (19, 23),
+            kname = 'sk_ring_kernel<ITER>' if sk_storage == 'fp32' else f'skq_iter_kernel<{sk_storage}>'
+            return {'kernel': kname + ' (one Sinkhorn iteration, %d of the %d launches of a scoring)' % (19, 23),
                     'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'launch_ms': it_s * 1e3,
+                    'storage': {'format': sk_storage, 'bytes_per_element': sk_bytes,
+                                'moved_GBps': ach * sk_bytes / 4.0, 'moved_frac_of_peak': ach * sk_bytes / 4.0 / peaks['hbm_gbs'],
+                                'note': 'the iteration sweeps stream a %d-byte copy of softmax(M); `achieved` counts the '
+                                        'ALGORITHMIC 4 B per element, `moved_GBps` the bytes actually requested' % sk_bytes},
                     'reference_counting': {'achieved': 2 * ach, 'frac': 2 * ach / peaks['hbm_gbs'],
                                            'note': '2 sweeps per iteration as the reference algorithm is counted in SURVEY.md 8(d)'},
                     'whole_scoring': {'ms': tot / n, 'sweep_equivalents': 23, 'GBps': 23 * mat / (tot / n / 1e3) / 1e9},
@@ -296,7 +303,7 @@ def run_gpu(args, rank, world, local_rank):
         with open(tr) as f:
             t = json.load(f)
         for r in [roofline] + list(extra.values()):
-            key = 'sinkhorn' if r['kernel'].startswith('sk_ring') else r['kernel']
+            key = ('sinkhorn_' + sk_storage) if r['kernel'].startswith('sk') else r['kernel']
             if key in t:
                 r['traffic'] = t[key]
 
@@ -313,7 +320,7 @@ def run_gpu(args, rank, world, local_rank):
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16x3 split (fp32-equivalent) projections/scores, '
                  + ('f16x3 split' if args.attention_precision == 'high' else 'f16') +
-                 ' attention operands, f32 accumulate/softmax/Sinkhorn',
+                 ' attention operands, f32 accumulate/softmax/Sinkhorn (iteration sweeps read a ' + sk_storage + ' copy of softmax(M))',
         'data': 'synthetic',
         'config': {'workload': f'BASELINE.json configs[1]: DGNNS.forward (IMP), batch={BATCH} pairs/GPU, N={N_KPTS}, D=256, '
                                f'{N_ITERS} iters, Sinkhorn(20)+matches every iteration',
@@ -360,6 +367,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--attention-precision', default='fp16', choices=['fp16', 'high'],
                     help="'high' = split-precision attention (DESIGN.md section 2); default = the fast fp16 mode")
+    ap.add_argument('--sinkhorn-storage', default=None, choices=['fp32', 'fp24', 'fp16'],
+                    help='storage of softmax(M) for the Sinkhorn iteration sweeps (DESIGN.md section 2); default = library default')
     ap.add_argument('--ncu', action='store_true', help='profiling aid: 1 warm-up + 1 resident step, nothing else (numbers invalid)')
     args = ap.parse_args()
     rank = int(os.environ.get('RANK', '0'))

@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12, which libimp_b200.so links a
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libimp_b200.so')
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class ImpLibraryError(RuntimeError):
@@ -51,7 +51,8 @@ class SinkhornArgs(C.Structure):
     _fields_ = [('dist', c_vp), ('dist_batch_stride', c_i64), ('ldd', c_i32), ('iters', c_i32), ('bin_score', c_vp),
                 ('P', c_vp), ('p_batch_stride', c_i64), ('ldp', c_i32), ('_pad', c_i32), ('u', c_vp), ('colbuf', c_vp),
                 ('row_max', c_vp), ('row_arg', c_vp), ('col_key', c_vp), ('row_mass', c_vp), ('col_mass', c_vp),
-                ('n0s', c_vp), ('n1s', c_vp), ('N0max', c_i32), ('N1max', c_i32), ('batch', c_i32), ('write_scores', c_i32)]
+                ('n0s', c_vp), ('n1s', c_vp), ('N0max', c_i32), ('N1max', c_i32), ('batch', c_i32), ('write_scores', c_i32),
+                ('q_store', c_vp), ('q_batch_stride', c_i64), ('row_stats', c_vp), ('storage', c_i32), ('_pad2', c_i32)]
 
 
 class MatchArgs(C.Structure):

@@ -21,23 +21,13 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "sinkhorn_common.cuh"
 
 namespace imp {
 
-static constexpr float SK_EPS = 1e-8f;
 static constexpr int SKR_CONSUMERS = 4;
 static constexpr int SKR_THREADS = (SKR_CONSUMERS + 1) * 32;  // + one producer warp
 static constexpr int SKR_SMEM_BUDGET = 113 * 1024;            // two CTAs per SM (228 KB - 2 x 1 KB reserved)
-
-struct SkDims {
-  int R, C;  // augmented rows / cols of this sample
-};
-__device__ __forceinline__ SkDims sk_dims(const int* n0s, const int* n1s, int b, int N0max, int N1max) {
-  SkDims d;
-  d.R = (n0s ? n0s[b] : N0max) + 1;
-  d.C = (n1s ? n1s[b] : N1max) + 1;
-  return d;
-}
 
 struct SkParams {
   const float* dist;
@@ -62,36 +52,9 @@ struct SkParams {
   int write_scores;  // final: store (p u) v back into P
 };
 
-__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(smem_dst)),
-               "l"(reinterpret_cast<uint64_t>(gsrc)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SKR_CONSUMERS * 32) : "memory"); }
 
-__device__ __forceinline__ float4 v_from_colsum(const float* __restrict__ colsum, int c0, int C) {
-  // v_j = c_j / (colsum_j + eps);  c_j = 1, last real column C-1 has mass C;  pad columns -> 0
-  const float4 s = *reinterpret_cast<const float4*>(colsum + c0);
-  float4 v;
-  v.x = (c0 + 0 < C) ? ((c0 + 0 == C - 1) ? (float)C : 1.f) / (s.x + SK_EPS) : 0.f;
-  v.y = (c0 + 1 < C) ? ((c0 + 1 == C - 1) ? (float)C : 1.f) / (s.y + SK_EPS) : 0.f;
-  v.z = (c0 + 2 < C) ? ((c0 + 2 == C - 1) ? (float)C : 1.f) / (s.z + SK_EPS) : 0.f;
-  v.w = (c0 + 3 < C) ? ((c0 + 3 == C - 1) ? (float)C : 1.f) / (s.w + SK_EPS) : 0.f;
-  return v;
-}
-
 enum { SK_INIT = 0, SK_ITER = 1, SK_FINAL = 2 };
-
-// exp(x) for x <= 0 with ~3e-7 relative error in 6 instructions: x*log2(e) is split into a rounded product t and its
-// exact residual e (FMA), 2^t comes from the MUFU and the residual is applied to first order.  (expf() costs ~20
-// instructions and made the softmax pass compute-bound: 1.28 ms per launch instead of the ~0.33 ms its traffic needs.)
-__device__ __forceinline__ float sk_exp(float x) {
-  x = fmaxf(x, -200.f);  // exp(-200) underflows to 0 in fp32; also keeps the residual finite for the -FLT_MAX pad
-  const float t = x * 1.4426950408889634f;
-  const float e = fmaf(x, 1.4426950408889634f, -t) + x * 1.925963033500235e-8f;
-  return fast_exp2(t) * fmaf(e, 0.6931471805599453f, 1.0f);
-}
 
 // MODE: SK_INIT  P = softmax_rows(pad(dist)) (+ first half-iteration: u with v = 1, column sums with that u)
 //       SK_ITER  one full Sinkhorn iteration (u, then column sums) in a single sweep over P
@@ -353,11 +316,6 @@ __global__ void __launch_bounds__(SKR_THREADS, 2) sk_ring_kernel(const SkParams 
       for (int j = ct; j < d.C; j += SKR_CONSUMERS * 32) atomicAdd(p.col_acc + (long long)b * p.ldp + j, s_col[j]);
     }
   }
-}
-
-__device__ __forceinline__ unsigned long long pack_max_key(float val, int idx) {
-  // scores are >= 0, so the raw bits order like the values; ~idx makes the LOWEST index win ties
-  return (static_cast<unsigned long long>(__float_as_uint(val)) << 32) | (0xFFFFFFFFu - (unsigned)idx);
 }
 
 // column arg-max over the non-dustbin block: thread per column (coalesced), 256-row slabs, packed atomicMax
@@ -655,6 +613,18 @@ float sinkhorn_iter_ms() {
   if (cudaEventElapsedTime(&ms, g_ev0, g_ev1) != cudaSuccess) return -1.f;
   return ms / (float)g_ev_iters;
 }
+bool sk_profiling_on() { return g_profile != 0; }
+void sk_profile_begin(cudaStream_t st) {
+  if (g_ev0 == nullptr) {
+    cudaEventCreate(&g_ev0);
+    cudaEventCreate(&g_ev1);
+  }
+  cudaEventRecord(g_ev0, st);
+}
+void sk_profile_end(cudaStream_t st, int launches) {
+  cudaEventRecord(g_ev1, st);
+  g_ev_iters = launches;
+}
 
 template <int NV>
 static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
@@ -721,6 +691,10 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     }
   }
 
+  // big batches: the iteration sweeps read a compact (16- or 24-bit) copy of softmax(M) instead of the fp32 matrix
+  if (a.storage != IMP_SK_STORE_F32 && a.q_store != nullptr && a.row_stats != nullptr && a.N1max + 1 >= 64)
+    return run_sinkhorn_compact(a, st);
+
   for (int b0 = 0; b0 < a.batch; b0 += chunk) {
     const int nb = (a.batch - b0 < chunk) ? a.batch - b0 : chunk;
     SkParams p;
@@ -741,23 +715,7 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     p.N0max = a.N0max;
     p.N1max = a.N1max;
     p.write_scores = a.write_scores;
-    // rows per CTA (multiple of the consumer-warp count, 8..128): pick the block height whose CTA count fills whole
-    // waves of 2 CTAs/SM best -- e.g. 64 x 2001 rows: 128-row blocks give 1024 CTAs = 3.46 waves, 88-row blocks
-    // 1472 CTAs = 4.97 waves.  Larger blocks win ties (fewer column-sum flushes).
-    const long long wave = 2LL * num_sms();
-    int rows_per_cta = 8;
-    double best_eff = -1.0;
-    for (int r = 128; r >= 8; r -= SKR_CONSUMERS) {
-      const long long ctas = (long long)nb * ((R + r - 1) / r);
-      const long long waves = (ctas + wave - 1) / wave;
-      const double eff = (double)ctas / (double)(waves * wave) * ((R % r == 0 || r <= R) ? 1.0 : 1.0);
-      const double balance = (double)R / (double)(((R + r - 1) / r) * r);  // ragged last block of each matrix
-      const double score = eff * balance;
-      if (score > best_eff + 1e-3) {
-        best_eff = score;
-        rows_per_cta = r;
-      }
-    }
+    const int rows_per_cta = sk_rows_per_cta(R, nb, num_sms(), SKR_CONSUMERS);
     p.rows_per_cta = rows_per_cta;
     int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
     if (slots > 64) slots = 64;
@@ -777,23 +735,14 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     p.do_iter = iters > 0 ? 1 : 0;
     sk_ring_kernel<NV, SK_INIT><<<grid, SKR_THREADS, smem, st>>>(p);
     const bool prof = g_profile && b0 == 0 && nb == a.batch && iters > 1;
-    if (prof) {
-      if (g_ev0 == nullptr) {
-        cudaEventCreate(&g_ev0);
-        cudaEventCreate(&g_ev1);
-      }
-      cudaEventRecord(g_ev0, st);
-    }
+    if (prof) sk_profile_begin(st);
     for (int k = 1; k < iters; ++k) {
       p.col_prev = col[(k - 1) % 3];
       p.col_acc = col[k % 3];
       p.col_zero = col[(k + 1) % 3];
       sk_ring_kernel<NV, SK_ITER><<<grid, SKR_THREADS, smem, st>>>(p);
     }
-    if (prof) {
-      cudaEventRecord(g_ev1, st);
-      g_ev_iters = iters - 1;
-    }
+    if (prof) sk_profile_end(st, iters - 1);
     const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
     p.col_prev = col_last;
     p.col_acc = nullptr;
@@ -804,6 +753,16 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
         p.P, a.p_batch_stride, a.ldp, p.u, col_last, a.write_scores, iters > 0 ? 1 : 0,
         reinterpret_cast<unsigned long long*>(a.col_key) + (size_t)b0 * a.N1max, p.n0s, p.n1s, a.N0max, a.N1max, slab);
   }
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// column arg-max of an already scaled score matrix (used by the compact-storage path when the scores were written)
+int launch_sk_colmax_scaled(const float* P, long long p_bs, int ldp, unsigned long long* col_key, const int* n0s,
+                            const int* n1s, int N0max, int N1max, int batch, cudaStream_t st) {
+  const int slab = 256;
+  sk_colmax_kernel<<<dim3((N1max + 127) / 128, (N0max + slab - 1) / slab, batch), 128, 0, st>>>(
+      P, p_bs, ldp, nullptr, nullptr, 1, 0, col_key, n0s, n1s, N0max, N1max, slab);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }

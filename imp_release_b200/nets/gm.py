@@ -64,6 +64,11 @@ class GM(nn.Module):
         self.attention_precision = self.config.get('attention_precision', 'fp16')
         if self.attention_precision not in ('fp16', 'high'):
             raise ValueError("attention_precision must be 'fp16' or 'high'")
+        # second B200-specific knob: how softmax(M) is stored for the Sinkhorn iteration sweeps of big batches
+        # ('fp32' | 'fp24' | 'fp16', include/imp_b200.h IMP_SK_STORE_*); None = library default (IMP_SK_STORAGE or 'fp24')
+        self.sinkhorn_storage = self.config.get('sinkhorn_storage', None)
+        if self.sinkhorn_storage not in (None, 'fp32', 'fp24', 'fp16'):
+            raise ValueError("sinkhorn_storage must be 'fp32', 'fp24' or 'fp16'")
         self.self_prob0 = self.self_prob1 = self.cross_prob0 = self.cross_prob1 = None
         self._engine: Optional[Engine] = None
         self._engine_key = None
@@ -103,12 +108,12 @@ class GM(nn.Module):
 
     def _sinkhorn_ws(self, B, N0, N1, device, want_mass=False, fresh=False) -> SinkhornWorkspace:
         if fresh:
-            return SinkhornWorkspace(B, N0, N1, device, want_mass)
+            return SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage)
         key = (B, N0, N1, str(device), want_mass)
         if key not in self._sk_cache:
             if len(self._sk_cache) > 8:
                 self._sk_cache.clear()
-            self._sk_cache[key] = SinkhornWorkspace(B, N0, N1, device, want_mass)
+            self._sk_cache[key] = SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage)
         return self._sk_cache[key]
 
     # ------------------------------------------------------------------ batched entry points

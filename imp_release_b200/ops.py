@@ -3,6 +3,7 @@ in libimp_b200.so).  Every function enqueues on the current CUDA stream and neve
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Tuple
 
 import torch
@@ -186,12 +187,31 @@ def small_linear(X, ldx, W, bias, Y, ldy, rows, cin, cout):
               'imp_small_linear')
 
 
+SK_STORAGE = {'fp32': 0, 'fp16': 1, 'fp24': 2}
+SK_STORAGE_BYTES = {0: 4, 1: 2, 2: 3}
+
+
+def default_sk_storage() -> str:
+    """Storage of softmax(M) for the Sinkhorn iteration sweeps (include/imp_b200.h, IMP_SK_STORE_*)."""
+    return os.environ.get('IMP_SK_STORAGE', 'fp24')
+
+
+def _sk_resident_fits(batch: int, R: int, ldp: int, device) -> bool:
+    """Mirror of run_sinkhorn's test (csrc/sinkhorn.cu) for the shared-memory-resident kernel, which never touches the
+    compact copy: lets small problems skip its allocation."""
+    wave = 2 * torch.cuda.get_device_properties(device).multi_processor_count
+    rpc = -(-batch * R // wave)
+    rpc = -(-rpc // 4) * 4
+    return batch * -(-R // rpc) <= wave and (rpc + 2) * ldp * 4 + rpc * 4 + 16 <= 113 * 1024
+
+
 class SinkhornWorkspace:
     """Buffers for one Sinkhorn + matching call on [batch, N0max, N1max] problems."""
 
-    def __init__(self, batch: int, N0max: int, N1max: int, device, want_mass: bool = False):
+    def __init__(self, batch: int, N0max: int, N1max: int, device, want_mass: bool = False, storage: Optional[str] = None):
         self.batch, self.N0max, self.N1max = batch, N0max, N1max
         self.ldp = (N1max + 1 + 3) // 4 * 4
+        self.storage = SK_STORAGE[storage if storage is not None else default_sk_storage()]
         f32 = dict(dtype=torch.float32, device=device)
         self.P = torch.zeros(batch, N0max + 1, self.ldp, **f32)
         self.u = torch.empty(batch, N0max + 1, **f32)
@@ -201,6 +221,13 @@ class SinkhornWorkspace:
         self.col_key = torch.zeros(batch, N1max, dtype=torch.int64, device=device)
         self.row_mass = torch.zeros(batch, N0max, **f32) if want_mass else None
         self.col_mass = torch.zeros(batch, N1max, **f32) if want_mass else None
+        self.q_store = self.row_stats = None
+        self.q_batch_stride = 0
+        if self.storage != 0 and N1max + 1 >= 64 and not _sk_resident_fits(batch, N0max + 1, self.ldp, device):
+            ldq = (N1max + 1 + 15) // 16 * 16
+            self.q_batch_stride = (N0max + 1) * ldq * SK_STORAGE_BYTES[self.storage]
+            self.q_store = torch.empty(batch, self.q_batch_stride, dtype=torch.uint8, device=device)
+            self.row_stats = torch.empty(2, batch, N0max + 1, **f32)
 
     def scores(self) -> torch.Tensor:
         """[batch, N0max+1, N1max+1] view of the padded score buffer (a real torch.Tensor)."""
@@ -221,6 +248,7 @@ def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, 
     a.n0s, a.n1s = ptr(n0s), ptr(n1s)
     a.N0max, a.N1max, a.batch = ws.N0max, ws.N1max, ws.batch
     a.write_scores = int(write_scores)
+    a.q_store, a.q_batch_stride, a.row_stats, a.storage = ptr(ws.q_store), ws.q_batch_stride, ptr(ws.row_stats), ws.storage
     mat_bytes = 4.0 * ws.batch * (ws.N0max + 1) * (ws.N1max + 1)
     # algorithmic traffic: 2 sweeps per iteration + init (read dist, write p) + final (read, write)
     with _Span('sinkhorn', 3 + max(iters - 1, 0), mat_bytes * (2 * iters + 4)):

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IMP_B200_ABI_VERSION 1
+#define IMP_B200_ABI_VERSION 2
 #if defined(__GNUC__)
 #define IMP_API __attribute__((visibility("default")))
 #else
@@ -119,8 +119,22 @@ typedef struct imp_sinkhorn_args {
   float* col_mass;   /* [batch, N1max] or NULL */
   const int32_t *n0s, *n1s; /* per-sample sizes or NULL */
   int32_t N0max, N1max, batch;
-  int32_t write_scores; /* 1: store the final (p u) v into P; 0: P keeps softmax(M) and only arg-max / masses are produced */
+  int32_t write_scores; /* 1: store the final (p u) v into P; 0: only arg-max / masses are produced (P is scratch) */
+  /* Compact storage of softmax(M) for the iteration sweeps (the HBM-bound part: one sweep per iteration).  With
+   * storage != IMP_SK_STORE_F32 the iterations stream a 16- or 24-bit copy of p from q_store, the row softmax
+   * statistics are kept in row_stats, and the final scores / arg-max are recomputed from dist in fp32, so only the
+   * scaling vectors u, v carry the storage rounding (measured deviations: DESIGN.md section 2).  Problems small enough
+   * for the shared-memory-resident kernel ignore it.  q_store: q_batch_stride bytes per matrix, at least
+   * (N0max+1) * roundup16(N1max+1) * (2 or 3) bytes, 16-byte aligned.  row_stats: [2, batch, N0max+1] floats. */
+  void* q_store;
+  int64_t q_batch_stride;
+  float* row_stats;
+  int32_t storage; /* IMP_SK_STORE_* */
+  int32_t _pad2;
 } imp_sinkhorn_args;
+#define IMP_SK_STORE_F32 0 /* iterate on the fp32 matrix in P (bit-for-bit the reference recurrence) */
+#define IMP_SK_STORE_F16 1 /* p * 2^14 as IEEE fp16: 2 bytes per element */
+#define IMP_SK_STORE_F24 2 /* top 16 bits of the fp32 word + one byte of mantissa extension (planar): 3 bytes per element */
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
 /* Measurement aid for bench.py: with profiling on, imp_sinkhorn brackets its iteration launches with CUDA events on the
  * launching stream; imp_sinkhorn_iter_ms() waits for them and returns the mean duration of one iteration kernel of the

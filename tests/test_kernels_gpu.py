@@ -152,7 +152,7 @@ def test_sinkhorn_and_matches(B, N0, N1, iters):
     ldd = (N1 + 3) // 4 * 4
     dd = torch.zeros(B, N0, ldd, device=DEV)
     dd[:, :, :N1] = dist.to(DEV)
-    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True)
+    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True, storage='fp32')
     ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws)
     sc = ws.scores().cpu()
     assert float((sc - ref).abs().max() / ref.abs().max()) < 2e-5
@@ -163,7 +163,7 @@ def test_sinkhorn_and_matches(B, N0, N1, iters):
     assert float((ws.row_mass.cpu() - ref[:, :-1, :-1].sum(-1)).abs().max()) < 1e-4
     assert float((ws.col_mass.cpu() - ref[:, :-1, :-1].sum(1)).abs().max()) < 1e-4
     # arg-max only mode (no write-back of the scaled matrix): identical matches, P keeps softmax(M)
-    ws2 = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True)
+    ws2 = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True, storage='fp32')
     ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws2, write_scores=False)
     k0, k1, q0, q1 = ops.matches(ws2.row_max, ws2.row_arg, ws2.col_key, 0.2, N0, N1, B)
     # (column sums are accumulated with float atomics, so two runs agree to rounding, not bit-for-bit)
@@ -183,7 +183,7 @@ def test_sinkhorn_varlen_and_ties():
     n0s = torch.tensor([200, 150, 33], dtype=torch.int32)
     n1s = torch.tensor([180, 21, 180], dtype=torch.int32)
     ldd = 180
-    ws = ops.SinkhornWorkspace(B, N0, N1, DEV)
+    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, storage='fp32')
     bin_score = torch.tensor(0.7)
     ops.sinkhorn(dist.to(DEV).contiguous(), ldd, bin_score.to(DEV), 20, ws, n0s=n0s.to(DEV), n1s=n1s.to(DEV))
     i0, i1, m0, m1 = ops.matches(ws.row_max, ws.row_arg, ws.col_key, 0.2, N0, N1, B, n0s=n0s.to(DEV), n1s=n1s.to(DEV))
@@ -198,6 +198,96 @@ def test_sinkhorn_varlen_and_ties():
     ops.sinkhorn(torch.zeros(1, 40, 52, device=DEV), 52, bin_score.to(DEV), 3, ws2)
     assert int(ws2.row_arg.max()) == 0
     assert int(((0xFFFFFFFF - (ws2.col_key & 0xFFFFFFFF))).max()) == 0
+
+
+def _quantise_like_kernel(p: torch.Tensor, storage: str) -> torch.Tensor:
+    """CPU restatement of the compact encodings of csrc/sinkhorn_q.cu (skq_store4 / skq_decode8)."""
+    if storage == 'fp16':
+        return (p * 16384.0).half().float() / 16384.0
+    bits = p.contiguous().view(torch.int32)
+    hi, lo = bits >> 16, bits & 0xFFFF
+    q = (lo + 128) // 257
+    return ((hi << 16) | (q << 8) | q).view(torch.float32)
+
+
+def _sinkhorn_on_quantised(p: torch.Tensor, pq: torch.Tensor, iters: int) -> torch.Tensor:
+    """nets/layers.py:27-46 with the iterations reading pq (the first half-iteration and the final scaling use p)."""
+    b, R, C = p.shape
+    r = p.new_ones(b, R); r[:, -1] = R
+    c = p.new_ones(b, C); c[:, -1] = C
+    u, v = torch.ones_like(r), torch.ones_like(c)
+    for k in range(iters):
+        src = p if k == 0 else pq
+        u = r / ((src * v[:, None, :]).sum(-1) + 1e-8)
+        v = c / ((src * u[:, :, None]).sum(-2) + 1e-8)
+    return p * u[:, :, None] * v[:, None, :]
+
+
+@pytest.mark.parametrize('storage,tol', [('fp24', 4e-5), ('fp16', 1e-3)])
+@pytest.mark.parametrize('B,N0,N1,iters', [(40, 700, 650, 20), (12, 1500, 1490, 3), (20, 999, 1040, 20), (6, 2000, 2000, 20),
+                                           (6, 2047, 2047, 20), (48, 600, 250, 1)])
+def test_sinkhorn_compact_storage(storage, tol, B, N0, N1, iters):
+    """Big batches stream a 16-/24-bit copy of softmax(M) in the iteration sweeps.  Two checks: (1) the kernels do exactly
+    what the format says -- a CPU recurrence on the GPU's own p, quantised like the kernel does, must agree to fp32
+    rounding; (2) the result stays within the documented distance of the fp32 oracle."""
+    g = torch.Generator().manual_seed(200 + N0)
+    dist = torch.randn(B, N0, N1, generator=g) * 3
+    for b in range(B):
+        idx = torch.randperm(min(N0, N1), generator=g)[: min(N0, N1) // 2]
+        dist[b, idx, idx] += 12.0
+    bin_score = torch.tensor(1.3)
+    ldd = (N1 + 3) // 4 * 4
+    dd = torch.zeros(B, N0, ldd, device=DEV)
+    dd[:, :, :N1] = dist.to(DEV)
+    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True, storage=storage)
+    assert ws.q_store is not None, 'problem too small to exercise the compact path'
+    ops.sinkhorn(dd, ldd, bin_score.to(DEV), 0, ws)                     # iters = 0: scores = softmax(M)
+    p_gpu = ws.scores().cpu().clone()
+    assert float((p_gpu - torch.softmax(imp_oracle.pad_dustbin(dist, bin_score), -1)).abs().max()) < 1e-6
+    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True, storage=storage)
+    ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws)
+    sc = ws.scores().cpu()
+    emu = _sinkhorn_on_quantised(p_gpu, _quantise_like_kernel(p_gpu, storage), iters)
+    assert float((sc - emu).abs().max() / emu.abs().max()) < 2e-5
+    assert float((sc[:, :-1, :-1] - emu[:, :-1, :-1]).abs().max()) < 1e-5
+    ref = imp_oracle.sink_algorithm(dist, bin_score, iters)
+    assert float((sc[:, :-1, :-1] - ref[:, :-1, :-1]).abs().max()) < tol
+    i0, i1, m0, m1 = ops.matches(ws.row_max, ws.row_arg, ws.col_key, 0.2, N0, N1, B)
+    ei0, ei1, em0, em1 = imp_oracle.compute_matches(emu, 0.2)
+    assert torch.equal(i0.cpu(), ei0) and torch.equal(i1.cpu(), ei1)
+    assert float((m0.cpu() - em0).abs().max()) < 1e-5 and float((m1.cpu() - em1).abs().max()) < 1e-5
+    ri0, ri1, rm0, rm1 = imp_oracle.compute_matches(ref, 0.2)
+    assert torch.equal(i0.cpu(), ri0) and float((m0.cpu() - rm0).abs().max()) < tol
+    assert float((ws.row_mass.cpu() - emu[:, :-1, :-1].sum(-1)).abs().max()) < 1e-4
+    assert float((ws.col_mass.cpu() - emu[:, :-1, :-1].sum(1)).abs().max()) < 1e-4
+    # arg-max only mode: the column arg-max re-derives the scores from dist instead of reading P
+    ws2 = ops.SinkhornWorkspace(B, N0, N1, DEV, want_mass=True, storage=storage)
+    ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws2, write_scores=False)
+    k0, k1, q0, q1 = ops.matches(ws2.row_max, ws2.row_arg, ws2.col_key, 0.2, N0, N1, B)
+    assert torch.equal(k0, i0) and torch.equal(k1, i1) and float((q0 - m0).abs().max()) < 1e-5
+    assert float(ws2.P.abs().max()) == 0.0, 'P must stay untouched when the scores are not requested'
+
+
+@pytest.mark.parametrize('storage', ['fp24', 'fp16'])
+def test_sinkhorn_compact_varlen(storage):
+    B, N0, N1 = 18, 800, 760
+    g = torch.Generator().manual_seed(6)
+    dist = torch.randn(B, N0, N1, generator=g) * 2
+    n0s = torch.randint(1, N0 + 1, (B,), generator=g).to(torch.int32)
+    n1s = torch.randint(1, N1 + 1, (B,), generator=g).to(torch.int32)
+    n0s[0], n1s[0], n0s[1], n1s[1], n0s[2], n1s[2] = N0, N1, 5, N1, N0, 3
+    ws = ops.SinkhornWorkspace(B, N0, N1, DEV, storage=storage)
+    assert ws.q_store is not None
+    bin_score = torch.tensor(0.7)
+    ops.sinkhorn(dist.to(DEV).contiguous(), N1, bin_score.to(DEV), 20, ws, n0s=n0s.to(DEV), n1s=n1s.to(DEV))
+    i0, i1, m0, m1 = ops.matches(ws.row_max, ws.row_arg, ws.col_key, 0.2, N0, N1, B, n0s=n0s.to(DEV), n1s=n1s.to(DEV))
+    tol = 4e-5 if storage == 'fp24' else 1e-3
+    for b in range(B):
+        a, c = int(n0s[b]), int(n1s[b])
+        ref = imp_oracle.sink_algorithm(dist[b:b + 1, :a, :c], bin_score, 20)
+        assert float((ws.P[b, :a + 1, :c + 1].cpu() - ref[0])[:-1, :-1].abs().max()) < tol
+        ri0, ri1, rm0, rm1 = imp_oracle.compute_matches(ref, 0.2)
+        assert torch.equal(i0[b, :a].cpu(), ri0[0]) and torch.equal(i1[b, :c].cpu(), ri1[0])
 
 
 def test_instnorm_small_linear_kenc_gather():
