@@ -691,9 +691,8 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     }
   }
 
-  // big batches: the iteration sweeps read a compact (16- or 24-bit) copy of softmax(M) instead of the fp32 matrix
-  if (a.storage != IMP_SK_STORE_F32 && a.q_store != nullptr && a.row_stats != nullptr && a.N1max + 1 >= 64)
-    return run_sinkhorn_compact(a, st);
+  // big batches with a q_store workspace: column-split kernels over a stored (fp32 / 24-bit / fp16) copy of softmax(M)
+  if (a.q_store != nullptr && a.row_stats != nullptr && a.N1max + 1 >= 64 && a.N1max + 1 <= 4096) return run_sinkhorn_compact(a, st);
 
   for (int b0 = 0; b0 < a.batch; b0 += chunk) {
     const int nb = (a.batch - b0 < chunk) ? a.batch - b0 : chunk;
@@ -753,16 +752,6 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
         p.P, a.p_batch_stride, a.ldp, p.u, col_last, a.write_scores, iters > 0 ? 1 : 0,
         reinterpret_cast<unsigned long long*>(a.col_key) + (size_t)b0 * a.N1max, p.n0s, p.n1s, a.N0max, a.N1max, slab);
   }
-  IMP_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
-// column arg-max of an already scaled score matrix (used by the compact-storage path when the scores were written)
-int launch_sk_colmax_scaled(const float* P, long long p_bs, int ldp, unsigned long long* col_key, const int* n0s,
-                            const int* n1s, int N0max, int N1max, int batch, cudaStream_t st) {
-  const int slab = 256;
-  sk_colmax_kernel<<<dim3((N1max + 127) / 128, (N0max + slab - 1) / slab, batch), 128, 0, st>>>(
-      P, p_bs, ldp, nullptr, nullptr, 1, 0, col_key, n0s, n1s, N0max, N1max, slab);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }

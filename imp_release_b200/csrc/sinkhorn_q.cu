@@ -1,14 +1,21 @@
-// Sinkhorn with compact storage of softmax(M) for the iteration sweeps (nets/layers.py:27-46, same recurrence as
-// sinkhorn.cu).  At 64 pairs x 2001^2 the 19 iteration sweeps are pure HBM streaming, so the only way to make them
-// faster is to move fewer bytes: the init pass writes p = softmax_rows(pad(dist)) as a 16-bit (p * 2^14 in IEEE fp16)
-// or 24-bit (top 16 bits of the fp32 word + one byte of mantissa extension, planar) copy, the iteration kernel streams
-// that copy through the same shared-memory row ring (1-D bulk TMA copies, producer warp + consumer warps, 2 CTAs/SM),
-// and the final pass and the column arg-max re-derive p in fp32 from dist and the saved row statistics (max, 1/sum), so
-// the rounding of the copy only enters through the scaling vectors u and v (deviations measured in DESIGN.md).
-// All arithmetic on the decoded values is fp32.
+// Sinkhorn for big batches (nets/layers.py:27-46, same recurrence as sinkhorn.cu), "column-split" streaming kernels.
 //
-// Sweep direction alternates from launch to launch (blocks are walked back to front on odd launches) so that the tail
-// of the previous sweep, still resident in the 126 MB L2, is what the next sweep reads first.
+// At 64 pairs x 2001^2 the 19 iteration sweeps are pure HBM streaming, so they get faster only by moving fewer bytes and
+// by keeping the SM-side cost per element far below the HBM rate:
+//  * storage: the init pass writes p = softmax_rows(pad(dist)) as fp32, as a 24-bit copy (top 16 bits of the fp32 word +
+//    one byte of mantissa extension, planar) or as p * 2^14 in IEEE fp16; the final pass re-derives p in fp32 from dist
+//    and the saved row statistics (max, 1/sum), so the rounding of the copy only enters through the scaling vectors u, v
+//    (measured deviations: DESIGN.md section 2).  All arithmetic on decoded values is fp32.
+//  * work split: a CTA owns a block of rows; its 8 consumer warps split the COLUMNS, every lane owning 8 fixed columns.
+//    v_j, the column-sum accumulators and (final pass) the column arg-max trackers of those columns live in registers for
+//    the whole CTA, so shared memory is touched exactly once per element (the bulk-TMA landing zone).  Rows are handled
+//    T at a time: per-row partial sums are reduced with a transposed shuffle tree (9 shuffles for 8 rows), exchanged
+//    through a few floats of shared memory with ONE named barrier per T rows, and the slot is handed back to the producer
+//    warp as soon as the rows sit in registers.
+//  * one sweep per iteration (u_i, then p_ij u_i folded into the column sums the next launch turns into v), and the final
+//    pass also produces the column arg-max (packed atomicMax per owned column), so a scoring is 1 + 19 + 1 sweeps.
+//  * sweep direction alternates from launch to launch so that the tail of the previous sweep, still resident in the
+//    126 MB L2, is what the next sweep reads first.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -17,23 +24,26 @@
 
 namespace imp {
 
-int launch_sk_colmax_scaled(const float* P, long long p_bs, int ldp, unsigned long long* col_key, const int* n0s,
-                            const int* n1s, int N0max, int N1max, int batch, cudaStream_t st);  // sinkhorn.cu
-
-static constexpr int SKQ_CONSUMERS = 4;
-static constexpr int SKQ_THREADS = (SKQ_CONSUMERS + 1) * 32;  // + one producer warp
-static constexpr int SKQ_SMEM_BUDGET = 113 * 1024;            // two CTAs per SM
-static constexpr float SKQ_F16_SCALE = 16384.f;               // p <= 1 -> <= 2^14; fp16 normals reach down to p = 3.7e-9
+static constexpr int SKQ_CW = 8;                          // consumer warps (column owners)
+static constexpr int SKQ_THREADS = (SKQ_CW + 1) * 32;     // + one producer warp
+static constexpr int SKQ_SMEM_BUDGET = 113 * 1024;        // two CTAs per SM
+static constexpr int SKQ_FIXED_SMEM = 4096;               // partial-sum exchange + barriers
+static constexpr float SKQ_F16_SCALE = 16384.f;           // p <= 1 -> <= 2^14; fp16 normals reach down to p = 3.7e-9
 static constexpr float SKQ_F16_INV = 1.f / 16384.f;
 
-enum { QF16 = IMP_SK_STORE_F16, QF24 = IMP_SK_STORE_F24 };
+enum { QF32 = IMP_SK_STORE_F32, QF16 = IMP_SK_STORE_F16, QF24 = IMP_SK_STORE_F24 };
+template <int FMT>
+struct QFmt {
+  static constexpr int BPE = FMT == QF32 ? 4 : (FMT == QF16 ? 2 : 3);  // bytes per element
+  static constexpr int RAW = FMT == QF32 ? 8 : (FMT == QF16 ? 4 : 6);  // 32-bit registers per 8 elements
+};
 
 struct SkqParams {
   const float* dist;
   long long dist_bs;
   int ldd;
   const float* bin_score;
-  unsigned char* Q;  // per matrix: [Rmax][ldq] 16-bit plane, then (24-bit format) [Rmax][ldq] 8-bit plane
+  unsigned char* Q;  // per matrix [Rmax][ldq] x {fp32 | fp16 | 16-bit plane followed by an 8-bit plane}
   long long q_bs;    // bytes
   int ldq, Rmax;
   float* P;
@@ -50,14 +60,28 @@ struct SkqParams {
   int* row_arg;
   float* row_mass;
   float* col_mass;
+  unsigned long long* col_key;
   const int *n0s, *n1s;
   int N0max, N1max;
-  int rows_per_cta, ring_slots, slot_bytes;
+  int rows_per_cta, nslots, slot_bytes, row_bytes;
   int do_iter, write_scores, reverse;
 };
 
-__device__ __forceinline__ void skq_consumer_sync() {
-  asm volatile("bar.sync 1, %0;" ::"n"(SKQ_CONSUMERS * 32) : "memory");
+__device__ __forceinline__ void skq_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SKQ_CW * 32) : "memory"); }
+
+// Hand a ring slot back to the producer.  The arrive must not overtake the shared-memory loads that filled the consumer's
+// registers: an LDS that is issued but not yet performed is NOT ordered before a later mbarrier.arrive by the hardware
+// (measured: a few rows per launch read the refilled slot), so the arrive is made data-dependent on `dep`, a value that
+// every lane's loads of the slot feed through a warp shuffle reduction (bits 0xffffffff = a NaN pattern the reductions
+// never produce, so the predicate is always true, but ptxas cannot know).
+__device__ __forceinline__ void skq_release(uint64_t* bar, int lane, float dep) {
+  if (lane == 0)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.u32 p, %1, 0xffffffff;\n\t"
+        "@p mbarrier.arrive.shared::cta.b64 _, [%0];\n\t}\n" ::"r"(smem_u32(bar)),
+        "r"(__float_as_uint(dep))
+        : "memory");
 }
 
 // logits of one float4 group of the padded matrix: dustbin column / row = bin, -FLT_MAX beyond C
@@ -84,50 +108,92 @@ __device__ __forceinline__ void skq_enc24(float x, uint32_t& hi, uint32_t& lo) {
 }
 
 template <int FMT>
-__device__ __forceinline__ void skq_store4(unsigned char* qhi, unsigned char* qlo, int c0, float4 t) {
-  if (FMT == QF16) {
+__device__ __forceinline__ void skq_store4(unsigned char* qrow, unsigned char* qlo, int c0, float4 t) {
+  if (FMT == QF32) {
+    *reinterpret_cast<float4*>(qrow + 4 * c0) = t;
+  } else if (FMT == QF16) {
     uint2 e;
     e.x = pack_half2(t.x * SKQ_F16_SCALE, t.y * SKQ_F16_SCALE);
     e.y = pack_half2(t.z * SKQ_F16_SCALE, t.w * SKQ_F16_SCALE);
-    *reinterpret_cast<uint2*>(qhi + 2 * c0) = e;
+    *reinterpret_cast<uint2*>(qrow + 2 * c0) = e;
   } else {
     uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
     skq_enc24(t.x, h0, l0);
     skq_enc24(t.y, h1, l1);
     skq_enc24(t.z, h2, l2);
     skq_enc24(t.w, h3, l3);
-    *reinterpret_cast<uint2*>(qhi + 2 * c0) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
+    *reinterpret_cast<uint2*>(qrow + 2 * c0) = make_uint2(h0 | (h1 << 16), h2 | (h3 << 16));
     *reinterpret_cast<uint32_t*>(qlo + c0) = l0 | (l1 << 8) | (l2 << 16) | (l3 << 24);
   }
 }
 
-// eight consecutive elements of a ring slot -> fp32 (fp16 format: still scaled by 2^14)
+// eight consecutive elements of a staged row: raw registers <- shared memory, fp32 <- raw registers
 template <int FMT>
-__device__ __forceinline__ void skq_decode8(const unsigned char* srow, int lo_off, int c0, float (&f)[8]) {
-  const uint4 h = *reinterpret_cast<const uint4*>(srow + 2 * c0);
-  if (FMT == QF16) {
-    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&h.x));
-    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&h.y));
-    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&h.z));
-    const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&h.w));
-    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y; f[4] = c.x; f[5] = c.y; f[6] = d.x; f[7] = d.y;
+__device__ __forceinline__ void skq_load8(const unsigned char* srow, int lo_off, int c0, uint32_t (&r)[QFmt<FMT>::RAW]) {
+  if constexpr (FMT == QF32) {
+    const uint4 a = *reinterpret_cast<const uint4*>(srow + 4 * c0);
+    const uint4 b = *reinterpret_cast<const uint4*>(srow + 4 * c0 + 16);
+    r[0] = a.x; r[1] = a.y; r[2] = a.z; r[3] = a.w;
+    r[4] = b.x; r[5] = b.y; r[6] = b.z; r[7] = b.w;
   } else {
-    const uint2 l = *reinterpret_cast<const uint2*>(srow + lo_off + c0);
-    f[0] = __uint_as_float(__byte_perm(h.x, l.x, 0x1044));
-    f[1] = __uint_as_float(__byte_perm(h.x, l.x, 0x3255));
-    f[2] = __uint_as_float(__byte_perm(h.y, l.x, 0x1066));
-    f[3] = __uint_as_float(__byte_perm(h.y, l.x, 0x3277));
-    f[4] = __uint_as_float(__byte_perm(h.z, l.y, 0x1044));
-    f[5] = __uint_as_float(__byte_perm(h.z, l.y, 0x3255));
-    f[6] = __uint_as_float(__byte_perm(h.w, l.y, 0x1066));
-    f[7] = __uint_as_float(__byte_perm(h.w, l.y, 0x3277));
+    const uint4 h = *reinterpret_cast<const uint4*>(srow + 2 * c0);
+    r[0] = h.x; r[1] = h.y; r[2] = h.z; r[3] = h.w;
+    if constexpr (FMT == QF24) {
+      const uint2 l = *reinterpret_cast<const uint2*>(srow + lo_off + c0);
+      r[4] = l.x;
+      r[5] = l.y;
+    }
+  }
+}
+template <int FMT>
+__device__ __forceinline__ void skq_decode8(const uint32_t (&r)[QFmt<FMT>::RAW], float (&f)[8]) {
+  if constexpr (FMT == QF32) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(r[q]);
+  } else if constexpr (FMT == QF16) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r[q]));
+      f[2 * q] = a.x;
+      f[2 * q + 1] = a.y;
+    }
+  } else {
+    f[0] = __uint_as_float(__byte_perm(r[0], r[4], 0x1044));
+    f[1] = __uint_as_float(__byte_perm(r[0], r[4], 0x3255));
+    f[2] = __uint_as_float(__byte_perm(r[1], r[4], 0x1066));
+    f[3] = __uint_as_float(__byte_perm(r[1], r[4], 0x3277));
+    f[4] = __uint_as_float(__byte_perm(r[2], r[5], 0x1044));
+    f[5] = __uint_as_float(__byte_perm(r[2], r[5], 0x3255));
+    f[6] = __uint_as_float(__byte_perm(r[3], r[5], 0x1066));
+    f[7] = __uint_as_float(__byte_perm(r[3], r[5], 0x3277));
   }
 }
 
-// The iteration kernel reads v and accumulates column sums in groups of eight columns per lane; to keep the float4
-// shared-memory accesses of a warp on consecutive 16-byte words, columns 8g..8g+3 live at [4g..4g+3] and columns
-// 8g+4..8g+7 at [half + 4g ..].
-__device__ __forceinline__ int skq_perm(int c, int half) { return ((c >> 3) << 2) + (c & 3) + ((c & 4) ? half : 0); }
+// Transposed warp reduction of T per-row values: after log2(T) "keep one half, send the other" steps every lane holds
+// ONE row's partial, the remaining steps are plain butterflies.  Returns the warp total of row skq_rid<T>(lane) (the same
+// in the 32/T lanes that share that row id).  9 shuffles for T = 8 instead of 40.
+template <int T>
+__device__ __forceinline__ int skq_rid(int lane) {
+  return T == 8 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) : (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+}
+template <int T, typename Op>
+__device__ __forceinline__ float skq_tr_reduce(float (&a)[T], int lane, Op op) {
+  static_assert(T == 4 || T == 8, "T must be 4 or 8");
+  int h = 16;
+#pragma unroll
+  for (int n = T / 2; n >= 1; n >>= 1, h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const float send = up ? a[i] : a[i + n];
+      const float keep = up ? a[i + n] : a[i];
+      a[i] = op(keep, __shfl_xor_sync(0xffffffffu, send, h));
+    }
+  }
+  float r = a[0];
+  for (; h >= 1; h >>= 1) r = op(r, __shfl_xor_sync(0xffffffffu, r, h));
+  return r;
+}
 
 struct SkqCta {
   int b, row0, nrows, R, C, Cq;
@@ -145,449 +211,530 @@ __device__ __forceinline__ bool skq_cta(const SkqParams& p, SkqCta& c) {
   return true;
 }
 
-// producer warp for the passes that stream dist rows (init, final)
-__device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqCta& c, unsigned char* ring, uint64_t* full_bar,
-                                                 uint64_t* empty_bar) {
+struct SkqSmem {
+  unsigned char* ring;
+  float* part;  // exchange area, 512 floats
+  uint64_t *full_bar, *empty_bar;
+};
+__device__ __forceinline__ SkqSmem skq_smem_setup(unsigned char* base, const SkqParams& p) {
+  SkqSmem s;
+  s.ring = base;
+  s.part = reinterpret_cast<float*>(base + (size_t)p.nslots * p.slot_bytes);
+  s.full_bar = reinterpret_cast<uint64_t*>(s.part + 512);
+  s.empty_bar = s.full_bar + p.nslots;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < p.nslots; ++i) {
+      mbar_init(&s.full_bar[i], 1);
+      mbar_init(&s.empty_bar[i], SKQ_CW);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+  return s;
+}
+
+// producer warp for the passes that stream dist rows (init, final): T rows per slot
+template <int T>
+__device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqCta& c, const SkqSmem& s) {
   if (lane_id() != 0) return;
   const float* src = p.dist + c.b * p.dist_bs;
   const uint32_t bytes = (uint32_t)(((c.C - 1 + 3) & ~3) * 4);
-  const int S = p.ring_slots;
-  for (int r = 0; r < c.nrows; ++r) {
-    const int s = r % S;
-    mbar_wait(&empty_bar[s], ((r / S) & 1) ^ 1);
-    const int i = c.row0 + r;
-    if (i == c.R - 1 || bytes == 0) {
-      mbar_arrive(&full_bar[s]);  // the dustbin row has no source: the consumer synthesises it
-    } else {
-      mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_copy_g2s(ring + (size_t)s * p.slot_bytes, src + (long long)i * p.ldd, bytes, &full_bar[s]);
+  const int nbatch = (c.nrows + T - 1) / T;
+  for (int n = 0; n < nbatch; ++n) {
+    const int slot = n % p.nslots;
+    mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+    const int i0 = c.row0 + n * T;
+    const int nb = min(T, c.nrows - n * T);
+    int ncopy = 0;
+    for (int t = 0; t < nb; ++t) ncopy += (i0 + t != c.R - 1 && bytes != 0) ? 1 : 0;  // the dustbin row has no source
+    if (ncopy == 0) {
+      mbar_arrive(&s.full_bar[slot]);
+      continue;
     }
+    mbar_arrive_expect_tx(&s.full_bar[slot], bytes * ncopy);
+    unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
+    for (int t = 0; t < nb; ++t)
+      if (i0 + t != c.R - 1 && bytes != 0)
+        bulk_copy_g2s(dst + (size_t)t * p.row_bytes, src + (long long)(i0 + t) * p.ldd, bytes, &s.full_bar[slot]);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// init: p = softmax_rows(pad(dist)) -> compact copy + row statistics (+ first half-iteration: u with v = 1 and the
-// column sums with that u, from the exact fp32 p)
-template <int NV4, int FMT>
+// init: p = softmax_rows(pad(dist)) -> stored copy + row statistics (+ first half-iteration: u with v = 1 and the
+// column sums with that u, from the exact fp32 p).  Lanes own NG = 2 * NVW float4 column groups.
+template <int FMT, int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
+  constexpr int NG = 2 * NVW;
   SkqCta c;
   if (!skq_cta(p, c)) return;
-  const int S = p.ring_slots;
-  unsigned char* ring = skq_smem;
-  float* s_col = reinterpret_cast<float*>(ring + (size_t)S * p.slot_bytes) + p.ldq;  // [ldq] (after the unused s_v)
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_col + p.ldq);
-  uint64_t* empty_bar = full_bar + S;
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (warp == SKQ_CONSUMERS) {
-    skq_produce_dist(p, c, ring, full_bar, empty_bar);
+  const SkqSmem s = skq_smem_setup(skq_smem, p);
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  if (warp == SKQ_CW) {
+    skq_produce_dist<T>(p, c, s);
     return;
   }
-  const int ct = threadIdx.x;
   const int b = c.b;
   if (c.row0 == 0 && p.col_zero != nullptr)
-    for (int j = ct; j < p.ldc; j += SKQ_CONSUMERS * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
-  for (int j = ct; j < p.ldq; j += SKQ_CONSUMERS * 32) s_col[j] = 0.f;
-  skq_consumer_sync();
-
+    for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
+  float* s_max = s.part;              // [T][CW]
+  float* s_sum = s.part + T * SKQ_CW; // [T][CW]
   const float bin = *p.bin_score;
-  float4 acc[NV4];
+  const int rid = skq_rid<T>(lane);
+  int c0s[NG];
 #pragma unroll
-  for (int k = 0; k < NV4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NG; ++k) c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
+  float4 acc[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int r = warp; r < c.nrows; r += SKQ_CONSUMERS) {
-    const int s = r % S;
-    const int i = c.row0 + r;
-    mbar_wait(&full_bar[s], (r / S) & 1);
-    float* srow = reinterpret_cast<float*>(ring + (size_t)s * p.slot_bytes);
-    const bool bin_row = (i == c.R - 1);
-    // pass 1: materialise the padded logits in the slot and take the row max (each lane only touches its own groups)
-    float m = -FLT_MAX;
+  const int nbatch = (c.nrows + T - 1) / T;
+  for (int n = 0; n < nbatch; ++n) {
+    const int slot = n % p.nslots;
+    const int nb = min(T, c.nrows - n * T);
+    const int i0 = c.row0 + n * T;
+    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
+    // pass 1: padded logits into registers, per-row max
+    float4 x[T][NG];
+    float red[T];
 #pragma unroll
-    for (int k = 0; k < NV4; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 < c.C) {
-        const float4 t = skq_logits(srow, c0, c.C, bin_row, bin);
-        if (bin_row || c0 + 3 >= c.C - 1) *reinterpret_cast<float4*>(srow + c0) = t;
-        m = fmaxf(m, fmaxf(fmaxf(t.x, t.y), fmaxf(t.z, t.w)));
+    for (int t = 0; t < T; ++t) {
+      red[t] = -FLT_MAX;
+      if (t < nb) {
+        const bool bin_row = (i0 + t == c.R - 1);
+        const float* srow = reinterpret_cast<const float*>(sb + (size_t)t * p.row_bytes);
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+          if (c0s[k] < c.C) {
+            x[t][k] = skq_logits(srow, c0s[k], c.C, bin_row, bin);
+            red[t] = fmaxf(red[t], fmaxf(fmaxf(x[t][k].x, x[t][k].y), fmaxf(x[t][k].z, x[t][k].w)));
+          }
       }
     }
-    m = warp_max(m);
-    // pass 2: e = exp(x - max) in place, row sum
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV4; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 < c.C) {
-        float4 t = *reinterpret_cast<const float4*>(srow + c0);
-        t.x = sk_exp(t.x - m);
-        t.y = sk_exp(t.y - m);
-        t.z = sk_exp(t.z - m);
-        t.w = sk_exp(t.w - m);
-        *reinterpret_cast<float4*>(srow + c0) = t;
-        sum += (t.x + t.y) + (t.z + t.w);
-      }
-    }
-    sum = warp_sum(sum);
-    const float inv_sum = 1.0f / sum;
-    const float ui = p.do_iter ? (bin_row ? (float)c.R : 1.f) / (sum * inv_sum + SK_EPS) : 0.f;
-    if (lane_id() == 0) {
-      if (p.do_iter) p.u[(long long)b * p.Rmax + i] = ui;
-      p.row_m[(long long)b * p.Rmax + i] = m;
-      p.row_inv[(long long)b * p.Rmax + i] = inv_sum;
-    }
-    // pass 3: normalise, encode, store; fold p * u into the column accumulators
-    unsigned char* qhi = p.Q + b * p.q_bs + (size_t)i * p.ldq * 2;
-    unsigned char* qlo = p.Q + b * p.q_bs + (size_t)p.Rmax * p.ldq * 2 + (size_t)i * p.ldq;
-#pragma unroll
-    for (int k = 0; k < NV4; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 < c.C) {
-        float4 t = *reinterpret_cast<const float4*>(srow + c0);
-        t.x = __fmul_rn(t.x, inv_sum);
-        t.y = __fmul_rn(t.y, inv_sum);
-        t.z = __fmul_rn(t.z, inv_sum);
-        t.w = __fmul_rn(t.w, inv_sum);
-        skq_store4<FMT>(qhi, qlo, c0, t);
-        acc[k].x += t.x * ui;
-        acc[k].y += t.y * ui;
-        acc[k].z += t.z * ui;
-        acc[k].w += t.w * ui;
-      } else if (c0 < c.Cq) {
-        skq_store4<FMT>(qhi, qlo, c0, make_float4(0.f, 0.f, 0.f, 0.f));
-      }
-    }
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(&empty_bar[s]);
-  }
-
-  if (p.do_iter) {
-#pragma unroll
-    for (int k = 0; k < NV4; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 < c.C) {
-        atomicAdd(s_col + c0 + 0, acc[k].x);
-        atomicAdd(s_col + c0 + 1, acc[k].y);
-        atomicAdd(s_col + c0 + 2, acc[k].z);
-        atomicAdd(s_col + c0 + 3, acc[k].w);
-      }
+    {
+      const float m = skq_tr_reduce<T>(red, lane, [](float a, float b2) { return fmaxf(a, b2); });
+      skq_release(&s.empty_bar[slot], lane, m);  // every lane's logits sit in registers (they fed m)
+      if ((lane & (32 / T - 1)) == 0) s_max[rid * SKQ_CW + warp] = m;
     }
     skq_consumer_sync();
-    for (int j = ct; j < c.C; j += SKQ_CONSUMERS * 32) atomicAdd(p.col_acc + (long long)b * p.ldc + j, s_col[j]);
+    float my_m = -FLT_MAX;
+    if (lane < T) {
+      const float4 a = *reinterpret_cast<const float4*>(s_max + lane * SKQ_CW);
+      const float4 d = *reinterpret_cast<const float4*>(s_max + lane * SKQ_CW + 4);
+      my_m = fmaxf(fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)), fmaxf(fmaxf(d.x, d.y), fmaxf(d.z, d.w)));
+    }
+    // pass 2: e = exp(x - max), per-row sum
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float m = __shfl_sync(0xffffffffu, my_m, t);
+      red[t] = 0.f;
+      if (t < nb) {
+#pragma unroll
+        for (int k = 0; k < NG; ++k)
+          if (c0s[k] < c.C) {
+            x[t][k].x = sk_exp(x[t][k].x - m);
+            x[t][k].y = sk_exp(x[t][k].y - m);
+            x[t][k].z = sk_exp(x[t][k].z - m);
+            x[t][k].w = sk_exp(x[t][k].w - m);
+            red[t] += (x[t][k].x + x[t][k].y) + (x[t][k].z + x[t][k].w);
+          }
+      }
+    }
+    {
+      const float sm = skq_tr_reduce<T>(red, lane, [](float a, float b2) { return a + b2; });
+      if ((lane & (32 / T - 1)) == 0) s_sum[rid * SKQ_CW + warp] = sm;
+    }
+    skq_consumer_sync();
+    float my_inv = 0.f, my_u = 0.f;
+    if (lane < T) {
+      const float4 a = *reinterpret_cast<const float4*>(s_sum + lane * SKQ_CW);
+      const float4 d = *reinterpret_cast<const float4*>(s_sum + lane * SKQ_CW + 4);
+      const float sum = ((a.x + a.y) + (a.z + a.w)) + ((d.x + d.y) + (d.z + d.w));
+      my_inv = 1.0f / sum;  // one division per row; p = e * (1/sum) differs from e / sum by <= 1 ulp
+      // first half-iteration with v = 1: sum_j p_ij = sum * inv_sum to ~1e-7 relative
+      my_u = p.do_iter ? ((i0 + lane == c.R - 1) ? (float)c.R : 1.f) / (sum * my_inv + SK_EPS) : 0.f;
+      if (warp == 0 && lane < nb) {
+        const long long o = (long long)b * p.Rmax + i0 + lane;
+        if (p.do_iter) p.u[o] = my_u;
+        p.row_m[o] = my_m;
+        p.row_inv[o] = my_inv;
+      }
+    }
+    // pass 3: normalise, encode, store; fold p * u into the column accumulators
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float inv = __shfl_sync(0xffffffffu, my_inv, t);
+      const float ui = __shfl_sync(0xffffffffu, my_u, t);
+      if (t < nb) {
+        unsigned char* qrow = p.Q + b * p.q_bs + (size_t)(i0 + t) * p.ldq * (FMT == QF24 ? 2 : QFmt<FMT>::BPE);
+        unsigned char* qlo = p.Q + b * p.q_bs + (size_t)p.Rmax * p.ldq * 2 + (size_t)(i0 + t) * p.ldq;
+#pragma unroll
+        for (int k = 0; k < NG; ++k) {
+          if (c0s[k] < c.C) {
+            float4 e = x[t][k];
+            e.x = __fmul_rn(e.x, inv);
+            e.y = __fmul_rn(e.y, inv);
+            e.z = __fmul_rn(e.z, inv);
+            e.w = __fmul_rn(e.w, inv);
+            skq_store4<FMT>(qrow, qlo, c0s[k], e);
+            acc[k].x = fmaf(e.x, ui, acc[k].x);
+            acc[k].y = fmaf(e.y, ui, acc[k].y);
+            acc[k].z = fmaf(e.z, ui, acc[k].z);
+            acc[k].w = fmaf(e.w, ui, acc[k].w);
+          } else if (c0s[k] < c.Cq) {
+            skq_store4<FMT>(qrow, qlo, c0s[k], make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+      }
+    }
+  }
+  if (p.do_iter) {
+    float* ca = p.col_acc + (long long)b * p.ldc;
+#pragma unroll
+    for (int k = 0; k < NG; ++k) {
+      if (c0s[k] + 0 < c.C) atomicAdd(ca + c0s[k] + 0, acc[k].x);
+      if (c0s[k] + 1 < c.C) atomicAdd(ca + c0s[k] + 1, acc[k].y);
+      if (c0s[k] + 2 < c.C) atomicAdd(ca + c0s[k] + 2, acc[k].z);
+      if (c0s[k] + 3 < c.C) atomicAdd(ca + c0s[k] + 3, acc[k].w);
+    }
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// one Sinkhorn iteration in a single sweep over the compact copy: u_i = r_i / (sum_j p_ij v_j + eps), then p_ij u_i
-// folded into the column sums the next launch turns into v
-template <int NV8, int FMT>
+// one Sinkhorn iteration in a single sweep over the stored copy: u_i = r_i / (sum_j p_ij v_j + eps), then p_ij u_i
+// folded into the column sums the next launch turns into v.  Lanes own NVW groups of 8 columns.
+template <int FMT, int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
+  constexpr int RAW = QFmt<FMT>::RAW;
   SkqCta c;
   if (!skq_cta(p, c)) return;
-  const int S = p.ring_slots;
-  unsigned char* ring = skq_smem;
-  float* s_v = reinterpret_cast<float*>(ring + (size_t)S * p.slot_bytes);  // [ldq], permuted (skq_perm), pre-scaled
-  float* s_col = s_v + p.ldq;                                               // [ldq], permuted
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_col + p.ldq);
-  uint64_t* empty_bar = full_bar + S;
-  const int warp = threadIdx.x >> 5;
-  const int half = p.ldq >> 1;
-  const int lo_off = p.ldq * 2;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
+  const SkqSmem s = skq_smem_setup(skq_smem, p);
+  const int warp = threadIdx.x >> 5, lane = lane_id();
   const int b = c.b;
+  const int lo_off = p.ldq * 2;
+  const int nbatch = (c.nrows + T - 1) / T;
 
-  if (warp == SKQ_CONSUMERS) {
-    if (lane_id() == 0) {
-      const unsigned char* qhi = p.Q + b * p.q_bs;
-      const unsigned char* qlo = qhi + (size_t)p.Rmax * p.ldq * 2;
-      const uint32_t hi_bytes = (uint32_t)c.Cq * 2, lo_bytes = (uint32_t)c.Cq;
-      for (int r = 0; r < c.nrows; ++r) {
-        const int s = r % S;
-        mbar_wait(&empty_bar[s], ((r / S) & 1) ^ 1);
-        const int i = c.row0 + r;
-        unsigned char* dst = ring + (size_t)s * p.slot_bytes;
-        mbar_arrive_expect_tx(&full_bar[s], FMT == QF16 ? hi_bytes : hi_bytes + lo_bytes);
-        bulk_copy_g2s(dst, qhi + (size_t)i * p.ldq * 2, hi_bytes, &full_bar[s]);
-        if (FMT == QF24) bulk_copy_g2s(dst + lo_off, qlo + (size_t)i * p.ldq, lo_bytes, &full_bar[s]);
+  if (warp == SKQ_CW) {
+    if (lane == 0) {
+      const unsigned char* q0 = p.Q + b * p.q_bs;
+      const unsigned char* qlo = q0 + (size_t)p.Rmax * p.ldq * 2;
+      const uint32_t main_bytes = (uint32_t)c.Cq * (FMT == QF24 ? 2 : QFmt<FMT>::BPE), lo_bytes = (uint32_t)c.Cq;
+      const size_t main_stride = (size_t)p.ldq * (FMT == QF24 ? 2 : QFmt<FMT>::BPE);
+      for (int n = 0; n < nbatch; ++n) {
+        const int slot = n % p.nslots;
+        mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+        const int i0 = c.row0 + n * T;
+        const int nb = min(T, c.nrows - n * T);
+        mbar_arrive_expect_tx(&s.full_bar[slot], (FMT == QF24 ? main_bytes + lo_bytes : main_bytes) * nb);
+        unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
+        for (int t = 0; t < nb; ++t) {
+          bulk_copy_g2s(dst + (size_t)t * p.row_bytes, q0 + (size_t)(i0 + t) * main_stride, main_bytes, &s.full_bar[slot]);
+          if (FMT == QF24)
+            bulk_copy_g2s(dst + (size_t)t * p.row_bytes + lo_off, qlo + (size_t)(i0 + t) * p.ldq, lo_bytes, &s.full_bar[slot]);
+        }
       }
     }
     return;
   }
 
-  const int ct = threadIdx.x;
   if (c.row0 == 0 && p.col_zero != nullptr)
-    for (int j = ct; j < p.ldc; j += SKQ_CONSUMERS * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
+    for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
+  // v_j of the owned columns (pre-scaled for the fp16 copy) and their column-sum accumulators
   const float vscale = (FMT == QF16) ? SKQ_F16_INV : 1.f;
-  for (int c0 = 4 * ct; c0 < p.ldq; c0 += 4 * SKQ_CONSUMERS * 32) {
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (c0 < c.C) v = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0, c.C);  // C <= ldc, both multiples of 4 apart
-    v.x *= vscale;
-    v.y *= vscale;
-    v.z *= vscale;
-    v.w *= vscale;
-    const int o = skq_perm(c0, half);  // c0 % 4 == 0: the four columns stay adjacent
-    *reinterpret_cast<float4*>(s_v + o) = v;
-    *reinterpret_cast<float4*>(s_col + o) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  skq_consumer_sync();
-
-  float acc[NV8][8];
+  int c0s[NVW];
+  float v[NVW][8], acc[NVW][8];
 #pragma unroll
-  for (int k = 0; k < NV8; ++k)
+  for (int k = 0; k < NVW; ++k) {
+    c0s[k] = 8 * ((warp * NVW + k) * 32 + lane);
+    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
+    if (c0s[k] < c.C) va = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k], c.C);  // C <= ldc, both multiples of 4 apart
+    if (c0s[k] + 4 < c.C) vb = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k] + 4, c.C);
+    v[k][0] = va.x * vscale; v[k][1] = va.y * vscale; v[k][2] = va.z * vscale; v[k][3] = va.w * vscale;
+    v[k][4] = vb.x * vscale; v[k][5] = vb.y * vscale; v[k][6] = vb.z * vscale; v[k][7] = vb.w * vscale;
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
-
-  for (int r = warp; r < c.nrows; r += SKQ_CONSUMERS) {
-    const int s = r % S;
-    const int i = c.row0 + r;
-    mbar_wait(&full_bar[s], (r / S) & 1);
-    const unsigned char* srow = ring + (size_t)s * p.slot_bytes;
-    float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV8; ++k) {
-      const int g = lane_id() + 32 * k;
-      if (8 * g < c.Cq) {
-        float f[8];
-        skq_decode8<FMT>(srow, lo_off, 8 * g, f);
-        const float4 va = *reinterpret_cast<const float4*>(s_v + 4 * g);
-        const float4 vb = *reinterpret_cast<const float4*>(s_v + half + 4 * g);
-        rs0 += (f[0] * va.x + f[1] * va.y) + (f[2] * va.z + f[3] * va.w);
-        rs1 += (f[4] * vb.x + f[5] * vb.y) + (f[6] * vb.z + f[7] * vb.w);
-      }
-    }
-    const float rs = warp_sum(rs0 + rs1);
-    const float ui = ((i == c.R - 1) ? (float)c.R : 1.f) / (rs + SK_EPS);
-    if (lane_id() == 0) p.u[(long long)b * p.Rmax + i] = ui;
-    const float uis = ui * vscale;
-#pragma unroll
-    for (int k = 0; k < NV8; ++k) {
-      const int g = lane_id() + 32 * k;
-      if (8 * g < c.Cq) {
-        float f[8];
-        skq_decode8<FMT>(srow, lo_off, 8 * g, f);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) acc[k][q] = fmaf(f[q], uis, acc[k][q]);
-      }
-    }
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(&empty_bar[s]);  // the ring slot is free again
   }
+  const int rid = skq_rid<T>(lane);
 
-  // combine the CTA's warps in shared memory, then one global atomic per column
+  for (int n = 0; n < nbatch; ++n) {
+    const int slot = n % p.nslots;
+    const int nb = min(T, c.nrows - n * T);
+    const int i0 = c.row0 + n * T;
+    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
+    uint32_t raw[T][NVW][RAW];
+    float red[T];
 #pragma unroll
-  for (int k = 0; k < NV8; ++k) {
-    const int g = lane_id() + 32 * k;
-    if (8 * g < c.Cq) {
+    for (int t = 0; t < T; ++t) {
+      red[t] = 0.f;
+      if (t < nb) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        atomicAdd(s_col + 4 * g + q, acc[k][q]);
-        atomicAdd(s_col + half + 4 * g + q, acc[k][4 + q]);
+        for (int k = 0; k < NVW; ++k)
+          if (c0s[k] < c.Cq) skq_load8<FMT>(sb + (size_t)t * p.row_bytes, lo_off, c0s[k], raw[t][k]);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      if (t < nb) {
+        float r0 = 0.f, r1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < NVW; ++k)
+          if (c0s[k] < c.Cq) {
+            float f[8];
+            skq_decode8<FMT>(raw[t][k], f);
+            r0 += (f[0] * v[k][0] + f[1] * v[k][1]) + (f[2] * v[k][2] + f[3] * v[k][3]);
+            r1 += (f[4] * v[k][4] + f[5] * v[k][5]) + (f[6] * v[k][6] + f[7] * v[k][7]);
+          }
+        red[t] = r0 + r1;
+      }
+    }
+    float* part = s.part + (n & 1) * (T * SKQ_CW);
+    {
+      const float tot = skq_tr_reduce<T>(red, lane, [](float a, float b2) { return a + b2; });
+      skq_release(&s.empty_bar[slot], lane, tot);  // every lane's rows sit in registers (they fed tot)
+      if ((lane & (32 / T - 1)) == 0) part[rid * SKQ_CW + warp] = tot;
+    }
+    skq_consumer_sync();
+    float my_u = 0.f;
+    if (lane < T) {
+      const float4 a = *reinterpret_cast<const float4*>(part + lane * SKQ_CW);
+      const float4 d = *reinterpret_cast<const float4*>(part + lane * SKQ_CW + 4);
+      const float rs = ((a.x + a.y) + (a.z + a.w)) + ((d.x + d.y) + (d.z + d.w));
+      my_u = ((i0 + lane == c.R - 1) ? (float)c.R : 1.f) / (rs + SK_EPS);
+      if (warp == 0 && lane < nb) p.u[(long long)b * p.Rmax + i0 + lane] = my_u;
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const float uis = __shfl_sync(0xffffffffu, my_u, t) * vscale;
+      if (t < nb) {
+#pragma unroll
+        for (int k = 0; k < NVW; ++k)
+          if (c0s[k] < c.Cq) {
+            float f[8];
+            skq_decode8<FMT>(raw[t][k], f);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) acc[k][q] = fmaf(f[q], uis, acc[k][q]);
+          }
       }
     }
   }
-  skq_consumer_sync();
-  for (int j = ct; j < c.C; j += SKQ_CONSUMERS * 32) atomicAdd(p.col_acc + (long long)b * p.ldc + j, s_col[skq_perm(j, half)]);
+  // every column has exactly one owner lane in the CTA: straight to the global accumulators
+  float* ca = p.col_acc + (long long)b * p.ldc;
+#pragma unroll
+  for (int k = 0; k < NVW; ++k)
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      if (c0s[k] + q < c.C) atomicAdd(ca + c0s[k] + q, acc[k][q]);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
 // final: out = (p u) v with p re-derived in fp32 from dist and the row statistics; row arg-max / masses over the
-// non-dustbin block; scores written to P only when the caller wants the matrix
-template <int NV4>
+// non-dustbin block, column arg-max of the owned columns (packed atomicMax, lowest row wins ties); scores written to P
+// only when the caller wants the matrix
+struct SkqBest {
+  float v;
+  int j;
+  float m;
+};
+__device__ __forceinline__ SkqBest skq_best_merge(SkqBest a, SkqBest o) {
+  SkqBest r;
+  const bool take = o.v > a.v || (o.v == a.v && o.j < a.j);  // lowest column wins ties
+  r.v = take ? o.v : a.v;
+  r.j = take ? o.j : a.j;
+  r.m = a.m + o.m;
+  return r;
+}
+__device__ __forceinline__ SkqBest skq_best_shfl(SkqBest a, int h) {
+  SkqBest r;
+  r.v = __shfl_xor_sync(0xffffffffu, a.v, h);
+  r.j = __shfl_xor_sync(0xffffffffu, a.j, h);
+  r.m = __shfl_xor_sync(0xffffffffu, a.m, h);
+  return r;
+}
+template <int T>
+__device__ __forceinline__ SkqBest skq_tr_reduce_best(SkqBest (&a)[T], int lane) {
+  int h = 16;
+#pragma unroll
+  for (int n = T / 2; n >= 1; n >>= 1, h >>= 1) {
+    const bool up = (lane & h) != 0;
+#pragma unroll
+    for (int i = 0; i < n; ++i) {
+      const SkqBest send = up ? a[i] : a[i + n];
+      const SkqBest keep = up ? a[i + n] : a[i];
+      a[i] = skq_best_merge(keep, skq_best_shfl(send, h));
+    }
+  }
+  SkqBest r = a[0];
+  for (; h >= 1; h >>= 1) r = skq_best_merge(r, skq_best_shfl(r, h));
+  return r;
+}
+
+template <int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
+  constexpr int NG = 2 * NVW;
   SkqCta c;
   if (!skq_cta(p, c)) return;
-  const int S = p.ring_slots;
-  unsigned char* ring = skq_smem;
-  float* s_v = reinterpret_cast<float*>(ring + (size_t)S * p.slot_bytes);  // [ldq], plain layout, unscaled
-  float* s_col = s_v + p.ldq;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_col + p.ldq);
-  uint64_t* empty_bar = full_bar + S;
-  const int warp = threadIdx.x >> 5;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < S; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    fence_barrier_init();
-  }
-  __syncthreads();
-  if (warp == SKQ_CONSUMERS) {
-    skq_produce_dist(p, c, ring, full_bar, empty_bar);
+  const SkqSmem s = skq_smem_setup(skq_smem, p);
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+  if (warp == SKQ_CW) {
+    skq_produce_dist<T>(p, c, s);
     return;
   }
-  const int ct = threadIdx.x;
   const int b = c.b;
-  const int C4 = (c.C + 3) & ~3;
-  for (int c0 = 4 * ct; c0 < C4; c0 += 4 * SKQ_CONSUMERS * 32) {
-    float4 v = make_float4(c0 + 0 < c.C ? 1.f : 0.f, c0 + 1 < c.C ? 1.f : 0.f, c0 + 2 < c.C ? 1.f : 0.f, c0 + 3 < c.C ? 1.f : 0.f);
-    if (p.do_iter) v = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0, c.C);
-    *reinterpret_cast<float4*>(s_v + c0) = v;
-    *reinterpret_cast<float4*>(s_col + c0) = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  skq_consumer_sync();
-
   const float bin = *p.bin_score;
   const bool want_col = p.col_mass != nullptr;
-  float4 acc[NV4];
+  const int rid = skq_rid<T>(lane);
+  int c0s[NG];
+  float4 v[NG], acc[NG], cbv[NG];
+  int4 cbi[NG];
 #pragma unroll
-  for (int k = 0; k < NV4; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NG; ++k) {
+    c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
+    v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0s[k] < c.C) {
+      v[k] = make_float4(1.f, c0s[k] + 1 < c.C ? 1.f : 0.f, c0s[k] + 2 < c.C ? 1.f : 0.f, c0s[k] + 3 < c.C ? 1.f : 0.f);
+      if (p.do_iter) v[k] = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k], c.C);
+    }
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    cbv[k] = make_float4(-1.f, -1.f, -1.f, -1.f);
+    cbi[k] = make_int4(0, 0, 0, 0);
+  }
 
-  for (int r = warp; r < c.nrows; r += SKQ_CONSUMERS) {
-    const int s = r % S;
-    const int i = c.row0 + r;
-    const float ui = p.do_iter ? p.u[(long long)b * p.Rmax + i] : 1.f;
-    const float m = p.row_m[(long long)b * p.Rmax + i];
-    const float inv = p.row_inv[(long long)b * p.Rmax + i];
-    mbar_wait(&full_bar[s], (r / S) & 1);
-    const float* srow = reinterpret_cast<const float*>(ring + (size_t)s * p.slot_bytes);
-    const bool bin_row = (i == c.R - 1);
-    const bool inner_row = !bin_row;
-    float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
-    if (inner_row || p.write_scores) {
-      // four independent (value, column) trackers -- one per float4 component -- keep the compare/select chains short
-      float bv[4] = {-1.f, -1.f, -1.f, -1.f}, ms[4] = {0.f, 0.f, 0.f, 0.f};
-      int bj[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
+  const int nbatch = (c.nrows + T - 1) / T;
+  for (int n = 0; n < nbatch; ++n) {
+    const int slot = n % p.nslots;
+    const int nb = min(T, c.nrows - n * T);
+    const int i0 = c.row0 + n * T;
+    // per-row scalars: lane t fetches those of row t
+    float my_m = 0.f, my_inv = 0.f, my_u = 1.f;
+    if (lane < nb) {
+      const long long o = (long long)b * p.Rmax + i0 + lane;
+      my_m = p.row_m[o];
+      my_inv = p.row_inv[o];
+      if (p.do_iter) my_u = p.u[o];
+    }
+    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
+    float4 x[T][NG];
 #pragma unroll
-      for (int k = 0; k < NV4; ++k) {
-        const int c0 = 4 * (lane_id() + 32 * k);
-        if (c0 >= c.C) continue;
-        const float4 x = skq_logits(srow, c0, c.C, bin_row, bin);
-        const float4 v = *reinterpret_cast<const float4*>(s_v + c0);
-        const float o[4] = {__fmul_rn(__fmul_rn(skq_prob(x.x, m, inv), ui), v.x), __fmul_rn(__fmul_rn(skq_prob(x.y, m, inv), ui), v.y),
-                            __fmul_rn(__fmul_rn(skq_prob(x.z, m, inv), ui), v.z), __fmul_rn(__fmul_rn(skq_prob(x.w, m, inv), ui), v.w)};
-        if (p.write_scores) *reinterpret_cast<float4*>(prow + c0) = make_float4(o[0], o[1], o[2], o[3]);
-        if (inner_row) {
-          if (c0 + 3 < c.C - 1) {  // interior group: no column masking needed
+    for (int t = 0; t < T; ++t)
+      if (t < nb) {
+        const bool bin_row = (i0 + t == c.R - 1);
+        const float* srow = reinterpret_cast<const float*>(sb + (size_t)t * p.row_bytes);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              ms[q] += o[q];
-              if (o[q] > bv[q]) {
-                bv[q] = o[q];
-                bj[q] = c0 + q;
-              }
-            }
-          } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const bool in = c0 + q < c.C - 1;
-              const float oq = in ? o[q] : -1.f;  // columns grow with k, so a strict > keeps the lowest column per tracker
-              ms[q] += in ? o[q] : 0.f;
-              if (oq > bv[q]) {
-                bv[q] = oq;
-                bj[q] = c0 + q;
-              }
-            }
-          }
-          if (want_col) {
-            acc[k].x += o[0];
-            acc[k].y += o[1];
-            acc[k].z += o[2];
-            acc[k].w += o[3];
-          }
-        }
+        for (int k = 0; k < NG; ++k)
+          if (c0s[k] < c.C) x[t][k] = skq_logits(srow, c0s[k], c.C, bin_row, bin);
       }
-      if (inner_row) {
-        float best = bv[0], mass = (ms[0] + ms[1]) + (ms[2] + ms[3]);
-        int best_j = bj[0];
+
+    SkqBest rb[T];
 #pragma unroll
-        for (int q = 1; q < 4; ++q)
-          if (bv[q] > best || (bv[q] == best && bj[q] < best_j)) {
-            best = bv[q];
-            best_j = bj[q];
-          }
+    for (int t = 0; t < T; ++t) {
+      const float m = __shfl_sync(0xffffffffu, my_m, t);
+      const float inv = __shfl_sync(0xffffffffu, my_inv, t);
+      const float ui = __shfl_sync(0xffffffffu, my_u, t);
+      rb[t].v = -1.f;
+      rb[t].j = 0x7fffffff;
+      rb[t].m = 0.f;
+      if (t < nb) {
+        const int i = i0 + t;
+        const bool inner_row = i < c.R - 1;
+        float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {  // warp arg-max, lowest index wins ties
-          const float ob = __shfl_xor_sync(0xffffffffu, best, o);
-          const int oj = __shfl_xor_sync(0xffffffffu, best_j, o);
-          if (ob > best || (ob == best && oj < best_j)) {
-            best = ob;
-            best_j = oj;
+        for (int k = 0; k < NG; ++k) {
+          if (c0s[k] >= c.C) continue;
+          const float o[4] = {__fmul_rn(__fmul_rn(skq_prob(x[t][k].x, m, inv), ui), v[k].x),
+                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].y, m, inv), ui), v[k].y),
+                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].z, m, inv), ui), v[k].z),
+                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].w, m, inv), ui), v[k].w)};
+          if (p.write_scores) *reinterpret_cast<float4*>(prow + c0s[k]) = make_float4(o[0], o[1], o[2], o[3]);
+          if (inner_row) {
+            // column trackers: rows ascend, so a strict > keeps the lowest row (the dustbin column is never flushed)
+            if (o[0] > cbv[k].x) { cbv[k].x = o[0]; cbi[k].x = i; }
+            if (o[1] > cbv[k].y) { cbv[k].y = o[1]; cbi[k].y = i; }
+            if (o[2] > cbv[k].z) { cbv[k].z = o[2]; cbi[k].z = i; }
+            if (o[3] > cbv[k].w) { cbv[k].w = o[3]; cbi[k].w = i; }
+            if (want_col) {
+              acc[k].x += o[0];
+              acc[k].y += o[1];
+              acc[k].z += o[2];
+              acc[k].w += o[3];
+            }
+            // row tracker over the non-dustbin columns: columns ascend with q and k, strict > keeps the lowest
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const bool in = c0s[k] + q < c.C - 1;
+              const float oq = in ? o[q] : -1.f;
+              rb[t].m += in ? o[q] : 0.f;
+              if (oq > rb[t].v) {
+                rb[t].v = oq;
+                rb[t].j = c0s[k] + q;
+              }
+            }
           }
-        }
-        mass = warp_sum(mass);
-        if (lane_id() == 0) {
-          p.row_max[(long long)b * p.N0max + i] = best;
-          p.row_arg[(long long)b * p.N0max + i] = best_j;
-          if (p.row_mass) p.row_mass[(long long)b * p.N0max + i] = mass;
         }
       }
     }
-    __syncwarp();
-    if (lane_id() == 0) mbar_arrive(&empty_bar[s]);
-  }
-
-  if (want_col) {
-#pragma unroll
-    for (int k = 0; k < NV4; ++k) {
-      const int c0 = 4 * (lane_id() + 32 * k);
-      if (c0 < c.C) {
-        atomicAdd(s_col + c0 + 0, acc[k].x);
-        atomicAdd(s_col + c0 + 1, acc[k].y);
-        atomicAdd(s_col + c0 + 2, acc[k].z);
-        atomicAdd(s_col + c0 + 3, acc[k].w);
+    // rows: warp-level transposed reduction, then one (value, column, mass) triple per warp and row through smem
+    float* part = s.part + (n & 1) * (3 * T * SKQ_CW);
+    {
+      const SkqBest r = skq_tr_reduce_best<T>(rb, lane);
+      skq_release(&s.empty_bar[slot], lane, r.m);  // every lane's logits sit in registers (they fed the row masses)
+      if ((lane & (32 / T - 1)) == 0) {
+        part[rid * SKQ_CW + warp] = r.v;
+        part[T * SKQ_CW + rid * SKQ_CW + warp] = __int_as_float(r.j);
+        part[2 * T * SKQ_CW + rid * SKQ_CW + warp] = r.m;
       }
     }
     skq_consumer_sync();
-    for (int j = ct; j < c.C - 1; j += SKQ_CONSUMERS * 32) atomicAdd(p.col_mass + (long long)b * p.N1max + j, s_col[j]);
-  }
-}
-
-// column arg-max over the non-dustbin block, scores re-derived from dist exactly like the final pass does:
-// thread per column (coalesced), row slabs, packed atomicMax (lowest row wins ties)
-__global__ void __launch_bounds__(128)
-skq_colmax_kernel(const float* __restrict__ dist, long long dist_bs, int ldd, const float* __restrict__ row_m,
-                  const float* __restrict__ row_inv, const float* __restrict__ u, const float* __restrict__ col_last, int ldc,
-                  int has_iter, unsigned long long* __restrict__ col_key, const int* __restrict__ n0s,
-                  const int* __restrict__ n1s, int N0max, int N1max, int slab, int reverse) {
-  const int b = reverse ? (int)(gridDim.z - 1 - blockIdx.z) : (int)blockIdx.z;
-  const int by = reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
-  const SkDims d = sk_dims(n0s, n1s, b, N0max, N1max);
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  const int i0 = by * slab;
-  if (j >= d.C - 1 || i0 >= d.R - 1) return;
-  const int i1 = min(i0 + slab, d.R - 1);
-  const float vj = has_iter ? 1.f / (col_last[(long long)b * ldc + j] + SK_EPS) : 1.f;  // c_j = 1 for j < C-1
-  const float* base = dist + b * dist_bs + j;
-  const long long rb = (long long)b * (N0max + 1);
-  float best = -1.f;
-  int bi = 0;
-#pragma unroll 4
-  for (int i = i0; i < i1; ++i) {
-    const float pr = skq_prob(base[(long long)i * ldd], row_m[rb + i], row_inv[rb + i]);
-    const float val = __fmul_rn(__fmul_rn(pr, has_iter ? u[rb + i] : 1.f), vj);
-    if (val > best) {
-      best = val;
-      bi = i;
+    if (warp == 0 && lane < nb && i0 + lane < c.R - 1) {
+      SkqBest r;
+      r.v = -1.f;
+      r.j = 0x7fffffff;
+      r.m = 0.f;
+#pragma unroll
+      for (int w = 0; w < SKQ_CW; ++w) {
+        SkqBest o;
+        o.v = part[lane * SKQ_CW + w];
+        o.j = __float_as_int(part[T * SKQ_CW + lane * SKQ_CW + w]);
+        o.m = part[2 * T * SKQ_CW + lane * SKQ_CW + w];
+        r = skq_best_merge(r, o);
+      }
+      const long long o = (long long)b * p.N0max + i0 + lane;
+      p.row_max[o] = r.v;
+      p.row_arg[o] = r.j;
+      if (p.row_mass) p.row_mass[o] = r.m;
     }
   }
-  atomicMax(col_key + (long long)b * N1max + j, pack_max_key(best, bi));
+
+  unsigned long long* ck = p.col_key + (long long)b * p.N1max;
+#pragma unroll
+  for (int k = 0; k < NG; ++k) {
+    const float bv[4] = {cbv[k].x, cbv[k].y, cbv[k].z, cbv[k].w};
+    const int bi[4] = {cbi[k].x, cbi[k].y, cbi[k].z, cbi[k].w};
+    const float am[4] = {acc[k].x, acc[k].y, acc[k].z, acc[k].w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int j = c0s[k] + q;
+      if (j < c.C - 1 && bv[q] >= 0.f) {
+        atomicMax(ck + j, pack_max_key(bv[q], bi[q]));
+        if (want_col) atomicAdd(p.col_mass + (long long)b * p.N1max + j, am[q]);
+      }
+    }
+  }
 }
 
-template <int NV8, int FMT>
+// ---------------------------------------------------------------------------------------------------------------
+template <int FMT, int NVW, int T_ITER>
 static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
-  constexpr int NV4 = 2 * NV8;
+  constexpr int T_DIST = 4;
+  constexpr int BPE = QFmt<FMT>::BPE;
   const int R = a.N0max + 1, C = a.N1max + 1;
   const int ldq = (C + 15) & ~15;
-  const size_t q_row = (size_t)ldq * (FMT == QF16 ? 2 : 3);
-  const size_t d_row = (size_t)((C + 3) & ~3) * 4;  // the padded row (C columns) is materialised in the slot
-  const size_t fixed = 2 * (size_t)ldq * sizeof(float) + 2 * 64 * sizeof(uint64_t);
+  const size_t q_row = (size_t)ldq * BPE;
+  const size_t d_row = (size_t)((C + 3) & ~3) * 4;  // the padded row (C columns) of the dist passes
   IMP_REQUIRE(a.q_batch_stride % 16 == 0 && (size_t)a.q_batch_stride >= (size_t)R * q_row &&
                   (reinterpret_cast<uintptr_t>(a.q_store) & 15) == 0,
               "sinkhorn: q_store needs %zu bytes per matrix (16-byte aligned), got %lld", (size_t)R * q_row,
@@ -599,9 +746,9 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
       if (e != cudaSuccess) return e;
       return cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
     };
-    IMP_CUDA_OK(conf((const void*)skq_init_kernel<NV4, FMT>));
-    IMP_CUDA_OK(conf((const void*)skq_iter_kernel<NV8, FMT>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NV4>));
+    IMP_CUDA_OK(conf((const void*)skq_init_kernel<FMT, NVW, T_DIST>));
+    IMP_CUDA_OK(conf((const void*)skq_iter_kernel<FMT, NVW, T_ITER>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST>));
     configured = true;
   }
   SkqParams p;
@@ -611,64 +758,54 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   p.row_m = a.row_stats; p.row_inv = a.row_stats + (size_t)a.batch * R;
   p.u = a.u; p.ldc = a.ldp;
   p.row_max = a.row_max; p.row_arg = a.row_arg; p.row_mass = a.row_mass; p.col_mass = a.col_mass;
+  p.col_key = reinterpret_cast<unsigned long long*>(a.col_key);
   p.n0s = a.n0s; p.n1s = a.n1s; p.N0max = a.N0max; p.N1max = a.N1max;
   p.write_scores = a.write_scores;
   const int iters = a.iters;
   p.do_iter = iters > 0 ? 1 : 0;
-  const int rows_per_cta = sk_rows_per_cta(R, a.batch, num_sms(), SKQ_CONSUMERS);
+  // rows per CTA: a multiple of both batch heights that fills whole waves of 2 CTAs/SM best
+  const int rows_per_cta = sk_rows_per_cta(R, a.batch, num_sms(), 8);
   p.rows_per_cta = rows_per_cta;
-  auto slots_for = [&](size_t row_bytes) {
-    int s = (int)((SKQ_SMEM_BUDGET - fixed) / row_bytes);
-    if (s > 64) s = 64;
-    if (s > rows_per_cta) s = rows_per_cta;
-    // slot s must always be drained by the same consumer warp (row r -> warp r % CONSUMERS, slot r % slots)
-    return s / SKQ_CONSUMERS * SKQ_CONSUMERS;
+  auto slots_for = [&](size_t slot_bytes) {
+    int s = (int)((SKQ_SMEM_BUDGET - SKQ_FIXED_SMEM) / slot_bytes);
+    return s > 4 ? 4 : s;
   };
-  const int slots_d = slots_for(d_row), slots_q = slots_for(q_row);
-  IMP_REQUIRE(slots_d >= SKQ_CONSUMERS && slots_q >= SKQ_CONSUMERS,
-              "sinkhorn: a row of %d columns does not fit the shared-memory ring", C);
+  const int slots_d = slots_for(T_DIST * d_row), slots_q = slots_for(T_ITER * q_row);
+  IMP_REQUIRE(slots_d >= 2 && slots_q >= 2, "sinkhorn: a row of %d columns does not fit the shared-memory ring", C);
   dim3 grid((R + rows_per_cta - 1) / rows_per_cta, a.batch);
   float* col[3] = {a.colbuf, a.colbuf + (size_t)a.batch * a.ldp, a.colbuf + 2 * (size_t)a.batch * a.ldp};
 
-  p.ring_slots = slots_d;
-  p.slot_bytes = (int)d_row;
+  p.nslots = slots_d;
+  p.row_bytes = (int)d_row;
+  p.slot_bytes = (int)(T_DIST * d_row);
   p.col_prev = nullptr;
   p.col_acc = col[0];
   p.col_zero = col[1];
   p.reverse = 0;
-  skq_init_kernel<NV4, FMT><<<grid, SKQ_THREADS, slots_d * d_row + fixed, st>>>(p);
+  skq_init_kernel<FMT, NVW, T_DIST><<<grid, SKQ_THREADS, (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
 
   const bool prof = sk_profiling_on() && iters > 1;
   if (prof) sk_profile_begin(st);
-  p.ring_slots = slots_q;
-  p.slot_bytes = (int)q_row;
+  p.nslots = slots_q;
+  p.row_bytes = (int)q_row;
+  p.slot_bytes = (int)(T_ITER * q_row);
   for (int k = 1; k < iters; ++k) {
     p.col_prev = col[(k - 1) % 3];
     p.col_acc = col[k % 3];
     p.col_zero = col[(k + 1) % 3];
     p.reverse = k & 1;
-    skq_iter_kernel<NV8, FMT><<<grid, SKQ_THREADS, slots_q * q_row + fixed, st>>>(p);
+    skq_iter_kernel<FMT, NVW, T_ITER><<<grid, SKQ_THREADS, (size_t)slots_q * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
   }
   if (prof) sk_profile_end(st, iters - 1);
 
-  const float* col_last = col[(iters > 0 ? iters - 1 : 0) % 3];
-  p.ring_slots = slots_d;
-  p.slot_bytes = (int)d_row;
-  p.col_prev = col_last;
+  p.nslots = slots_d;
+  p.row_bytes = (int)d_row;
+  p.slot_bytes = (int)(T_DIST * d_row);
+  p.col_prev = col[(iters > 0 ? iters - 1 : 0) % 3];
   p.col_acc = nullptr;
   p.col_zero = nullptr;
   p.reverse = 0;
-  skq_final_kernel<NV4><<<grid, SKQ_THREADS, slots_d * d_row + fixed, st>>>(p);
-  if (a.write_scores) {
-    if (int rc = launch_sk_colmax_scaled(a.P, a.p_batch_stride, a.ldp, reinterpret_cast<unsigned long long*>(a.col_key), a.n0s,
-                                         a.n1s, a.N0max, a.N1max, a.batch, st))
-      return rc;
-  } else {
-    const int slab = 256;
-    skq_colmax_kernel<<<dim3((a.N1max + 127) / 128, (a.N0max + slab - 1) / slab, a.batch), 128, 0, st>>>(
-        a.dist, a.dist_batch_stride, a.ldd, p.row_m, p.row_inv, a.u, col_last, a.ldp, iters > 0 ? 1 : 0,
-        reinterpret_cast<unsigned long long*>(a.col_key), a.n0s, a.n1s, a.N0max, a.N1max, slab, 1);
-  }
+  skq_final_kernel<NVW, T_DIST><<<grid, SKQ_THREADS, (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -676,15 +813,14 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
 template <int FMT>
 static int dispatch_nv(const SinkhornArgs& a, cudaStream_t st) {
   const int C = a.N1max + 1;
-  if (C <= 256 * 2) return run_compact<2, FMT>(a, st);
-  if (C <= 256 * 4) return run_compact<4, FMT>(a, st);
-  if (C <= 256 * 8) return run_compact<8, FMT>(a, st);
-  if (C <= 256 * 13) return run_compact<13, FMT>(a, st);
-  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 256 * 13 - 1);
+  if (C <= 2048) return run_compact<FMT, 1, (FMT == QF32 ? 4 : 8)>(a, st);
+  if (C <= 4096) return run_compact<FMT, 2, 4>(a, st);
+  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4095);
   return 2;
 }
 
 int run_sinkhorn_compact(const SinkhornArgs& a, cudaStream_t st) {
+  if (a.storage == IMP_SK_STORE_F32) return dispatch_nv<QF32>(a, st);
   if (a.storage == IMP_SK_STORE_F16) return dispatch_nv<QF16>(a, st);
   if (a.storage == IMP_SK_STORE_F24) return dispatch_nv<QF24>(a, st);
   set_error("sinkhorn: unknown storage format %d", a.storage);

@@ -223,7 +223,8 @@ class SinkhornWorkspace:
         self.col_mass = torch.zeros(batch, N1max, **f32) if want_mass else None
         self.q_store = self.row_stats = None
         self.q_batch_stride = 0
-        if self.storage != 0 and N1max + 1 >= 64 and not _sk_resident_fits(batch, N0max + 1, self.ldp, device):
+        legacy = os.environ.get('IMP_SK_LEGACY', '0') == '1'      # row-ring fp32 kernels of csrc/sinkhorn.cu
+        if not legacy and 64 <= N1max + 1 <= 4096 and not _sk_resident_fits(batch, N0max + 1, self.ldp, device):
             ldq = (N1max + 1 + 15) // 16 * 16
             self.q_batch_stride = (N0max + 1) * ldq * SK_STORAGE_BYTES[self.storage]
             self.q_store = torch.empty(batch, self.q_batch_stride, dtype=torch.uint8, device=device)
