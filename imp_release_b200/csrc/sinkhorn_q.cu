@@ -63,7 +63,7 @@ struct SkqParams {
   unsigned long long* col_key;
   const int *n0s, *n1s;
   int N0max, N1max;
-  int rows_per_cta, nslots, slot_bytes, row_bytes;
+  int rows_per_cta, blocks_per_mat, n_items, nslots, slot_bytes, row_bytes;
   int do_iter, write_scores, reverse;
 };
 
@@ -174,11 +174,12 @@ __device__ __forceinline__ void skq_decode8(const uint32_t (&r)[QFmt<FMT>::RAW],
 // in the 32/T lanes that share that row id).  9 shuffles for T = 8 instead of 40.
 template <int T>
 __device__ __forceinline__ int skq_rid(int lane) {
-  return T == 8 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1)) : (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1));
+  return T == 8 ? (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1))
+                : (T == 4 ? (((lane >> 4) & 1) * 2 + ((lane >> 3) & 1)) : ((lane >> 4) & 1));
 }
 template <int T, typename Op>
 __device__ __forceinline__ float skq_tr_reduce(float (&a)[T], int lane, Op op) {
-  static_assert(T == 4 || T == 8, "T must be 4 or 8");
+  static_assert(T == 2 || T == 4 || T == 8, "T must be 2, 4 or 8");
   int h = 16;
 #pragma unroll
   for (int n = T / 2; n >= 1; n >>= 1, h >>= 1) {
@@ -195,12 +196,15 @@ __device__ __forceinline__ float skq_tr_reduce(float (&a)[T], int lane, Op op) {
   return r;
 }
 
+// Work item = one block of rows_per_cta rows of one matrix.  The kernels are persistent: CTA k walks items k, k + grid,
+// k + 2 grid, ... with one running batch counter, so the bulk-copy ring keeps streaming across item boundaries.
 struct SkqCta {
   int b, row0, nrows, R, C, Cq;
 };
-__device__ __forceinline__ bool skq_cta(const SkqParams& p, SkqCta& c) {
-  const int bx = p.reverse ? (int)(gridDim.x - 1 - blockIdx.x) : (int)blockIdx.x;
-  c.b = p.reverse ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+__device__ __forceinline__ bool skq_item(const SkqParams& p, int item, SkqCta& c) {
+  if (p.reverse) item = p.n_items - 1 - item;
+  c.b = item / p.blocks_per_mat;
+  const int bx = item - c.b * p.blocks_per_mat;
   const SkDims d = sk_dims(p.n0s, p.n1s, c.b, p.N0max, p.N1max);
   c.R = d.R;
   c.C = d.C;
@@ -235,27 +239,32 @@ __device__ __forceinline__ SkqSmem skq_smem_setup(unsigned char* base, const Skq
 
 // producer warp for the passes that stream dist rows (init, final): T rows per slot
 template <int T>
-__device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqCta& c, const SkqSmem& s) {
+__device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqSmem& s) {
   if (lane_id() != 0) return;
-  const float* src = p.dist + c.b * p.dist_bs;
-  const uint32_t bytes = (uint32_t)(((c.C - 1 + 3) & ~3) * 4);
-  const int nbatch = (c.nrows + T - 1) / T;
-  for (int n = 0; n < nbatch; ++n) {
-    const int slot = n % p.nslots;
-    mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
-    const int i0 = c.row0 + n * T;
-    const int nb = min(T, c.nrows - n * T);
-    int ncopy = 0;
-    for (int t = 0; t < nb; ++t) ncopy += (i0 + t != c.R - 1 && bytes != 0) ? 1 : 0;  // the dustbin row has no source
-    if (ncopy == 0) {
-      mbar_arrive(&s.full_bar[slot]);
-      continue;
+  int n = 0;  // running batch counter of this CTA (slot = n % nslots)
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    SkqCta c;
+    if (!skq_item(p, item, c)) continue;
+    const float* src = p.dist + c.b * p.dist_bs;
+    const uint32_t bytes = (uint32_t)(((c.C - 1 + 3) & ~3) * 4);
+    const int nbatch = (c.nrows + T - 1) / T;
+    for (int j = 0; j < nbatch; ++j, ++n) {
+      const int slot = n % p.nslots;
+      mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+      const int i0 = c.row0 + j * T;
+      const int nb = min(T, c.nrows - j * T);
+      int ncopy = 0;
+      for (int t = 0; t < nb; ++t) ncopy += (i0 + t != c.R - 1 && bytes != 0) ? 1 : 0;  // the dustbin row has no source
+      if (ncopy == 0) {
+        mbar_arrive(&s.full_bar[slot]);
+        continue;
+      }
+      mbar_arrive_expect_tx(&s.full_bar[slot], bytes * ncopy);
+      unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
+      for (int t = 0; t < nb; ++t)
+        if (i0 + t != c.R - 1 && bytes != 0)
+          bulk_copy_g2s(dst + (size_t)t * p.row_bytes, src + (long long)(i0 + t) * p.ldd, bytes, &s.full_bar[slot]);
     }
-    mbar_arrive_expect_tx(&s.full_bar[slot], bytes * ncopy);
-    unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
-    for (int t = 0; t < nb; ++t)
-      if (i0 + t != c.R - 1 && bytes != 0)
-        bulk_copy_g2s(dst + (size_t)t * p.row_bytes, src + (long long)(i0 + t) * p.ldd, bytes, &s.full_bar[slot]);
   }
 }
 
@@ -266,17 +275,12 @@ template <int FMT, int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
   constexpr int NG = 2 * NVW;
-  SkqCta c;
-  if (!skq_cta(p, c)) return;
   const SkqSmem s = skq_smem_setup(skq_smem, p);
   const int warp = threadIdx.x >> 5, lane = lane_id();
   if (warp == SKQ_CW) {
-    skq_produce_dist<T>(p, c, s);
+    skq_produce_dist<T>(p, s);
     return;
   }
-  const int b = c.b;
-  if (c.row0 == 0 && p.col_zero != nullptr)
-    for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
   float* s_max = s.part;              // [T][CW]
   float* s_sum = s.part + T * SKQ_CW; // [T][CW]
   const float bin = *p.bin_score;
@@ -284,15 +288,22 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
   int c0s[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
+  int n = 0;  // running batch counter (matches the producer's)
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+  SkqCta c;
+  if (!skq_item(p, item, c)) continue;
+  const int b = c.b;
+  if (c.row0 == 0 && p.col_zero != nullptr)
+    for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
   float4 acc[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   const int nbatch = (c.nrows + T - 1) / T;
-  for (int n = 0; n < nbatch; ++n) {
+  for (int jb = 0; jb < nbatch; ++jb, ++n) {
     const int slot = n % p.nslots;
-    const int nb = min(T, c.nrows - n * T);
-    const int i0 = c.row0 + n * T;
+    const int nb = min(T, c.nrows - jb * T);
+    const int i0 = c.row0 + jb * T;
     mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
     const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
     // pass 1: padded logits into registers, per-row max
@@ -399,6 +410,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
       if (c0s[k] + 3 < c.C) atomicAdd(ca + c0s[k] + 3, acc[k].w);
     }
   }
+  }  // items
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -408,46 +420,56 @@ template <int FMT, int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
   constexpr int RAW = QFmt<FMT>::RAW;
-  SkqCta c;
-  if (!skq_cta(p, c)) return;
   const SkqSmem s = skq_smem_setup(skq_smem, p);
   const int warp = threadIdx.x >> 5, lane = lane_id();
-  const int b = c.b;
   const int lo_off = p.ldq * 2;
-  const int nbatch = (c.nrows + T - 1) / T;
 
   if (warp == SKQ_CW) {
     if (lane == 0) {
-      const unsigned char* q0 = p.Q + b * p.q_bs;
-      const unsigned char* qlo = q0 + (size_t)p.Rmax * p.ldq * 2;
-      const uint32_t main_bytes = (uint32_t)c.Cq * (FMT == QF24 ? 2 : QFmt<FMT>::BPE), lo_bytes = (uint32_t)c.Cq;
-      const size_t main_stride = (size_t)p.ldq * (FMT == QF24 ? 2 : QFmt<FMT>::BPE);
-      for (int n = 0; n < nbatch; ++n) {
-        const int slot = n % p.nslots;
-        mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
-        const int i0 = c.row0 + n * T;
-        const int nb = min(T, c.nrows - n * T);
-        mbar_arrive_expect_tx(&s.full_bar[slot], (FMT == QF24 ? main_bytes + lo_bytes : main_bytes) * nb);
-        unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
-        for (int t = 0; t < nb; ++t) {
-          bulk_copy_g2s(dst + (size_t)t * p.row_bytes, q0 + (size_t)(i0 + t) * main_stride, main_bytes, &s.full_bar[slot]);
-          if (FMT == QF24)
-            bulk_copy_g2s(dst + (size_t)t * p.row_bytes + lo_off, qlo + (size_t)(i0 + t) * p.ldq, lo_bytes, &s.full_bar[slot]);
+      const uint32_t bpe_main = FMT == QF24 ? 2 : QFmt<FMT>::BPE;
+      const size_t main_stride = (size_t)p.ldq * bpe_main;
+      int n = 0;  // running batch counter of this CTA (slot = n % nslots)
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        SkqCta c;
+        if (!skq_item(p, item, c)) continue;
+        const unsigned char* q0 = p.Q + c.b * p.q_bs;
+        const unsigned char* qlo = q0 + (size_t)p.Rmax * p.ldq * 2;
+        const uint32_t main_bytes = (uint32_t)c.Cq * bpe_main, lo_bytes = (uint32_t)c.Cq;
+        const int nbatch = (c.nrows + T - 1) / T;
+        for (int jb = 0; jb < nbatch; ++jb, ++n) {
+          const int slot = n % p.nslots;
+          mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+          const int i0 = c.row0 + jb * T;
+          const int nb = min(T, c.nrows - jb * T);
+          mbar_arrive_expect_tx(&s.full_bar[slot], (FMT == QF24 ? main_bytes + lo_bytes : main_bytes) * nb);
+          unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
+          for (int t = 0; t < nb; ++t) {
+            bulk_copy_g2s(dst + (size_t)t * p.row_bytes, q0 + (size_t)(i0 + t) * main_stride, main_bytes, &s.full_bar[slot]);
+            if (FMT == QF24)
+              bulk_copy_g2s(dst + (size_t)t * p.row_bytes + lo_off, qlo + (size_t)(i0 + t) * p.ldq, lo_bytes, &s.full_bar[slot]);
+          }
         }
       }
     }
     return;
   }
 
+  const float vscale = (FMT == QF16) ? SKQ_F16_INV : 1.f;
+  const int rid = skq_rid<T>(lane);
+  int c0s[NVW];
+#pragma unroll
+  for (int k = 0; k < NVW; ++k) c0s[k] = 8 * ((warp * NVW + k) * 32 + lane);
+  int n = 0;  // running batch counter (matches the producer's)
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+  SkqCta c;
+  if (!skq_item(p, item, c)) continue;
+  const int b = c.b;
   if (c.row0 == 0 && p.col_zero != nullptr)
     for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
   // v_j of the owned columns (pre-scaled for the fp16 copy) and their column-sum accumulators
-  const float vscale = (FMT == QF16) ? SKQ_F16_INV : 1.f;
-  int c0s[NVW];
   float v[NVW][8], acc[NVW][8];
 #pragma unroll
   for (int k = 0; k < NVW; ++k) {
-    c0s[k] = 8 * ((warp * NVW + k) * 32 + lane);
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
     if (c0s[k] < c.C) va = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k], c.C);  // C <= ldc, both multiples of 4 apart
     if (c0s[k] + 4 < c.C) vb = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k] + 4, c.C);
@@ -456,12 +478,12 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[k][q] = 0.f;
   }
-  const int rid = skq_rid<T>(lane);
 
-  for (int n = 0; n < nbatch; ++n) {
+  const int nbatch = (c.nrows + T - 1) / T;
+  for (int jb = 0; jb < nbatch; ++jb, ++n) {
     const int slot = n % p.nslots;
-    const int nb = min(T, c.nrows - n * T);
-    const int i0 = c.row0 + n * T;
+    const int nb = min(T, c.nrows - jb * T);
+    const int i0 = c.row0 + jb * T;
     mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
     const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
     uint32_t raw[T][NVW][RAW];
@@ -527,6 +549,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
 #pragma unroll
     for (int q = 0; q < 8; ++q)
       if (c0s[k] + q < c.C) atomicAdd(ca + c0s[k] + q, acc[k][q]);
+  }  // items
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -575,24 +598,27 @@ template <int NVW, int T>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
   constexpr int NG = 2 * NVW;
-  SkqCta c;
-  if (!skq_cta(p, c)) return;
   const SkqSmem s = skq_smem_setup(skq_smem, p);
   const int warp = threadIdx.x >> 5, lane = lane_id();
   if (warp == SKQ_CW) {
-    skq_produce_dist<T>(p, c, s);
+    skq_produce_dist<T>(p, s);
     return;
   }
-  const int b = c.b;
   const float bin = *p.bin_score;
   const bool want_col = p.col_mass != nullptr;
   const int rid = skq_rid<T>(lane);
   int c0s[NG];
+#pragma unroll
+  for (int k = 0; k < NG; ++k) c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
+  int n = 0;  // running batch counter (matches the producer's)
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+  SkqCta c;
+  if (!skq_item(p, item, c)) continue;
+  const int b = c.b;
   float4 v[NG], acc[NG], cbv[NG];
   int4 cbi[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
-    c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
     v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c0s[k] < c.C) {
       v[k] = make_float4(1.f, c0s[k] + 1 < c.C ? 1.f : 0.f, c0s[k] + 2 < c.C ? 1.f : 0.f, c0s[k] + 3 < c.C ? 1.f : 0.f);
@@ -604,10 +630,10 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
   }
 
   const int nbatch = (c.nrows + T - 1) / T;
-  for (int n = 0; n < nbatch; ++n) {
+  for (int jb = 0; jb < nbatch; ++jb, ++n) {
     const int slot = n % p.nslots;
-    const int nb = min(T, c.nrows - n * T);
-    const int i0 = c.row0 + n * T;
+    const int nb = min(T, c.nrows - jb * T);
+    const int i0 = c.row0 + jb * T;
     // per-row scalars: lane t fetches those of row t
     float my_m = 0.f, my_inv = 0.f, my_u = 1.f;
     if (lane < nb) {
@@ -724,6 +750,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
       }
     }
   }
+  }  // items
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -763,16 +790,20 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   p.write_scores = a.write_scores;
   const int iters = a.iters;
   p.do_iter = iters > 0 ? 1 : 0;
-  // rows per CTA: a multiple of both batch heights that fills whole waves of 2 CTAs/SM best
+  // persistent grid: two CTAs per SM; rows per work item = the multiple of 8 whose item count fills whole rounds of the
+  // grid best
+  const int ctas = 2 * num_sms();
   const int rows_per_cta = sk_rows_per_cta(R, a.batch, num_sms(), 8);
   p.rows_per_cta = rows_per_cta;
+  p.blocks_per_mat = (R + rows_per_cta - 1) / rows_per_cta;
+  p.n_items = p.blocks_per_mat * a.batch;
   auto slots_for = [&](size_t slot_bytes) {
     int s = (int)((SKQ_SMEM_BUDGET - SKQ_FIXED_SMEM) / slot_bytes);
     return s > 4 ? 4 : s;
   };
   const int slots_d = slots_for(T_DIST * d_row), slots_q = slots_for(T_ITER * q_row);
   IMP_REQUIRE(slots_d >= 2 && slots_q >= 2, "sinkhorn: a row of %d columns does not fit the shared-memory ring", C);
-  dim3 grid((R + rows_per_cta - 1) / rows_per_cta, a.batch);
+  dim3 grid(p.n_items < ctas ? p.n_items : ctas);
   float* col[3] = {a.colbuf, a.colbuf + (size_t)a.batch * a.ldp, a.colbuf + 2 * (size_t)a.batch * a.ldp};
 
   p.nslots = slots_d;

@@ -29,7 +29,8 @@ for rep in sorted(f for f in os.listdir('gpurun_out') if f.startswith(tag + '_')
             if w in idx: out.append(f'| {w} | {r[idx[w]]} | {units[idx[w]]} |\n')
         tb = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
         out.append(f'| **dram traffic (read+write)** | {tb/1e6:.1f} | MB |\n')
-        key = 'attention' if 'attention_kernel' in name else ('sinkhorn' if 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
+        fmt = {'0': 'fp32', '1': 'fp16', '2': 'fp24'}
+        key = 'attention' if 'attention_kernel' in name else (('sinkhorn_' + fmt.get(r[idx['Kernel Name']].split('<')[1][:1] if '<' in r[idx['Kernel Name']] else '', 'fp32')) if 'skq_iter' in name or 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
         traffic.setdefault(key, []).append(tb)
     src = subprocess.run(['ncu', '-i', os.path.join('gpurun_out', rep), '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     p = subprocess.run([sys.executable, 'tools/ncu_src.py', '0', '12'], input=src, capture_output=True, text=True).stdout
@@ -51,5 +52,7 @@ if os.path.isfile(lp):
         out.append(f'| `{k}` | {v[0]} | {v[1]:.3f} | {v[1]/tot:.3f} |\n')
 open(f'profiles/{tag}_ncu_summary.md', 'w').write(''.join(out))
 # per-launch DRAM traffic for bench.py's roofline.traffic (sinkhorn: one sweep kernel; bench multiplies nothing)
-json.dump({k: sum(v) / len(v) for k, v in traffic.items()}, open('profiles/traffic.json', 'w'), indent=1)
+old = json.load(open('profiles/traffic.json')) if os.path.isfile('profiles/traffic.json') else {}
+old.update({k: sum(v) / len(v) for k, v in traffic.items()})
+json.dump(old, open('profiles/traffic.json', 'w'), indent=1)
 print(''.join(out)[:6000])
