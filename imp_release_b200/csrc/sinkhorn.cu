@@ -714,7 +714,7 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     p.N0max = a.N0max;
     p.N1max = a.N1max;
     p.write_scores = a.write_scores;
-    const int rows_per_cta = sk_rows_per_cta(R, nb, num_sms(), SKR_CONSUMERS);
+    const int rows_per_cta = sk_rows_per_cta(R, nb, 2 * num_sms(), SKR_CONSUMERS);
     p.rows_per_cta = rows_per_cta;
     int slots = (int)((SKR_SMEM_BUDGET - fixed) / row_bytes);
     if (slots > 64) slots = 64;

@@ -57,10 +57,10 @@ __device__ __forceinline__ unsigned long long pack_max_key(float val, int idx) {
 }
 
 // wave-aware block height shared by both streaming paths: rows per CTA (multiple of `step`, 8..128) whose CTA count
-// fills whole waves of 2 CTAs/SM best -- e.g. 64 x 2001 rows: 128-row blocks give 1024 CTAs = 3.46 waves, 88-row blocks
+// fills whole waves of `wave_ctas` resident CTAs best -- e.g. 64 x 2001 rows: 128-row blocks give 1024 CTAs = 3.46 waves, 88-row blocks
 // 1472 CTAs = 4.97 waves.  Larger blocks win ties (fewer column-sum flushes).
-inline int sk_rows_per_cta(int R, int nb, int sms, int step) {
-  const long long wave = 2LL * sms;
+inline int sk_rows_per_cta(int R, int nb, int wave_ctas, int step) {
+  const long long wave = wave_ctas;
   int rows_per_cta = 8;
   double best = -1.0;
   for (int r = 128; r >= 8; r -= step) {

@@ -19,6 +19,8 @@
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.h"
 #include "sinkhorn_common.cuh"
 
@@ -67,6 +69,26 @@ struct SkqParams {
   int do_iter, write_scores, reverse;
 };
 
+// mbarrier wait whose polls are suspended in hardware for up to ~20 us at a time: the plain try_wait loop of ptx.cuh
+// re-polls every few hundred cycles, and in these memory-bound kernels the polls of the waiting warps were 14 % of all
+// issued instructions (ncu), competing with the warps that have work
+__device__ __forceinline__ void skq_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, 20000;\n\t"
+      "@!P bra WAIT_%=;\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// ring position of the running batch counter, kept incrementally (n % nslots and n / nslots by a run-time nslots cost
+// two integer divisions per batch)
+__device__ __forceinline__ void skq_ring_next(int& slot, uint32_t& phase, int nslots) {
+  if (++slot == nslots) {
+    slot = 0;
+    phase ^= 1u;
+  }
+}
 __device__ __forceinline__ void skq_consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SKQ_CW * 32) : "memory"); }
 
 // Hand a ring slot back to the producer.  The arrive must not overtake the shared-memory loads that filled the consumer's
@@ -95,8 +117,20 @@ __device__ __forceinline__ float4 skq_logits(const float* srow, int c0, int C, b
   t.w = (c0 + 3 < C) ? ((bin_row || c0 + 3 == C - 1) ? bin : t.w) : -FLT_MAX;
   return t;
 }
-// p = exp(x - max) * (1 / sum): the one expression every pass uses to (re)derive a probability
-__device__ __forceinline__ float skq_prob(float x, float m, float inv) { return __fmul_rn(sk_exp(x - m), inv); }
+// the same with the per-lane case analysis hoisted out of the row loop: `interior` (all four columns < C-1) is a property
+// of the lane's group and the work item; only the one boundary group and the groups beyond C take the slow path
+__device__ __forceinline__ float4 skq_logits_fast(const float* srow, int c0, int C, bool interior, bool bin_row, float bin) {
+  if (interior && !bin_row) return *reinterpret_cast<const float4*>(srow + c0);
+  return skq_logits(srow, c0, C, bin_row, bin);
+}
+// e = exp(x - max) in two instructions, 2^(x log2e - max log2e): the init and final passes are issue-bound, not HBM-bound,
+// with the 8-instruction sk_exp.  Relative error ~ 4e-8 |t| (t = the exponent; the rounding of the FMA) + 2 ulp of
+// MUFU.EX2, i.e. < 7e-7 wherever the probability exceeds 1e-3 of the row maximum; both passes use this one expression
+// with the stored row max, so they derive identical bits.  -FLT_MAX (pad) overflows to -inf -> exactly 0.
+__device__ __forceinline__ float skq_exp(float x, float max_log2e) {
+  return fast_exp2(__fmaf_rn(x, 1.4426950408889634f, -max_log2e));
+}
+__device__ __forceinline__ float skq_max_log2e(float m) { return __fmul_rn(m, 1.4426950408889634f); }
 
 // 24-bit encoding of a non-negative fp32: the top 16 bits verbatim, the low 16 bits L rounded to the nearest multiple of
 // 257 (q = (L + 128) / 257 in 0..255, no carry since 255 * 257 = 65535) so that a single byte-permute rebuilds the word
@@ -104,7 +138,7 @@ __device__ __forceinline__ float skq_prob(float x, float m, float inv) { return 
 __device__ __forceinline__ void skq_enc24(float x, uint32_t& hi, uint32_t& lo) {
   const uint32_t bits = __float_as_uint(x);
   hi = bits >> 16;
-  lo = ((bits & 0xFFFFu) + 128u) / 257u;
+  lo = ((bits & 0xFFFFu) * 65281u + 128u * 65281u) >> 24;  // == ((bits & 0xFFFF) + 128) / 257 for all 16-bit inputs
 }
 
 template <int FMT>
@@ -241,16 +275,16 @@ __device__ __forceinline__ SkqSmem skq_smem_setup(unsigned char* base, const Skq
 template <int T>
 __device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqSmem& s) {
   if (lane_id() != 0) return;
-  int n = 0;  // running batch counter of this CTA (slot = n % nslots)
+  int n = 0, slot = 0;  // running batch counter of this CTA and its ring position
+  uint32_t phase = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
     SkqCta c;
     if (!skq_item(p, item, c)) continue;
     const float* src = p.dist + c.b * p.dist_bs;
     const uint32_t bytes = (uint32_t)(((c.C - 1 + 3) & ~3) * 4);
     const int nbatch = (c.nrows + T - 1) / T;
-    for (int j = 0; j < nbatch; ++j, ++n) {
-      const int slot = n % p.nslots;
-      mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+    for (int j = 0; j < nbatch; ++j, ++n, skq_ring_next(slot, phase, p.nslots)) {
+      skq_wait(&s.empty_bar[slot], phase ^ 1u);
       const int i0 = c.row0 + j * T;
       const int nb = min(T, c.nrows - j * T);
       int ncopy = 0;
@@ -288,7 +322,8 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
   int c0s[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
-  int n = 0;  // running batch counter (matches the producer's)
+  int n = 0, slot = 0;  // running batch counter (matches the producer's) and its ring position
+  uint32_t phase = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
   SkqCta c;
   if (!skq_item(p, item, c)) continue;
@@ -296,15 +331,18 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
   if (c.row0 == 0 && p.col_zero != nullptr)
     for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
   float4 acc[NG];
+  bool interior[NG];
 #pragma unroll
-  for (int k = 0; k < NG; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < NG; ++k) {
+    acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    interior[k] = c0s[k] + 3 < c.C - 1;
+  }
 
   const int nbatch = (c.nrows + T - 1) / T;
-  for (int jb = 0; jb < nbatch; ++jb, ++n) {
-    const int slot = n % p.nslots;
+  for (int jb = 0; jb < nbatch; ++jb, ++n, skq_ring_next(slot, phase, p.nslots)) {
     const int nb = min(T, c.nrows - jb * T);
     const int i0 = c.row0 + jb * T;
-    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    skq_wait(&s.full_bar[slot], phase);
     const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
     // pass 1: padded logits into registers, per-row max
     float4 x[T][NG];
@@ -316,11 +354,10 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
         const bool bin_row = (i0 + t == c.R - 1);
         const float* srow = reinterpret_cast<const float*>(sb + (size_t)t * p.row_bytes);
 #pragma unroll
-        for (int k = 0; k < NG; ++k)
-          if (c0s[k] < c.C) {
-            x[t][k] = skq_logits(srow, c0s[k], c.C, bin_row, bin);
-            red[t] = fmaxf(red[t], fmaxf(fmaxf(x[t][k].x, x[t][k].y), fmaxf(x[t][k].z, x[t][k].w)));
-          }
+        for (int k = 0; k < NG; ++k) {  // groups beyond C come back as -FLT_MAX: exp -> 0, nothing to guard below
+          x[t][k] = skq_logits_fast(srow, c0s[k], c.C, interior[k], bin_row, bin);
+          red[t] = fmaxf(red[t], fmaxf(fmaxf(x[t][k].x, x[t][k].y), fmaxf(x[t][k].z, x[t][k].w)));
+        }
       }
     }
     {
@@ -338,18 +375,17 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
     // pass 2: e = exp(x - max), per-row sum
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const float m = __shfl_sync(0xffffffffu, my_m, t);
+      const float mL = skq_max_log2e(__shfl_sync(0xffffffffu, my_m, t));
       red[t] = 0.f;
       if (t < nb) {
 #pragma unroll
-        for (int k = 0; k < NG; ++k)
-          if (c0s[k] < c.C) {
-            x[t][k].x = sk_exp(x[t][k].x - m);
-            x[t][k].y = sk_exp(x[t][k].y - m);
-            x[t][k].z = sk_exp(x[t][k].z - m);
-            x[t][k].w = sk_exp(x[t][k].w - m);
-            red[t] += (x[t][k].x + x[t][k].y) + (x[t][k].z + x[t][k].w);
-          }
+        for (int k = 0; k < NG; ++k) {
+          x[t][k].x = skq_exp(x[t][k].x, mL);
+          x[t][k].y = skq_exp(x[t][k].y, mL);
+          x[t][k].z = skq_exp(x[t][k].z, mL);
+          x[t][k].w = skq_exp(x[t][k].w, mL);
+          red[t] += (x[t][k].x + x[t][k].y) + (x[t][k].z + x[t][k].w);
+        }
       }
     }
     {
@@ -382,20 +418,16 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_init_kernel(const SkqParam
         unsigned char* qlo = p.Q + b * p.q_bs + (size_t)p.Rmax * p.ldq * 2 + (size_t)(i0 + t) * p.ldq;
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-          if (c0s[k] < c.C) {
-            float4 e = x[t][k];
-            e.x = __fmul_rn(e.x, inv);
-            e.y = __fmul_rn(e.y, inv);
-            e.z = __fmul_rn(e.z, inv);
-            e.w = __fmul_rn(e.w, inv);
-            skq_store4<FMT>(qrow, qlo, c0s[k], e);
-            acc[k].x = fmaf(e.x, ui, acc[k].x);
-            acc[k].y = fmaf(e.y, ui, acc[k].y);
-            acc[k].z = fmaf(e.z, ui, acc[k].z);
-            acc[k].w = fmaf(e.w, ui, acc[k].w);
-          } else if (c0s[k] < c.Cq) {
-            skq_store4<FMT>(qrow, qlo, c0s[k], make_float4(0.f, 0.f, 0.f, 0.f));
-          }
+          float4 e = x[t][k];  // exactly 0 in the pad columns [C, Cq)
+          e.x = __fmul_rn(e.x, inv);
+          e.y = __fmul_rn(e.y, inv);
+          e.z = __fmul_rn(e.z, inv);
+          e.w = __fmul_rn(e.w, inv);
+          if (c0s[k] < c.Cq) skq_store4<FMT>(qrow, qlo, c0s[k], e);
+          acc[k].x = fmaf(e.x, ui, acc[k].x);
+          acc[k].y = fmaf(e.y, ui, acc[k].y);
+          acc[k].z = fmaf(e.z, ui, acc[k].z);
+          acc[k].w = fmaf(e.w, ui, acc[k].w);
         }
       }
     }
@@ -428,7 +460,8 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
     if (lane == 0) {
       const uint32_t bpe_main = FMT == QF24 ? 2 : QFmt<FMT>::BPE;
       const size_t main_stride = (size_t)p.ldq * bpe_main;
-      int n = 0;  // running batch counter of this CTA (slot = n % nslots)
+      int n = 0, slot = 0;  // running batch counter of this CTA and its ring position
+  uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         SkqCta c;
         if (!skq_item(p, item, c)) continue;
@@ -436,9 +469,8 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
         const unsigned char* qlo = q0 + (size_t)p.Rmax * p.ldq * 2;
         const uint32_t main_bytes = (uint32_t)c.Cq * bpe_main, lo_bytes = (uint32_t)c.Cq;
         const int nbatch = (c.nrows + T - 1) / T;
-        for (int jb = 0; jb < nbatch; ++jb, ++n) {
-          const int slot = n % p.nslots;
-          mbar_wait(&s.empty_bar[slot], ((n / p.nslots) & 1) ^ 1);
+        for (int jb = 0; jb < nbatch; ++jb, ++n, skq_ring_next(slot, phase, p.nslots)) {
+              skq_wait(&s.empty_bar[slot], phase ^ 1u);
           const int i0 = c.row0 + jb * T;
           const int nb = min(T, c.nrows - jb * T);
           mbar_arrive_expect_tx(&s.full_bar[slot], (FMT == QF24 ? main_bytes + lo_bytes : main_bytes) * nb);
@@ -459,17 +491,21 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
   int c0s[NVW];
 #pragma unroll
   for (int k = 0; k < NVW; ++k) c0s[k] = 8 * ((warp * NVW + k) * 32 + lane);
-  int n = 0;  // running batch counter (matches the producer's)
+  int n = 0, slot = 0;  // running batch counter (matches the producer's) and its ring position
+  uint32_t phase = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
   SkqCta c;
   if (!skq_item(p, item, c)) continue;
   const int b = c.b;
   if (c.row0 == 0 && p.col_zero != nullptr)
     for (int j = threadIdx.x; j < p.ldc; j += SKQ_CW * 32) p.col_zero[(long long)b * p.ldc + j] = 0.f;
-  // v_j of the owned columns (pre-scaled for the fp16 copy) and their column-sum accumulators
+  // v_j of the owned columns (pre-scaled for the fp16 copy) and their column-sum accumulators.  Lanes whose columns lie
+  // beyond the matrix read column group 0 with v = 0 instead of branching around every load (they flush nothing).
   float v[NVW][8], acc[NVW][8];
+  int c0e[NVW];
 #pragma unroll
   for (int k = 0; k < NVW; ++k) {
+    c0e[k] = c0s[k] < c.Cq ? c0s[k] : 0;
     float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
     if (c0s[k] < c.C) va = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k], c.C);  // C <= ldc, both multiples of 4 apart
     if (c0s[k] + 4 < c.C) vb = v_from_colsum(p.col_prev + (long long)b * p.ldc, c0s[k] + 4, c.C);
@@ -480,67 +516,67 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_iter_kernel(const SkqParam
   }
 
   const int nbatch = (c.nrows + T - 1) / T;
-  for (int jb = 0; jb < nbatch; ++jb, ++n) {
-    const int slot = n % p.nslots;
+  for (int jb = 0; jb < nbatch; ++jb, ++n, skq_ring_next(slot, phase, p.nslots)) {
     const int nb = min(T, c.nrows - jb * T);
     const int i0 = c.row0 + jb * T;
-    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    skq_wait(&s.full_bar[slot], phase);
     const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
-    uint32_t raw[T][NVW][RAW];
-    float red[T];
+    float* part = s.part + (n & 1) * (T * SKQ_CW);
+    // FULL = all T rows of the batch exist (every batch but the last of an item): no per-row guards
+    auto batch = [&](auto full) {
+      constexpr bool FULL = decltype(full)::value;
+      uint32_t raw[T][NVW][RAW];
+      float red[T];
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      red[t] = 0.f;
-      if (t < nb) {
+      for (int t = 0; t < T; ++t)
+        if (FULL || t < nb) {
 #pragma unroll
-        for (int k = 0; k < NVW; ++k)
-          if (c0s[k] < c.Cq) skq_load8<FMT>(sb + (size_t)t * p.row_bytes, lo_off, c0s[k], raw[t][k]);
-      }
-    }
+          for (int k = 0; k < NVW; ++k) skq_load8<FMT>(sb + (size_t)t * p.row_bytes, lo_off, c0e[k], raw[t][k]);
+        }
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      if (t < nb) {
-        float r0 = 0.f, r1 = 0.f;
+      for (int t = 0; t < T; ++t) {
+        red[t] = 0.f;
+        if (FULL || t < nb) {
+          float r0 = 0.f, r1 = 0.f;
 #pragma unroll
-        for (int k = 0; k < NVW; ++k)
-          if (c0s[k] < c.Cq) {
+          for (int k = 0; k < NVW; ++k) {
             float f[8];
             skq_decode8<FMT>(raw[t][k], f);
             r0 += (f[0] * v[k][0] + f[1] * v[k][1]) + (f[2] * v[k][2] + f[3] * v[k][3]);
             r1 += (f[4] * v[k][4] + f[5] * v[k][5]) + (f[6] * v[k][6] + f[7] * v[k][7]);
           }
-        red[t] = r0 + r1;
+          red[t] = r0 + r1;
+        }
       }
-    }
-    float* part = s.part + (n & 1) * (T * SKQ_CW);
-    {
-      const float tot = skq_tr_reduce<T>(red, lane, [](float a, float b2) { return a + b2; });
-      skq_release(&s.empty_bar[slot], lane, tot);  // every lane's rows sit in registers (they fed tot)
-      if ((lane & (32 / T - 1)) == 0) part[rid * SKQ_CW + warp] = tot;
-    }
-    skq_consumer_sync();
-    float my_u = 0.f;
-    if (lane < T) {
-      const float4 a = *reinterpret_cast<const float4*>(part + lane * SKQ_CW);
-      const float4 d = *reinterpret_cast<const float4*>(part + lane * SKQ_CW + 4);
-      const float rs = ((a.x + a.y) + (a.z + a.w)) + ((d.x + d.y) + (d.z + d.w));
-      my_u = ((i0 + lane == c.R - 1) ? (float)c.R : 1.f) / (rs + SK_EPS);
-      if (warp == 0 && lane < nb) p.u[(long long)b * p.Rmax + i0 + lane] = my_u;
-    }
+      {
+        const float tot = skq_tr_reduce<T>(red, lane, [](float a, float b2) { return a + b2; });
+        skq_release(&s.empty_bar[slot], lane, tot);  // every lane's rows sit in registers (they fed tot)
+        if ((lane & (32 / T - 1)) == 0) part[rid * SKQ_CW + warp] = tot;
+      }
+      skq_consumer_sync();
+      float my_u = 0.f;
+      if (lane < T) {
+        const float4 a = *reinterpret_cast<const float4*>(part + lane * SKQ_CW);
+        const float4 d = *reinterpret_cast<const float4*>(part + lane * SKQ_CW + 4);
+        const float rs = ((a.x + a.y) + (a.z + a.w)) + ((d.x + d.y) + (d.z + d.w));
+        my_u = ((i0 + lane == c.R - 1) ? (float)c.R : 1.f) / (rs + SK_EPS);
+        if (warp == 0 && lane < nb) p.u[(long long)b * p.Rmax + i0 + lane] = my_u;
+      }
 #pragma unroll
-    for (int t = 0; t < T; ++t) {
-      const float uis = __shfl_sync(0xffffffffu, my_u, t) * vscale;
-      if (t < nb) {
+      for (int t = 0; t < T; ++t) {
+        const float uis = __shfl_sync(0xffffffffu, my_u, t) * vscale;
+        if (FULL || t < nb) {
 #pragma unroll
-        for (int k = 0; k < NVW; ++k)
-          if (c0s[k] < c.Cq) {
+          for (int k = 0; k < NVW; ++k) {
             float f[8];
             skq_decode8<FMT>(raw[t][k], f);
 #pragma unroll
             for (int q = 0; q < 8; ++q) acc[k][q] = fmaf(f[q], uis, acc[k][q]);
           }
+        }
       }
-    }
+    };
+    batch(std::false_type{});
   }
   // every column has exactly one owner lane in the CTA: straight to the global accumulators
   float* ca = p.col_acc + (long long)b * p.ldc;
@@ -594,7 +630,7 @@ __device__ __forceinline__ SkqBest skq_tr_reduce_best(SkqBest (&a)[T], int lane)
   return r;
 }
 
-template <int NVW, int T>
+template <int NVW, int T, bool WRITE, bool MASS>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
   constexpr int NG = 2 * NVW;
@@ -605,20 +641,22 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
     return;
   }
   const float bin = *p.bin_score;
-  const bool want_col = p.col_mass != nullptr;
   const int rid = skq_rid<T>(lane);
   int c0s[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) c0s[k] = 4 * ((warp * NG + k) * 32 + lane);
-  int n = 0;  // running batch counter (matches the producer's)
+  int n = 0, slot = 0;  // running batch counter (matches the producer's) and its ring position
+  uint32_t phase = 0;
   for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
   SkqCta c;
   if (!skq_item(p, item, c)) continue;
   const int b = c.b;
   float4 v[NG], acc[NG], cbv[NG];
   int4 cbi[NG];
+  bool interior[NG];
 #pragma unroll
   for (int k = 0; k < NG; ++k) {
+    interior[k] = c0s[k] + 3 < c.C - 1;
     v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c0s[k] < c.C) {
       v[k] = make_float4(1.f, c0s[k] + 1 < c.C ? 1.f : 0.f, c0s[k] + 2 < c.C ? 1.f : 0.f, c0s[k] + 3 < c.C ? 1.f : 0.f);
@@ -630,8 +668,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
   }
 
   const int nbatch = (c.nrows + T - 1) / T;
-  for (int jb = 0; jb < nbatch; ++jb, ++n) {
-    const int slot = n % p.nslots;
+  for (int jb = 0; jb < nbatch; ++jb, ++n, skq_ring_next(slot, phase, p.nslots)) {
     const int nb = min(T, c.nrows - jb * T);
     const int i0 = c.row0 + jb * T;
     // per-row scalars: lane t fetches those of row t
@@ -642,7 +679,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
       my_inv = p.row_inv[o];
       if (p.do_iter) my_u = p.u[o];
     }
-    mbar_wait(&s.full_bar[slot], (n / p.nslots) & 1);
+    skq_wait(&s.full_bar[slot], phase);
     const unsigned char* sb = s.ring + (size_t)slot * p.slot_bytes;
     float4 x[T][NG];
 #pragma unroll
@@ -651,14 +688,13 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
         const bool bin_row = (i0 + t == c.R - 1);
         const float* srow = reinterpret_cast<const float*>(sb + (size_t)t * p.row_bytes);
 #pragma unroll
-        for (int k = 0; k < NG; ++k)
-          if (c0s[k] < c.C) x[t][k] = skq_logits(srow, c0s[k], c.C, bin_row, bin);
+        for (int k = 0; k < NG; ++k) x[t][k] = skq_logits_fast(srow, c0s[k], c.C, interior[k], bin_row, bin);
       }
 
     SkqBest rb[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-      const float m = __shfl_sync(0xffffffffu, my_m, t);
+      const float mL = skq_max_log2e(__shfl_sync(0xffffffffu, my_m, t));
       const float inv = __shfl_sync(0xffffffffu, my_inv, t);
       const float ui = __shfl_sync(0xffffffffu, my_u, t);
       rb[t].v = -1.f;
@@ -670,33 +706,44 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
         float* prow = p.P + b * p.p_bs + (long long)i * p.ldp;
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
-          if (c0s[k] >= c.C) continue;
-          const float o[4] = {__fmul_rn(__fmul_rn(skq_prob(x[t][k].x, m, inv), ui), v[k].x),
-                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].y, m, inv), ui), v[k].y),
-                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].z, m, inv), ui), v[k].z),
-                              __fmul_rn(__fmul_rn(skq_prob(x[t][k].w, m, inv), ui), v[k].w)};
-          if (p.write_scores) *reinterpret_cast<float4*>(prow + c0s[k]) = make_float4(o[0], o[1], o[2], o[3]);
+          // (p u) v like the reference's p * u * v, with p = e * (1 / sum); groups beyond C evaluate to exactly 0
+          const float o[4] = {__fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].x, mL), inv), ui), v[k].x),
+                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].y, mL), inv), ui), v[k].y),
+                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].z, mL), inv), ui), v[k].z),
+                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].w, mL), inv), ui), v[k].w)};
+          if (WRITE && c0s[k] < c.C) *reinterpret_cast<float4*>(prow + c0s[k]) = make_float4(o[0], o[1], o[2], o[3]);
           if (inner_row) {
             // column trackers: rows ascend, so a strict > keeps the lowest row (the dustbin column is never flushed)
             if (o[0] > cbv[k].x) { cbv[k].x = o[0]; cbi[k].x = i; }
             if (o[1] > cbv[k].y) { cbv[k].y = o[1]; cbi[k].y = i; }
             if (o[2] > cbv[k].z) { cbv[k].z = o[2]; cbi[k].z = i; }
             if (o[3] > cbv[k].w) { cbv[k].w = o[3]; cbi[k].w = i; }
-            if (want_col) {
+            if (MASS) {
               acc[k].x += o[0];
               acc[k].y += o[1];
               acc[k].z += o[2];
               acc[k].w += o[3];
             }
             // row tracker over the non-dustbin columns: columns ascend with q and k, strict > keeps the lowest
+            if (interior[k]) {  // no column masking
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const bool in = c0s[k] + q < c.C - 1;
-              const float oq = in ? o[q] : -1.f;
-              rb[t].m += in ? o[q] : 0.f;
-              if (oq > rb[t].v) {
-                rb[t].v = oq;
-                rb[t].j = c0s[k] + q;
+              for (int q = 0; q < 4; ++q) {
+                rb[t].m += o[q];
+                if (o[q] > rb[t].v) {
+                  rb[t].v = o[q];
+                  rb[t].j = c0s[k] + q;
+                }
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                const bool in = c0s[k] + q < c.C - 1;
+                const float oq = in ? o[q] : -1.f;
+                rb[t].m += in ? o[q] : 0.f;
+                if (oq > rb[t].v) {
+                  rb[t].v = oq;
+                  rb[t].j = c0s[k] + q;
+                }
               }
             }
           }
@@ -731,7 +778,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
       const long long o = (long long)b * p.N0max + i0 + lane;
       p.row_max[o] = r.v;
       p.row_arg[o] = r.j;
-      if (p.row_mass) p.row_mass[o] = r.m;
+      if (MASS && p.row_mass) p.row_mass[o] = r.m;
     }
   }
 
@@ -746,7 +793,7 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
       const int j = c0s[k] + q;
       if (j < c.C - 1 && bv[q] >= 0.f) {
         atomicMax(ck + j, pack_max_key(bv[q], bi[q]));
-        if (want_col) atomicAdd(p.col_mass + (long long)b * p.N1max + j, am[q]);
+        if (MASS && p.col_mass) atomicAdd(p.col_mass + (long long)b * p.N1max + j, am[q]);
       }
     }
   }
@@ -754,9 +801,8 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-template <int FMT, int NVW, int T_ITER>
+template <int FMT, int NVW, int T_ITER, int T_DIST>
 static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
-  constexpr int T_DIST = 4;
   constexpr int BPE = QFmt<FMT>::BPE;
   const int R = a.N0max + 1, C = a.N1max + 1;
   const int ldq = (C + 15) & ~15;
@@ -775,7 +821,10 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
     };
     IMP_CUDA_OK(conf((const void*)skq_init_kernel<FMT, NVW, T_DIST>));
     IMP_CUDA_OK(conf((const void*)skq_iter_kernel<FMT, NVW, T_ITER>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, false, false>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, false, true>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, false>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, true>));
     configured = true;
   }
   SkqParams p;
@@ -793,7 +842,7 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   // persistent grid: two CTAs per SM; rows per work item = the multiple of 8 whose item count fills whole rounds of the
   // grid best
   const int ctas = 2 * num_sms();
-  const int rows_per_cta = sk_rows_per_cta(R, a.batch, num_sms(), 8);
+  const int rows_per_cta = sk_rows_per_cta(R, a.batch, ctas, 8);
   p.rows_per_cta = rows_per_cta;
   p.blocks_per_mat = (R + rows_per_cta - 1) / rows_per_cta;
   p.n_items = p.blocks_per_mat * a.batch;
@@ -836,7 +885,17 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   p.col_acc = nullptr;
   p.col_zero = nullptr;
   p.reverse = 0;
-  skq_final_kernel<NVW, T_DIST><<<grid, SKQ_THREADS, (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
+  {
+    const size_t smem = (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM;
+    const bool mass = a.col_mass != nullptr || a.row_mass != nullptr;
+    if (a.write_scores) {
+      if (mass) skq_final_kernel<NVW, T_DIST, true, true><<<grid, SKQ_THREADS, smem, st>>>(p);
+      else skq_final_kernel<NVW, T_DIST, true, false><<<grid, SKQ_THREADS, smem, st>>>(p);
+    } else {
+      if (mass) skq_final_kernel<NVW, T_DIST, false, true><<<grid, SKQ_THREADS, smem, st>>>(p);
+      else skq_final_kernel<NVW, T_DIST, false, false><<<grid, SKQ_THREADS, smem, st>>>(p);
+    }
+  }
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -844,8 +903,8 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
 template <int FMT>
 static int dispatch_nv(const SinkhornArgs& a, cudaStream_t st) {
   const int C = a.N1max + 1;
-  if (C <= 2048) return run_compact<FMT, 1, (FMT == QF32 ? 4 : 8)>(a, st);
-  if (C <= 4096) return run_compact<FMT, 2, 4>(a, st);
+  if (C <= 2048) return run_compact<FMT, 1, (FMT == QF32 ? 4 : 8), 4>(a, st);
+  if (C <= 4096) return run_compact<FMT, 2, 4, 4>(a, st);
   set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4095);
   return 2;
 }

@@ -252,7 +252,8 @@ def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, 
     a.q_store, a.q_batch_stride, a.row_stats, a.storage = ptr(ws.q_store), ws.q_batch_stride, ptr(ws.row_stats), ws.storage
     mat_bytes = 4.0 * ws.batch * (ws.N0max + 1) * (ws.N1max + 1)
     # algorithmic traffic: 2 sweeps per iteration + init (read dist, write p) + final (read, write)
-    with _Span('sinkhorn', 3 + max(iters - 1, 0), mat_bytes * (2 * iters + 4)):
+    n_kernels = (2 if ws.q_store is not None else 3) + max(iters - 1, 0)     # init, iterations, final (+ column arg-max)
+    with _Span('sinkhorn', n_kernels, mat_bytes * (2 * iters + 4)):
         check(_lib.load().imp_sinkhorn(C.byref(a), stream_ptr()), 'imp_sinkhorn')
 
 
