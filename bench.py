@@ -270,24 +270,29 @@ def run_gpu(args, rank, world, local_rank):
         tot, n, work = prof[name]
         avg_s = tot / n / 1e3
         if name.startswith('sinkhorn'):
-            # dominant kernel of the group: sk_ring_kernel<ITER>, one launch per Sinkhorn iteration.  Its algorithmic
-            # traffic is ONE sweep of the [B, N0+1, N1+1] fp32 matrix per launch (the reference
-            # formulation, SURVEY.md 8(d), counts two sweeps per iteration; this kernel fuses them).
+            # dominant kernel of the group: skq_iter_kernel, one launch per Sinkhorn iteration.  Its algorithmic traffic
+            #  is ONE sweep of the [B, N0+1, N1+1] fp32 matrix per launch (the reference formulation,
+            # SURVEY.md 8(d), counts two sweeps per iteration; this kernel fuses them).
             mat = 4.0 * BATCH * (N_KPTS + 1) * (N_KPTS + 1)
             sk_bytes = {'fp32': 4, 'fp24': 3, 'fp16': 2}[sk_storage]
-            it_s = (sk_iter_ms if sk_iter_ms > 0 else (tot / n) / 23.0) / 1e3
+            n_launch = 21           # init + 19 iterations + final (the column arg-max is fused into the final pass)
+            it_s = (sk_iter_ms if sk_iter_ms > 0 else (tot / n) / n_launch) / 1e3
             ach = mat / it_s / 1e9
-            kname = 'sk_ring_kernel<ITER>' if sk_storage == 'fp32' else f'skq_iter_kernel<{sk_storage}>'
-            return {'kernel': kname + ' (one Sinkhorn iteration, %d of the %d launches of a scoring)' % (19, 23),
+            moved = ach * sk_bytes / 4.0 * (2016.0 / 2001.0)       # rows are padded to 16 columns in the stored copy
+            return {'kernel': f'skq_iter_kernel<{sk_storage}> (one Sinkhorn iteration, 19 of the {n_launch} launches of a scoring)',
                     'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'launch_ms': it_s * 1e3,
-                    'storage': {'format': sk_storage, 'bytes_per_element': sk_bytes,
-                                'moved_GBps': ach * sk_bytes / 4.0, 'moved_frac_of_peak': ach * sk_bytes / 4.0 / peaks['hbm_gbs'],
-                                'note': 'the iteration sweeps stream a %d-byte copy of softmax(M); `achieved` counts the '
-                                        'ALGORITHMIC 4 B per element, `moved_GBps` the bytes actually requested' % sk_bytes},
+                    'storage': {'format': sk_storage, 'bytes_per_element': sk_bytes, 'moved_GBps': moved,
+                                'moved_frac_of_peak': moved / peaks['hbm_gbs'],
+                                'note': 'the iteration sweeps stream a %d-byte copy of softmax(M) (DESIGN.md section 2): `achieved` '
+                                        'counts the ALGORITHMIC 4 B per element, so frac can exceed 1; `moved_GBps` counts the bytes '
+                                        'actually requested from HBM and is the figure to hold against the copy peak' % sk_bytes},
                     'reference_counting': {'achieved': 2 * ach, 'frac': 2 * ach / peaks['hbm_gbs'],
                                            'note': '2 sweeps per iteration as the reference algorithm is counted in SURVEY.md 8(d)'},
-                    'whole_scoring': {'ms': tot / n, 'sweep_equivalents': 23, 'GBps': 23 * mat / (tot / n / 1e3) / 1e9},
+                    'whole_scoring': {'ms': tot / n, 'launches': n_launch,
+                                      'algorithmic_GBps': (2 * 20 + 4) * mat / (tot / n / 1e3) / 1e9,
+                                      'note': 'SURVEY.md 8(d) bytes of one scoring (2 sweeps x 20 iterations + init + final) over '
+                                              'the CUDA-event time of the whole imp_sinkhorn call'},
                     'note': 'achieved = 4 B x B x (N0+1) x (N1+1) per launch / mean CUDA-event duration of the 19 iteration '
                             'launches of each scoring (events recorded inside libimp_b200.so on the launching stream); '
                             'peak = STREAM-style copy of ' + peak_src}

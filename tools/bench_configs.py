@@ -55,12 +55,15 @@ with torch.no_grad():
 out['imp_b1_15it_layer_api_7_scorings'] = {'ms_per_pair': ms, 'pairs_per_s': 1e3 / ms}
 del net; torch.cuda.empty_cache()
 # ---- configs[4]: Sinkhorn only, 2048^2 (dist 2047^2), 100 iterations
-for Bs in (1, 16):
+for Bs, storage in ((1, None), (16, 'fp32'), (16, 'fp24'), (16, 'fp16')):
     N = 2047; ld = 2048
     dist = torch.randn(Bs, N, ld, device=dev) * 3
-    ws = ops.SinkhornWorkspace(Bs, N, N, dev); bs = torch.tensor(1.0, device=dev)
+    ws = ops.SinkhornWorkspace(Bs, N, N, dev, storage=storage); bs = torch.tensor(1.0, device=dev)
     ms = timed(lambda: ops.sinkhorn(dist, ld, bs, 100, ws, write_scores=True), warm=2, n=3)
     mat = 4.0 * Bs * 2048 * 2048
-    out[f'sinkhorn_2048sq_100it_b{Bs}'] = {'ms': ms, 'algorithmic_GBps': 2 * 100 * mat / ms / 1e6, 'actual_sweep_GBps': (100 + 4) * mat / ms / 1e6,
-                                         'frac_of_measured_hbm_6582': 2 * 100 * mat / ms / 1e6 / 6582.5}
+    peak = 6543.7   # MEASURED_PEAKS.json hbm_gbs
+    out[f'sinkhorn_2048sq_100it_b{Bs}' + (f'_{storage}' if storage else '')] = {
+        'ms': ms, 'algorithmic_GBps': 2 * 100 * mat / ms / 1e6, 'sweeps_GBps_at_4B_per_element': (100 + 2) * mat / ms / 1e6,
+        'frac_of_measured_hbm': 2 * 100 * mat / ms / 1e6 / peak,
+        'path': 'shared-memory resident (cooperative)' if ws.q_store is None else f'column-split streaming, {storage} copy'}
 print(json.dumps(out, indent=1))
