@@ -158,3 +158,26 @@ def test_high_precision_attention_with_peaky_weights(kind):
     diffs = sorted(float((a.cpu() - b).abs().max()) for a, b in zip(out['mscores0'], ref['mscores0']))
     assert mism == 0
     assert diffs[len(diffs) // 2] < 1e-4, diffs       # median over iterations (a single near-tie flip may spike one)
+
+
+def test_pair_feeder_stages_batches_in_order():
+    """PairFeeder (host -> device double buffering in front of the public API): batches come out intact and in order,
+    shape-only entries pass through, and over-staging is refused."""
+    from imp_release_b200.feeder import PairFeeder
+    feeder = PairFeeder('cuda', depth=2)
+    batches = [{'descriptors0': torch.full((2, 50, 256), float(i)).pin_memory(), 'scores0': torch.arange(100.).view(2, 50).pin_memory() + i,
+                'image0': torch.zeros(1, 1, 480, 640)} for i in range(5)]
+    feeder.stage(batches[0])
+    got = []
+    for i in range(5):
+        d = feeder.next()
+        if i + 1 < 5:
+            feeder.stage(batches[i + 1])           # lands in the other buffer while batch i is in use
+            with pytest.raises(RuntimeError):      # a third batch would overwrite the one in use
+                feeder.stage(batches[i + 1])
+        assert d['image0'].shape == (1, 1, 480, 640) and not d['image0'].is_cuda
+        got.append((d['descriptors0'] * 2).sum().item() / (2 * 50 * 256 * 2) + d['scores0'][0, 0].item())   # uses the slot on the compute stream
+    assert got == [2.0 * i for i in range(5)]
+    assert PairFeeder.bytes_of(batches[0]) == 2 * 50 * 256 * 4 + 100 * 4
+    with pytest.raises(RuntimeError):
+        feeder.next()
