@@ -769,7 +769,14 @@ int launch_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   if (C <= 4 * 32 * 9) return run_sinkhorn<9>(a, st);
   if (C <= 4 * 32 * 17) return run_sinkhorn<17>(a, st);
   if (C <= 4 * 32 * 25) return run_sinkhorn<25>(a, st);
-  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4 * 32 * 25 - 1);
+  if (C <= 4096 && a.q_store != nullptr && a.row_stats != nullptr) {  // beyond the row-ring kernels: column-split path only
+    IMP_CUDA_OK(cudaMemsetAsync(a.col_key, 0, (size_t)a.batch * a.N1max * sizeof(unsigned long long), st));
+    if (a.col_mass) IMP_CUDA_OK(cudaMemsetAsync(a.col_mass, 0, (size_t)a.batch * a.N1max * sizeof(float), st));
+    IMP_CUDA_OK(cudaMemsetAsync(a.colbuf, 0, (size_t)a.batch * a.ldp * sizeof(float), st));
+    return run_sinkhorn_compact(a, st);
+  }
+  set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns (%d with a q_store workspace)", a.N1max,
+            4 * 32 * 25 - 1, 4095);
   return 2;
 }
 

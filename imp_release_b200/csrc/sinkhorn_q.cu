@@ -904,7 +904,7 @@ template <int FMT>
 static int dispatch_nv(const SinkhornArgs& a, cudaStream_t st) {
   const int C = a.N1max + 1;
   if (C <= 2048) return run_compact<FMT, 1, (FMT == QF32 ? 4 : 8), 4>(a, st);
-  if (C <= 4096) return run_compact<FMT, 2, 4, 4>(a, st);
+  if (C <= 4096) return run_compact<FMT, 2, (FMT == QF32 ? 2 : 4), 2>(a, st);  // 16 KB rows: fewer rows per ring slot
   set_error("sinkhorn: N1 = %d exceeds the supported maximum of %d columns", a.N1max, 4095);
   return 2;
 }
