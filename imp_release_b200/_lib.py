@@ -82,6 +82,7 @@ SIGNATURES = {
     'imp_kenc_input': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'imp_small_linear': (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp]),
     'imp_sinkhorn': (C.c_int, [C.POINTER(SinkhornArgs), c_vp]),
+    'imp_sinkhorn_q_store_bytes': (c_i64, [c_i32, c_i32, c_i32, c_i32]),
     'imp_set_profiling': (C.c_int, [c_i32]),
     'imp_sinkhorn_iter_ms': (C.c_float, []),
     'imp_matches': (C.c_int, [C.POINTER(MatchArgs), c_vp]),

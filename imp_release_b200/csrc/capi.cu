@@ -17,6 +17,7 @@ int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max,
                         cudaStream_t st);
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
                         int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st);
+long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage);
 void sinkhorn_set_profiling(int on);
 float sinkhorn_iter_ms();
 }  // namespace imp
@@ -53,6 +54,9 @@ IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const 
   return imp::launch_small_linear(X, ldx, W, bias, Y, ldy, rows, Cin, Cout, ST(stream));
 }
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream) { return imp::launch_sinkhorn(*args, ST(stream)); }
+IMP_API int64_t imp_sinkhorn_q_store_bytes(int32_t batch, int32_t N0max, int32_t N1max, int32_t storage) {
+  return imp::sinkhorn_q_store_bytes(batch, N0max, N1max, storage);
+}
 IMP_API int imp_set_profiling(int32_t on) {
   imp::sinkhorn_set_profiling(on);
   return 0;

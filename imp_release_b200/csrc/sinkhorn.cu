@@ -602,6 +602,28 @@ static int sk_chunk_matrices(size_t matrix_bytes, int batch) {
   return c > batch ? batch : (int)c;
 }
 
+// Will a problem of this size run in the shared-memory-resident kernel (which needs no q_store workspace)?  One source of
+// truth for run_sinkhorn and for the workspace query of the C ABI.
+static bool sk_resident_geometry(int batch, int R, int ldp, int* rows_per_cta, int* ctas_per_mat, size_t* smem) {
+  const long long wave = 2LL * num_sms();
+  int rpc = (int)(((long long)batch * R + wave - 1) / wave);
+  rpc = (rpc + SKS_WARPS - 1) / SKS_WARPS * SKS_WARPS;
+  const int cpm = (R + rpc - 1) / rpc;
+  const size_t sm = ((size_t)rpc + 2) * (size_t)ldp * sizeof(float) + (size_t)rpc * sizeof(float) + 16;
+  if (rows_per_cta) *rows_per_cta = rpc;
+  if (ctas_per_mat) *ctas_per_mat = cpm;
+  if (smem) *smem = sm;
+  return (long long)batch * cpm <= wave && sm <= (size_t)SKR_SMEM_BUDGET;
+}
+
+long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage) {
+  const int R = N0max + 1, C = N1max + 1;
+  if (batch <= 0 || N0max <= 0 || N1max <= 0 || C < 64 || C > 4096) return 0;
+  if (sk_resident_geometry(batch, R, (C + 3) & ~3, nullptr, nullptr, nullptr)) return 0;
+  const int bpe = storage == IMP_SK_STORE_F16 ? 2 : (storage == IMP_SK_STORE_F24 ? 3 : 4);
+  return (long long)R * ((C + 15) & ~15) * bpe;
+}
+
 static int g_profile = 0;
 static cudaEvent_t g_ev0 = nullptr, g_ev1 = nullptr;
 static int g_ev_iters = 0;
@@ -654,12 +676,10 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
       const char* e = getenv("IMP_SK_RESIDENT");
       use_resident = e ? atoi(e) : 1;
     }
-    const long long wave = 2LL * num_sms();
-    int rpc = (int)(((long long)a.batch * R + wave - 1) / wave);
-    rpc = (rpc + SKS_WARPS - 1) / SKS_WARPS * SKS_WARPS;
-    const int ctas_per_mat = (R + rpc - 1) / rpc;
-    const size_t smem_res = ((size_t)rpc + 2) * row_bytes + (size_t)rpc * sizeof(float) + 16;
-    if (use_resident && (long long)a.batch * ctas_per_mat <= wave && smem_res <= (size_t)SKR_SMEM_BUDGET) {
+    int rpc, ctas_per_mat;
+    size_t smem_res;
+    const bool fits = sk_resident_geometry(a.batch, R, a.ldp, &rpc, &ctas_per_mat, &smem_res);
+    if (use_resident && fits) {
       static bool conf = false;
       if (!conf) {
         IMP_CUDA_OK(cudaFuncSetAttribute(sk_resident_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));

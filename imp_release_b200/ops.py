@@ -188,21 +188,11 @@ def small_linear(X, ldx, W, bias, Y, ldy, rows, cin, cout):
 
 
 SK_STORAGE = {'fp32': 0, 'fp16': 1, 'fp24': 2}
-SK_STORAGE_BYTES = {0: 4, 1: 2, 2: 3}
 
 
 def default_sk_storage() -> str:
     """Storage of softmax(M) for the Sinkhorn iteration sweeps (include/imp_b200.h, IMP_SK_STORE_*)."""
     return os.environ.get('IMP_SK_STORAGE', 'fp24')
-
-
-def _sk_resident_fits(batch: int, R: int, ldp: int, device) -> bool:
-    """Mirror of run_sinkhorn's test (csrc/sinkhorn.cu) for the shared-memory-resident kernel, which never touches the
-    compact copy: lets small problems skip its allocation."""
-    wave = 2 * torch.cuda.get_device_properties(device).multi_processor_count
-    rpc = -(-batch * R // wave)
-    rpc = -(-rpc // 4) * 4
-    return batch * -(-R // rpc) <= wave and (rpc + 2) * ldp * 4 + rpc * 4 + 16 <= 113 * 1024
 
 
 class SinkhornWorkspace:
@@ -224,10 +214,10 @@ class SinkhornWorkspace:
         self.q_store = self.row_stats = None
         self.q_batch_stride = 0
         legacy = os.environ.get('IMP_SK_LEGACY', '0') == '1'      # row-ring fp32 kernels of csrc/sinkhorn.cu
-        if not legacy and 64 <= N1max + 1 <= 4096 and not _sk_resident_fits(batch, N0max + 1, self.ldp, device):
-            ldq = (N1max + 1 + 15) // 16 * 16
-            self.q_batch_stride = (N0max + 1) * ldq * SK_STORAGE_BYTES[self.storage]
-            self.q_store = torch.empty(batch, self.q_batch_stride, dtype=torch.uint8, device=device)
+        per_matrix = 0 if legacy else int(_lib.load().imp_sinkhorn_q_store_bytes(batch, N0max, N1max, self.storage))
+        if per_matrix > 0:
+            self.q_batch_stride = per_matrix
+            self.q_store = torch.empty(batch, per_matrix, dtype=torch.uint8, device=device)
             self.row_stats = torch.empty(2, batch, N0max + 1, **f32)
 
     def scores(self) -> torch.Tensor:

@@ -136,6 +136,10 @@ typedef struct imp_sinkhorn_args {
 #define IMP_SK_STORE_F16 1 /* p * 2^14 as IEEE fp16: 2 bytes per element */
 #define IMP_SK_STORE_F24 2 /* top 16 bits of the fp32 word + one byte of mantissa extension (planar): 3 bytes per element */
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
+/* Workspace query (the library never allocates): bytes PER MATRIX of q_store that imp_sinkhorn wants for this problem size
+ * and storage format, or 0 when it will not use one (small problems run a shared-memory-resident kernel, N1 outside
+ * [63, 4095] the row-ring kernels).  Needs a CUDA device (the answer depends on its SM count). */
+IMP_API int64_t imp_sinkhorn_q_store_bytes(int32_t batch, int32_t N0max, int32_t N1max, int32_t storage);
 /* Measurement aid for bench.py: with profiling on, imp_sinkhorn brackets its iteration launches with CUDA events on the
  * launching stream; imp_sinkhorn_iter_ms() waits for them and returns the mean duration of one iteration kernel of the
  * most recent call (< 0 if none was recorded). */

@@ -16,7 +16,7 @@ def test_library_exports_every_declared_symbol():
     from imp_release_b200 import _lib
     lib = _lib.load()
     hdr = open(os.path.join(ROOT, 'include', 'imp_b200.h')).read()
-    declared = set(re.findall(r'IMP_API\s+(?:const\s+char\*|int|float)\s+(imp_[a-z0-9_]+)\s*\(', hdr))
+    declared = set(re.findall(r'IMP_API\s+(?:const\s+char\*|int64_t|int|float)\s+(imp_[a-z0-9_]+)\s*\(', hdr))
     assert declared, 'no declarations parsed'
     assert declared == set(_lib.SIGNATURES), (declared ^ set(_lib.SIGNATURES))
     for name in declared:
