@@ -14,8 +14,6 @@
 //    warp as soon as the rows sit in registers.
 //  * one sweep per iteration (u_i, then p_ij u_i folded into the column sums the next launch turns into v), and the final
 //    pass also produces the column arg-max (packed atomicMax per owned column), so a scoring is 1 + 19 + 1 sweeps.
-//  * sweep direction alternates from launch to launch so that the tail of the previous sweep, still resident in the
-//    126 MB L2, is what the next sweep reads first.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -66,7 +64,7 @@ struct SkqParams {
   const int *n0s, *n1s;
   int N0max, N1max;
   int rows_per_cta, blocks_per_mat, n_items, nslots, slot_bytes, row_bytes;
-  int do_iter, write_scores, reverse;
+  int do_iter, write_scores;
 };
 
 // mbarrier wait whose polls are suspended in hardware for up to ~20 us at a time: the plain try_wait loop of ptx.cuh
@@ -236,7 +234,6 @@ struct SkqCta {
   int b, row0, nrows, R, C, Cq;
 };
 __device__ __forceinline__ bool skq_item(const SkqParams& p, int item, SkqCta& c) {
-  if (p.reverse) item = p.n_items - 1 - item;
   c.b = item / p.blocks_per_mat;
   const int bx = item - c.b * p.blocks_per_mat;
   const SkDims d = sk_dims(p.n0s, p.n1s, c.b, p.N0max, p.N1max);
@@ -861,7 +858,6 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   p.col_prev = nullptr;
   p.col_acc = col[0];
   p.col_zero = col[1];
-  p.reverse = 0;
   skq_init_kernel<FMT, NVW, T_DIST><<<grid, SKQ_THREADS, (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
 
   const bool prof = sk_profiling_on() && iters > 1;
@@ -873,7 +869,6 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
     p.col_prev = col[(k - 1) % 3];
     p.col_acc = col[k % 3];
     p.col_zero = col[(k + 1) % 3];
-    p.reverse = k & 1;
     skq_iter_kernel<FMT, NVW, T_ITER><<<grid, SKQ_THREADS, (size_t)slots_q * p.slot_bytes + SKQ_FIXED_SMEM, st>>>(p);
   }
   if (prof) sk_profile_end(st, iters - 1);
@@ -884,7 +879,6 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   p.col_prev = col[(iters > 0 ? iters - 1 : 0) % 3];
   p.col_acc = nullptr;
   p.col_zero = nullptr;
-  p.reverse = 0;
   {
     const size_t smem = (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM;
     const bool mass = a.col_mass != nullptr || a.row_mass != nullptr;
