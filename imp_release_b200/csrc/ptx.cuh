@@ -47,8 +47,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+#ifdef IMP_MBAR_SUSPEND_NS
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P, [%0], %1, %2;\n\t"
+      "@!P bra WAIT_LOOP;\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "n"(IMP_MBAR_SUSPEND_NS)
+      : "memory");
+#else
   while (!mbar_try_wait(bar, parity)) {
   }
+#endif
 }
 
 // generic-proxy writes to smem must be fenced before the async proxy (TMA / UMMA) reads them
