@@ -124,3 +124,27 @@ def test_shard_indices_cover_everything():
     for n, w in ((4000, 8), (7, 2), (3, 4)):
         seen = sorted(i for r in range(w) for i in shard_indices(n, r, w))
         assert seen == list(range(n))
+
+
+def test_sinkhorn_24bit_copy_format_restated_on_cpu():
+    """The 24-bit storage format of csrc/sinkhorn_q.cu (skq_enc24 / skq_decode8), restated with integers: the top 16 bits of
+    the fp32 word verbatim, the low 16 bits L rounded to the nearest multiple of 257 so that one byte-permute rebuilds the
+    word as [b3 b2 q q].  Properties the kernels rely on: q fits a byte (no carry into the top half), the multiply-shift
+    the encoder uses equals the division for every 16-bit input, and the relative error stays below 128.5 ulp(fp32)."""
+    import numpy as np
+    L = np.arange(65536, dtype=np.uint64)
+    q = (L + 128) // 257
+    assert int(q.max()) == 255
+    assert np.array_equal(q, (L * 65281 + 128 * 65281) >> 24)
+    assert int(np.abs(q.astype(np.int64) * 257 - L.astype(np.int64)).max()) <= 128
+    rng = np.random.default_rng(0)
+    p = np.concatenate([rng.random(200000, dtype=np.float32), np.float32(10.0) ** rng.uniform(-37, 0, 200000).astype(np.float32),
+                        np.array([0.0, 1.0, 2.0 ** -126, 1e-30], dtype=np.float32)])
+    bits = p.view(np.uint32).astype(np.uint64)
+    hi, lo = bits >> 16, bits & 0xFFFF
+    qq = (lo * 65281 + 128 * 65281) >> 24
+    dec = ((hi << 16) | (qq << 8) | qq).astype(np.uint32).view(np.float32)
+    nz = p > 0
+    assert float(np.abs((dec[nz].astype(np.float64) - p[nz]) / p[nz]).max()) <= 128.5 * 2.0 ** -23
+    assert np.all(dec[~nz] == 0)
+    assert np.all(np.diff(dec[np.argsort(p, kind='stable')]) >= 0), 'the encoding must be monotone'
