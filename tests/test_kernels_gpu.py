@@ -313,6 +313,31 @@ def test_sinkhorn_compact_varlen(storage):
             assert torch.equal(i0[b, :a].cpu(), ri0[0]) and torch.equal(i1[b, :c].cpu(), ri1[0])
 
 
+def test_sinkhorn_row_ring_fallback_path(monkeypatch):
+    """Callers of the C ABI that pass no q_store workspace (and N1 < 63) stream the fp32 matrix through the round-1 row-ring
+    kernels of csrc/sinkhorn.cu; IMP_SK_LEGACY=1 makes the Python workspace do the same."""
+    monkeypatch.setenv('IMP_SK_LEGACY', '1')
+    for B, N0, N1, iters in ((40, 700, 650, 20), (400, 80, 40, 20)):
+        g = torch.Generator().manual_seed(300 + N0)
+        dist = torch.randn(B, N0, N1, generator=g) * 3
+        for b in range(B):
+            idx = torch.randperm(min(N0, N1), generator=g)[: min(N0, N1) // 2]
+            dist[b, idx, idx] += 12.0
+        bin_score = torch.tensor(1.3)
+        ref = imp_oracle.sink_algorithm(dist, bin_score, iters)
+        ri0, ri1, rm0, rm1 = imp_oracle.compute_matches(ref, 0.2)
+        ldd = (N1 + 3) // 4 * 4
+        dd = torch.zeros(B, N0, ldd, device=DEV)
+        dd[:, :, :N1] = dist.to(DEV)
+        ws = ops.SinkhornWorkspace(B, N0, N1, DEV, storage='fp32')
+        assert ws.q_store is None
+        ops.sinkhorn(dd, ldd, bin_score.to(DEV), iters, ws)
+        sc = ws.scores().cpu()
+        assert float((sc[:, :-1, :-1] - ref[:, :-1, :-1]).abs().max()) < 1e-5
+        i0, i1, m0, m1 = ops.matches(ws.row_max, ws.row_arg, ws.col_key, 0.2, N0, N1, B)
+        assert torch.equal(i0.cpu(), ri0) and torch.equal(i1.cpu(), ri1)
+
+
 def test_instnorm_small_linear_kenc_gather():
     B, N, C_ = 3, 777, 512
     h = _rand(B, N, C_, seed=20) * 3 + 1.5
