@@ -148,3 +148,52 @@ def test_sinkhorn_24bit_copy_format_restated_on_cpu():
     assert float(np.abs((dec[nz].astype(np.float64) - p[nz]) / p[nz]).max()) <= 128.5 * 2.0 ** -23
     assert np.all(dec[~nz] == 0)
     assert np.all(np.diff(dec[np.argsort(p, kind='stable')]) >= 0), 'the encoding must be monotone'
+
+
+def test_pose_overlap_matches_sequential_execution():
+    """PoseOverlap (host pose estimation off the GPU's critical path): results equal the sequential calls, come back in
+    submission order, exceptions surface through the Future, and the number of in-flight pairs is bounded."""
+    import threading
+    import time
+    import numpy as np
+    from imp_release_b200.pose_overlap import PoseOverlap
+    try:
+        import cv2
+    except ImportError:          # pragma: no cover
+        cv2 = None
+    rng = np.random.default_rng(0)
+    n = 400
+    pairs = []
+    for i in range(12):
+        k0 = rng.uniform(0, 640, (n, 2)).astype(np.float32)
+        H = np.array([[1.0, 0.02 * i, 5.0], [-0.01, 1.0, -3.0], [1e-5, 0.0, 1.0]])
+        k1 = (np.c_[k0, np.ones(n)] @ H.T)
+        k1 = (k1[:, :2] / k1[:, 2:]).astype(np.float32)
+        idx = torch.arange(n)
+        idx[rng.permutation(n)[: n // 3]] = -1                      # unmatched keypoints
+        pairs.append((idx, torch.rand(n, generator=torch.Generator().manual_seed(i)), k0, k1))
+    active, peak = [0], [0]
+    lock = threading.Lock()
+
+    def pose(indices0, mscores0, k0, k1):                              # stands in for eval/pose_estimation.py::estimate_pose
+        with lock:
+            active[0] += 1
+            peak[0] = max(peak[0], active[0])
+        time.sleep(0.01)
+        valid = indices0 >= 0
+        p0, p1 = k0[valid], k1[indices0[valid]]
+        F = cv2.findFundamentalMat(p0, p1, cv2.FM_8POINT)[0] if cv2 is not None else np.cov(p0.T, p1.T)
+        with lock:
+            active[0] -= 1
+        return int(valid.sum()), float(mscores0[valid].sum()), F
+
+    seq = [pose(i.numpy(), s.numpy(), k0, k1) for i, s, k0, k1 in pairs]
+    with PoseOverlap(workers=4, max_pending=6) as po:
+        futs = [po.submit(i, s, pose, k0, k1) for i, s, k0, k1 in pairs]
+        bad = po.submit(pairs[0][0], None, lambda idx, sc: 1 // 0)
+        got = [f.result() for f in futs]
+        with pytest.raises(ZeroDivisionError):
+            bad.result()
+    assert peak[0] > 1, 'the pose calls never overlapped'
+    for a, b in zip(got, seq):
+        assert a[0] == b[0] and a[1] == b[1] and np.allclose(a[2], b[2], rtol=0, atol=0)

@@ -181,3 +181,21 @@ def test_pair_feeder_stages_batches_in_order():
     assert PairFeeder.bytes_of(batches[0]) == 2 * 50 * 256 * 4 + 100 * 4
     with pytest.raises(RuntimeError):
         feeder.next()
+
+
+def test_pose_overlap_async_d2h_of_matches():
+    """PoseOverlap with CUDA tensors: the matches of each pair reach the worker through pinned buffers and a CUDA event,
+    without synchronising the stream; recycled buffers never leak one pair's matches into another."""
+    import numpy as np
+    from imp_release_b200.pose_overlap import PoseOverlap
+    g = torch.Generator().manual_seed(0)
+    pairs = [(torch.randint(-1, 2000, (1000 + 37 * i,), generator=g), torch.rand(1000 + 37 * i, generator=g)) for i in range(20)]
+    with PoseOverlap(workers=3, max_pending=4) as po:
+        futs = []
+        for idx, sc in pairs:
+            a, b = idx.cuda(), sc.cuda()
+            a2 = a * 1 + 0                                  # something enqueued on the stream before the staging
+            futs.append(po.submit(a2, b, lambda i, s: (i.copy(), s.copy())))
+        for (idx, sc), f in zip(pairs, futs):
+            gi, gs = f.result()
+            assert np.array_equal(gi, idx.numpy()) and np.array_equal(gs, sc.numpy())
