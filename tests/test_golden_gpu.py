@@ -127,3 +127,37 @@ def test_full_size_properties():
     for b in range(2):
         v = i0[b][i0[b] >= 0]
         assert v.numel() == v.unique().numel()                                                  # injective
+
+
+def test_full_size_batch_properties():
+    """BASELINE.json configs[1] at full size (64 pairs x N = 2000, 9 iterations, `model(data)`): the path bench.py times.
+    No CPU oracle run at this size; size-independent properties instead: every iteration's matches form a partial
+    permutation with scores in (0.2, 1], the streaming Sinkhorn meets the column marginals exactly (the loop ends on a column
+    update), and the default 24-bit copy agrees with fp32 storage to the documented 1e-3."""
+    from imp_release_b200 import ops
+    nl, B, N = 9, 64, 2000
+    net = DGNNS(cfg(nl))
+    net.load_state_dict(synth.make_state_dict('DGNNS', nl, seed=7), strict=True)
+    net = net.cuda().eval()
+    data = cuda(synth.make_pair_batch(seed=1, batch=B, n0=N, n1=N))
+    with torch.no_grad():
+        out = net(data)
+    assert len(out['indices0']) == nl and out['indices0'][-1].shape == (B, N)
+    assert int((out['indices0'][-1] >= 0).sum()) > 50000
+    for i0, m0 in zip(out['indices0'], out['mscores0']):
+        valid = i0 >= 0
+        assert bool((m0[valid] > 0.2).all()) and float(m0.max()) <= 1.0 + 1e-5 and float(m0.min()) >= 0.0
+        key = (i0 + torch.arange(B, device='cuda')[:, None] * (N + 1))[valid]        # (pair, matched column) must be unique
+        assert key.numel() == key.unique().numel()
+    dist = torch.randn(B, N, N, device='cuda', generator=torch.Generator('cuda').manual_seed(5)) * 3
+    res = {}
+    for storage in ('fp24', 'fp32'):
+        ws = ops.SinkhornWorkspace(B, N, N, 'cuda', storage=storage)
+        assert ws.q_store is not None, 'the full-size batch must take the streaming path'
+        ops.sinkhorn(dist, N, net.bin_score.data, 20, ws, write_scores=True)
+        sc = ws.scores()
+        cols = sc.sum(1)
+        assert float((cols[:, :-1] - 1).abs().max()) < 1e-4 and float((cols[:, -1] - (N + 1)).abs().max()) < 1e-1, storage
+        res[storage] = sc[:, :-1, :-1].clone()
+        del ws, sc
+    assert float((res['fp24'] - res['fp32']).abs().max()) < 1e-3
