@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12, which libimp_b200.so links a
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libimp_b200.so')
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class ImpLibraryError(RuntimeError):
@@ -44,7 +44,8 @@ class AttnArgs(C.Structure):
 class AttnColsumArgs(C.Structure):
     _fields_ = [('q', c_vp), ('k', c_vp), ('q_img_stride', c_i64), ('kv_img_stride', c_i64),
                 ('q_row_stride', c_i32), ('kv_row_stride', c_i32), ('n_img', c_i32), ('src_offset', c_i32), ('Nq_max', c_i32), ('Nk_max', c_i32),
-                ('nq', c_vp), ('nk', c_vp), ('lse', c_vp), ('colsum', c_vp)]
+                ('nq', c_vp), ('nk', c_vp), ('lse', c_vp), ('colsum', c_vp), ('q_lo', c_vp), ('k_lo', c_vp), ('scratch', c_vp),
+                ('by_key_image', c_i32), ('_pad', c_i32)]
 
 
 class SinkhornArgs(C.Structure):
@@ -72,6 +73,7 @@ class PoolArgs(C.Structure):
 SIGNATURES = {
     'imp_last_error': (C.c_char_p, []),
     'imp_abi_version': (C.c_int, []),
+    'imp_set_option': (C.c_int, [c_i32, c_i32]),
     'imp_split_planes': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp]),
     'imp_merge_planes': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'imp_gemm': (C.c_int, [C.POINTER(GemmArgs), c_vp]),
@@ -86,8 +88,8 @@ SIGNATURES = {
     'imp_set_profiling': (C.c_int, [c_i32]),
     'imp_sinkhorn_iter_ms': (C.c_float, []),
     'imp_matches': (C.c_int, [C.POINTER(MatchArgs), c_vp]),
-    'imp_dual_softmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
-    'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'imp_dual_softmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_i64, c_i32, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
+    'imp_score_argmax': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp, c_vp]),
     'imp_pool_select': (C.c_int, [C.POINTER(PoolArgs), c_vp]),
     'imp_scatter_matches': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'imp_gather_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),

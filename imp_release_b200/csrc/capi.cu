@@ -14,11 +14,14 @@ int launch_scatter_matches(const long long* idx0, const float* ms0, int ld_sub, 
                            cudaStream_t st);
 int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
                         unsigned long long* col_key, float* row_mass, float* col_mass, int N0, int N1, int batch,
-                        cudaStream_t st);
+                        const int* n0s, const int* n1s, cudaStream_t st);
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
-                        int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st);
+                        int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, const int* n0s, const int* n1s,
+                        cudaStream_t st);
 long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage);
 void sinkhorn_set_profiling(int on);
+void sinkhorn_set_resident(int on);
+void attention_set_variant(int v);
 float sinkhorn_iter_ms();
 }  // namespace imp
 
@@ -28,6 +31,14 @@ extern "C" {
 
 IMP_API const char* imp_last_error(void) { return imp::last_error(); }
 IMP_API int imp_abi_version(void) { return IMP_B200_ABI_VERSION; }
+
+IMP_API int imp_set_option(int32_t key, int32_t value) {
+  switch (key) {
+    case IMP_OPT_SK_RESIDENT: imp::sinkhorn_set_resident(value); return 0;
+    case IMP_OPT_ATTN_VARIANT: imp::attention_set_variant(value); return 0;
+    default: imp::set_error("imp_set_option: unknown key %d", key); return 2;
+  }
+}
 
 IMP_API int imp_split_planes(const float* x, const float* addend, void* hi, void* lo, int64_t n, void* stream) {
   return imp::launch_split_planes(x, addend, hi, lo, n, ST(stream));
@@ -64,13 +75,16 @@ IMP_API int imp_set_profiling(int32_t on) {
 IMP_API float imp_sinkhorn_iter_ms(void) { return imp::sinkhorn_iter_ms(); }
 IMP_API int imp_matches(const imp_match_args* args, void* stream) { return imp::launch_matches(*args, ST(stream)); }
 IMP_API int imp_dual_softmax(const float* dist, int64_t d_bs, int32_t ldd, const float* bin_score, float* P, int64_t p_bs,
-                     int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1, int32_t batch, void* stream) {
-  return imp::launch_dual_softmax(dist, d_bs, ldd, bin_score, P, p_bs, ldp, row_lse, col_lse, N0, N1, batch, ST(stream));
+                     int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1, int32_t batch, const int32_t* n0s,
+                     const int32_t* n1s, void* stream) {
+  return imp::launch_dual_softmax(dist, d_bs, ldd, bin_score, P, p_bs, ldp, row_lse, col_lse, N0, N1, batch, n0s, n1s,
+                                  ST(stream));
 }
 IMP_API int imp_score_argmax(const float* P, int64_t p_bs, int32_t ldp, float* row_max, int32_t* row_arg, uint64_t* col_key,
-                     float* row_mass, float* col_mass, int32_t N0, int32_t N1, int32_t batch, void* stream) {
+                     float* row_mass, float* col_mass, int32_t N0, int32_t N1, int32_t batch, const int32_t* n0s,
+                     const int32_t* n1s, void* stream) {
   return imp::launch_score_argmax(P, p_bs, ldp, row_max, row_arg, reinterpret_cast<unsigned long long*>(col_key),
-                                  row_mass, col_mass, N0, N1, batch, ST(stream));
+                                  row_mass, col_mass, N0, N1, batch, n0s, n1s, ST(stream));
 }
 IMP_API int imp_pool_select(const imp_pool_args* args, void* stream) { return imp::launch_pool_select(*args, ST(stream)); }
 IMP_API int imp_scatter_matches(const int64_t* idx0, const float* ms0, int32_t ld_sub, const int32_t* gids0, const int32_t* gids1,

@@ -35,4 +35,18 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 
 int num_sms();
 
+// cudaFuncSetAttribute state (dynamic shared memory limit, carve-out) is PER DEVICE: a launcher configures its kernels the
+// first time it runs on each device of the process, not once per process.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  bool first() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const unsigned long long bit = 1ull << (dev & 63);
+    if (mask & bit) return false;
+    mask |= bit;
+    return true;
+  }
+};
+
 }  // namespace imp

@@ -213,11 +213,10 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
   // 8-channel variant is opt-in (IMP_IN_VARIANT=0) only.
   if (aligned && variant == 0 && (size_t)Nmax * 8 * sizeof(float) <= 100 * 1024) {
     auto kern = instnorm_slab_kernel<8, 2>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
       IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-      configured = true;
     }
     kern<<<dim3(C / 8, batch), INS_THREADS, (size_t)Nmax * 8 * sizeof(float), st>>>(
         H, h_bs, ldh, ns, Nmax, eps, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), o_bs, ldo, relu);
@@ -226,10 +225,9 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
   }
   if (aligned && (size_t)Nmax * 16 * sizeof(float) <= 200 * 1024) {
     auto kern = instnorm_slab_kernel<16, 1>;
-    static bool configured = false;
-    if (!configured) {
+    static DeviceOnce configured;
+    if (configured.first()) {
       IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      configured = true;
     }
     kern<<<dim3(C / 16, batch), INS_THREADS, (size_t)Nmax * 16 * sizeof(float), st>>>(
         H, h_bs, ldh, ns, Nmax, eps, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), o_bs, ldo, relu);

@@ -381,10 +381,9 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
 
   const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float) + 4 * 32 * 144;
   auto kern = gemm_f16split_kernel<BN, STAGES, BK>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
   }
   p.tiles_n = (g.N + BN - 1) / BN;
   p.tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;

@@ -15,10 +15,13 @@ __device__ __forceinline__ unsigned long long pack_key(float val, int idx) {
 
 // rows: one warp per row over the non-dustbin block [N0, N1]
 __global__ void row_argmax_kernel(const float* __restrict__ P, long long p_bs, int ldp, float* __restrict__ row_max,
-                                  int* __restrict__ row_arg, float* __restrict__ row_mass, int N0, int N1) {
+                                  int* __restrict__ row_arg, float* __restrict__ row_mass, int N0max, int N1max,
+                                  const int* __restrict__ n0s, const int* __restrict__ n1s) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (i >= N0) return;
+  const int N0 = N0max;  // output stride
+  const int n0 = n0s ? n0s[b] : N0max, N1 = n1s ? n1s[b] : N1max;
+  if (i >= n0) return;
   const float* row = P + b * p_bs + (long long)i * ldp;
   float best = -FLT_MAX, mass = 0.f;
   int bj = 0x7fffffff;
@@ -49,13 +52,14 @@ __global__ void row_argmax_kernel(const float* __restrict__ P, long long p_bs, i
 
 // columns: thread per column over a slab of rows, merged with a packed atomicMax (lowest row wins ties)
 __global__ void col_argmax_kernel(const float* __restrict__ P, long long p_bs, int ldp,
-                                  unsigned long long* __restrict__ col_key, float* __restrict__ col_mass, int N0,
-                                  int N1, int rows_per_slab) {
+                                  unsigned long long* __restrict__ col_key, float* __restrict__ col_mass, int N0max,
+                                  int N1max, const int* __restrict__ n0s, const int* __restrict__ n1s, int rows_per_slab) {
   const int b = blockIdx.z;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= N1) return;
+  const int N1 = N1max;  // output stride
+  if (j >= (n1s ? n1s[b] : N1max)) return;
   const int i0 = blockIdx.y * rows_per_slab;
-  const int i1 = min(i0 + rows_per_slab, N0);
+  const int i1 = min(i0 + rows_per_slab, n0s ? n0s[b] : N0max);
   float best = -FLT_MAX, mass = 0.f;
   int bi = 0;
   for (int i = i0; i < i1; ++i) {
@@ -74,14 +78,14 @@ __global__ void col_argmax_kernel(const float* __restrict__ P, long long p_bs, i
 
 int launch_score_argmax(const float* P, long long p_bs, int ldp, float* row_max, int* row_arg,
                         unsigned long long* col_key, float* row_mass, float* col_mass, int N0, int N1, int batch,
-                        cudaStream_t st) {
+                        const int* n0s, const int* n1s, cudaStream_t st) {
   if (batch == 0 || N0 == 0 || N1 == 0) return 0;
   IMP_CUDA_OK(cudaMemsetAsync(col_key, 0, (size_t)batch * N1 * sizeof(unsigned long long), st));
   if (col_mass) IMP_CUDA_OK(cudaMemsetAsync(col_mass, 0, (size_t)batch * N1 * sizeof(float), st));
-  row_argmax_kernel<<<dim3((N0 + 7) / 8, batch), 256, 0, st>>>(P, p_bs, ldp, row_max, row_arg, row_mass, N0, N1);
+  row_argmax_kernel<<<dim3((N0 + 7) / 8, batch), 256, 0, st>>>(P, p_bs, ldp, row_max, row_arg, row_mass, N0, N1, n0s, n1s);
   const int slab = 64;
   col_argmax_kernel<<<dim3((N1 + 127) / 128, (N0 + slab - 1) / slab, batch), 128, 0, st>>>(P, p_bs, ldp, col_key,
-                                                                                           col_mass, N0, N1, slab);
+                                                                                           col_mass, N0, N1, n0s, n1s, slab);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -93,9 +97,11 @@ __device__ __forceinline__ float padded_at(const float* __restrict__ dist, int l
 }
 
 __global__ void ds_row_lse_kernel(const float* __restrict__ dist, long long d_bs, int ldd,
-                                  const float* __restrict__ bin_score, float* __restrict__ row_lse, int N0, int N1) {
+                                  const float* __restrict__ bin_score, float* __restrict__ row_lse, int N0max, int N1max,
+                                  const int* __restrict__ n0s, const int* __restrict__ n1s) {
   const int b = blockIdx.y;
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int N0 = n0s ? n0s[b] : N0max, N1 = n1s ? n1s[b] : N1max;
   if (i > N0) return;
   const float bin = *bin_score;
   const float* d = dist + b * d_bs;
@@ -105,13 +111,15 @@ __global__ void ds_row_lse_kernel(const float* __restrict__ dist, long long d_bs
   float s = 0.f;
   for (int j = lane_id(); j <= N1; j += 32) s += expf(padded_at(d, ldd, bin, i, j, N0, N1) - m);
   s = warp_sum(s);
-  if (lane_id() == 0) row_lse[(long long)b * (N0 + 1) + i] = m + logf(s);
+  if (lane_id() == 0) row_lse[(long long)b * (N0max + 1) + i] = m + logf(s);
 }
 
 __global__ void ds_col_lse_kernel(const float* __restrict__ dist, long long d_bs, int ldd,
-                                  const float* __restrict__ bin_score, float* __restrict__ col_lse, int N0, int N1) {
+                                  const float* __restrict__ bin_score, float* __restrict__ col_lse, int N0max, int N1max,
+                                  const int* __restrict__ n0s, const int* __restrict__ n1s) {
   const int b = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N0 = n0s ? n0s[b] : N0max, N1 = n1s ? n1s[b] : N1max;
   if (j > N1) return;
   const float bin = *bin_score;
   const float* d = dist + b * d_bs;
@@ -125,33 +133,37 @@ __global__ void ds_col_lse_kernel(const float* __restrict__ dist, long long d_bs
       s += expf(v - m);
     }
   }
-  col_lse[(long long)b * (N1 + 1) + j] = m + logf(s);
+  col_lse[(long long)b * (N1max + 1) + j] = m + logf(s);
 }
 
 __global__ void ds_apply_kernel(const float* __restrict__ dist, long long d_bs, int ldd,
                                 const float* __restrict__ bin_score, const float* __restrict__ row_lse,
-                                const float* __restrict__ col_lse, float* __restrict__ P, long long p_bs, int ldp, int N0,
-                                int N1) {
+                                const float* __restrict__ col_lse, float* __restrict__ P, long long p_bs, int ldp, int N0max,
+                                int N1max, const int* __restrict__ n0s, const int* __restrict__ n1s) {
   const int b = blockIdx.z;
   const int i = blockIdx.y;
   const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= ldp) return;
+  const int N0 = n0s ? n0s[b] : N0max, N1 = n1s ? n1s[b] : N1max;
   float out = 0.f;
-  if (j <= N1) {
+  if (i <= N0 && j <= N1) {
     const float x = padded_at(dist + b * d_bs, ldd, *bin_score, i, j, N0, N1);
     // exp(log_softmax_row + log_softmax_col)
-    out = expf((x - row_lse[(long long)b * (N0 + 1) + i]) + (x - col_lse[(long long)b * (N1 + 1) + j]));
+    out = expf((x - row_lse[(long long)b * (N0max + 1) + i]) + (x - col_lse[(long long)b * (N1max + 1) + j]));
   }
   P[b * p_bs + (long long)i * ldp + j] = out;
 }
 
+// per-sample sizes n0s / n1s (may be NULL): sample b scores its leading n0s[b] x n1s[b] block (+ dustbins right behind
+// it, like a stand-alone call on that block would); everything outside is written as 0
 int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float* bin_score, float* P, long long p_bs,
-                        int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, cudaStream_t st) {
+                        int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, const int* n0s, const int* n1s,
+                        cudaStream_t st) {
   if (batch == 0) return 0;
-  ds_row_lse_kernel<<<dim3((N0 + 1 + 7) / 8, batch), 256, 0, st>>>(dist, d_bs, ldd, bin_score, row_lse, N0, N1);
-  ds_col_lse_kernel<<<dim3((N1 + 1 + 127) / 128, batch), 128, 0, st>>>(dist, d_bs, ldd, bin_score, col_lse, N0, N1);
+  ds_row_lse_kernel<<<dim3((N0 + 1 + 7) / 8, batch), 256, 0, st>>>(dist, d_bs, ldd, bin_score, row_lse, N0, N1, n0s, n1s);
+  ds_col_lse_kernel<<<dim3((N1 + 1 + 127) / 128, batch), 128, 0, st>>>(dist, d_bs, ldd, bin_score, col_lse, N0, N1, n0s, n1s);
   ds_apply_kernel<<<dim3((ldp + 255) / 256, N0 + 1, batch), 256, 0, st>>>(dist, d_bs, ldd, bin_score, row_lse, col_lse, P,
-                                                                          p_bs, ldp, N0, N1);
+                                                                          p_bs, ldp, N0, N1, n0s, n1s);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }

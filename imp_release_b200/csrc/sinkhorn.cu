@@ -616,10 +616,23 @@ static bool sk_resident_geometry(int batch, int R, int ldp, int* rows_per_cta, i
   return (long long)batch * cpm <= wave && sm <= (size_t)SKR_SMEM_BUDGET;
 }
 
+// Run-time switch for the shared-memory-resident kernel (default on; IMP_SK_RESIDENT=0 or imp_set_option turn it off so
+// that small problems take the streaming kernels too -- the parity tests use this to put the model-level fixtures
+// through the path the big batches run).
+static int g_sk_resident = -1;
+static bool sk_resident_enabled() {
+  if (g_sk_resident < 0) {
+    const char* e = getenv("IMP_SK_RESIDENT");
+    g_sk_resident = e ? (atoi(e) != 0) : 1;
+  }
+  return g_sk_resident != 0;
+}
+void sinkhorn_set_resident(int on) { g_sk_resident = on ? 1 : 0; }
+
 long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage) {
   const int R = N0max + 1, C = N1max + 1;
   if (batch <= 0 || N0max <= 0 || N1max <= 0 || C < 64 || C > 4096) return 0;
-  if (sk_resident_geometry(batch, R, (C + 3) & ~3, nullptr, nullptr, nullptr)) return 0;
+  if (sk_resident_enabled() && sk_resident_geometry(batch, R, (C + 3) & ~3, nullptr, nullptr, nullptr)) return 0;
   const int bpe = storage == IMP_SK_STORE_F16 ? 2 : (storage == IMP_SK_STORE_F24 ? 3 : 4);
   return (long long)R * ((C + 15) & ~15) * bpe;
 }
@@ -653,8 +666,8 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   const int R = a.N0max + 1;
   const size_t row_bytes = (size_t)a.ldp * sizeof(float);
   const size_t fixed = 2 * row_bytes + 2 * 64 * sizeof(uint64_t);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_ITER>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
@@ -662,7 +675,6 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_INIT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_ITER>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     IMP_CUDA_OK(cudaFuncSetAttribute(sk_ring_kernel<NV, SK_FINAL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    configured = true;
   }
   const int chunk = sk_chunk_matrices((size_t)R * row_bytes, a.batch);
   const int iters = a.iters;
@@ -671,20 +683,16 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
   IMP_CUDA_OK(cudaMemsetAsync(a.colbuf, 0, (size_t)a.batch * a.ldp * sizeof(float), st));  // col[0]
 
   {  // small problems: everything resident in shared memory, one cooperative launch
-    static int use_resident = -1;
-    if (use_resident < 0) {
-      const char* e = getenv("IMP_SK_RESIDENT");
-      use_resident = e ? atoi(e) : 1;
-    }
+    static bool coop_ok = true;  // cleared when a cooperative launch is refused (profiler / MPS)
+    const bool use_resident = sk_resident_enabled() && coop_ok;
     int rpc, ctas_per_mat;
     size_t smem_res;
     const bool fits = sk_resident_geometry(a.batch, R, a.ldp, &rpc, &ctas_per_mat, &smem_res);
     if (use_resident && fits) {
-      static bool conf = false;
-      if (!conf) {
+      static DeviceOnce conf;
+      if (conf.first()) {
         IMP_CUDA_OK(cudaFuncSetAttribute(sk_resident_kernel<NV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SKR_SMEM_BUDGET));
         IMP_CUDA_OK(cudaFuncSetAttribute(sk_resident_kernel<NV>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        conf = true;
       }
       int max_blocks = 0;
       IMP_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, sk_resident_kernel<NV>, SKS_THREADS, smem_res));
@@ -706,7 +714,7 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
                                         smem_res, st) == cudaSuccess)
           return 0;
         (void)cudaGetLastError();  // cooperative launch unavailable (e.g. under a profiler / MPS): use the streaming path
-        use_resident = 0;
+        coop_ok = false;
       }
     }
   }

@@ -809,8 +809,8 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
                   (reinterpret_cast<uintptr_t>(a.q_store) & 15) == 0,
               "sinkhorn: q_store needs %zu bytes per matrix (16-byte aligned), got %lld", (size_t)R * q_row,
               (long long)a.q_batch_stride);
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;
+  if (configured.first()) {
     auto conf = [](const void* f) -> cudaError_t {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, SKQ_SMEM_BUDGET);
       if (e != cudaSuccess) return e;
@@ -822,7 +822,6 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
     IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, false, true>));
     IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, false>));
     IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, true>));
-    configured = true;
   }
   SkqParams p;
   p.dist = a.dist; p.dist_bs = a.dist_batch_stride; p.ldd = a.ldd; p.bin_score = a.bin_score;

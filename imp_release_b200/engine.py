@@ -95,6 +95,9 @@ class Workspace:
         # high-precision attention: "lo" planes of the Q|K|V projections (and of the compacted K|V)
         self.qkv_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
         self.kvc_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
+        # EIMP pooling: fp32-level row LSE of the stashed attention + per-head scratch of the column sums
+        self.lse_x: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
+        self.cs_scratch: Optional[torch.Tensor] = None
         # keypoint encoder scratch
         self.k_in = torch.zeros(T, 4, **f32)
         self.k_a = torch.zeros(T, 64, **f32)
@@ -108,6 +111,16 @@ class Workspace:
         if store[name] is None:
             store[name] = torch.zeros(self.n_img * self.Np, 2 * D, dtype=torch.float16, device=self.H.device)
         return store[name]
+
+    def lse_exact(self, name: str) -> torch.Tensor:
+        if self.lse_x[name] is None:
+            self.lse_x[name] = torch.zeros(self.n_img, HEADS, self.Np, dtype=torch.float32, device=self.H.device)
+        return self.lse_x[name]
+
+    def colsum_scratch(self) -> torch.Tensor:
+        if self.cs_scratch is None:
+            self.cs_scratch = torch.empty(self.n_img, HEADS, self.Np, dtype=torch.float32, device=self.H.device)
+        return self.cs_scratch
 
     def qkv_lo_buf(self, name: str) -> torch.Tensor:
         if self.qkv_lo[name] is None:
@@ -124,13 +137,18 @@ class RunState:
         self.key_cnt: Optional[torch.Tensor] = None   # [2B] int32 kept keys per image (EIMP), None = all
         self.key_ids: Optional[torch.Tensor] = None   # [2B, Np] int32 sorted kept ids
         self.stash_cnt = {'self': None, 'cross': None}  # key counts the stashed K (and LSE) were built with
+        self.stash_ok = {'self': False, 'cross': False}   # a non-sharing layer of this type has run on THIS state
 
 
 class Engine:
-    def __init__(self, pk: PackedModel, names: List[str], high_precision_attention: bool = False):
+    def __init__(self, pk: PackedModel, names: List[str], high_precision_attention: bool = False,
+                 stash_lo: bool = False):
         self.pk = pk
         self.names = names
         self.hp = high_precision_attention
+        # EIMP: non-sharing layers also keep the "lo" planes of Q and K, so that the pooling statistics (attention
+        # received per key) can be recomputed at fp32 level even when the layers themselves use single fp16 operands
+        self.stash_lo = stash_lo and not high_precision_attention
         self._ws: Dict[tuple, Workspace] = {}
 
     def workspace(self, n_img: int, Np: int, device) -> Workspace:
@@ -182,13 +200,19 @@ class Engine:
         lse = ws.lse[name]
         base = buf.data_ptr()
         hp = self.hp
-        buf_lo = ws.qkv_lo_buf(name) if hp else None
-        base_lo = buf_lo.data_ptr() if hp else None
-        mode = ops.OUT_SPLIT if hp else ops.OUT_F16
+        keep_lo = hp or (self.stash_lo and not L['sharing'])     # this call writes lo planes
+        buf_lo = ws.qkv_lo_buf(name) if keep_lo else None
+        base_lo = buf_lo.data_ptr() if hp else None              # ... and the attention kernel consumes them
+        mode = ops.OUT_SPLIT if keep_lo else ops.OUT_F16
         if not L['sharing']:
             ops.gemm(ws.X, L['Wqkv'], M=T, N=3 * D, K1=D, a_row_stride=D, b_row_stride=D, bias=L['bqkv'],
                      out_mode=mode, out0=buf, out1=buf_lo, out_row_stride=3 * D)
+            st.stash_ok[name] = True
         else:
+            if not st.stash_ok[name]:
+                # the reference fails with a shape error here (prob of another size / None, nets/layers.py:211-214)
+                raise RuntimeError(f'sharing layer {li} ({name}) has no attention stashed for inputs of this shape: run the '
+                                   f'preceding non-sharing {name} layer on the same keypoint sets first')
             ops.gemm(ws.X, L['Wv'], M=T, N=D, K1=D, a_row_stride=D, b_row_stride=D, bias=L['bv'],
                      out_mode=mode, out0=buf, out1=buf_lo, out_row_stride=3 * D, out_offset=2 * D)
         k_lo = v_lo = None
@@ -197,7 +221,7 @@ class Engine:
             if hp:
                 k_lo, v_lo = base_lo + 2 * D, base_lo + 2 * 2 * D
         else:
-            planes = [(buf, ws.kv_compact(name))] + ([(buf_lo, ws.kv_compact(name, lo=True))] if hp else [])
+            planes = [(buf, ws.kv_compact(name))] + ([(buf_lo, ws.kv_compact(name, lo=True))] if keep_lo else [])
             for src, kvc in planes:
                 src3 = src.view(n_img, Np, 3 * D)
                 dst3 = kvc.view(n_img, Np, 2 * D)
@@ -225,17 +249,37 @@ class Engine:
                  out_mode=ops.OUT_SPLIT_RESID, out0=ws.X.hi, out1=ws.X.lo, out_row_stride=D, res=ws.X)
 
     def received_attention(self, st: RunState, name: str, out: torch.Tensor):
-        """Un-normalised attention received by the (kept) keys, indexed by key position (nets/adgm.py:424-427)."""
+        """Un-normalised attention received by the (kept) keys of every image, indexed by key position and stored in the
+        row of the KEY image (nets/adgm.py:424-427: prob.sum over heads and queries).  Recomputed from the stashed Q, K
+        of the last non-sharing layer of this type.  With lo planes available (EIMP models, or attention_precision =
+        'high') scores are formed at fp32 level with a matching row LSE -- the pooling rule compares these sums with
+        their own median, so fp16 scores would flip tokens near it."""
         ws = st.ws
+        if not st.stash_ok[name]:
+            raise RuntimeError(f'no {name}-attention stashed for inputs of this shape (pool() follows forward_one_layer())')
         buf = ws.qkv[name]
         base = buf.data_ptr()
-        if st.key_ids is None or ws.kvc[name] is None or st.stash_cnt[name] is None:
+        lo = (self.hp or self.stash_lo) and ws.qkv_lo[name] is not None
+        base_lo = ws.qkv_lo[name].data_ptr() if lo else None
+        compact = not (st.key_ids is None or ws.kvc[name] is None or st.stash_cnt[name] is None)
+        if not compact:
             k_ptr, kv_rs, nk = base + 2 * D, 3 * D, st.n_tok
+            k_lo = base_lo + 2 * D if lo else None
         else:
             k_ptr, kv_rs, nk = ws.kvc[name].data_ptr(), 2 * D, st.stash_cnt[name]
-        ops.attention_colsum(base, k_ptr, n_img=ws.n_img, src_offset=(st.B if name == 'cross' else 0), Nq_max=ws.Np,
-                             Nk_max=ws.Np, nq=st.n_tok, nk=nk, lse=ws.lse[name], colsum=out, q_row_stride=3 * D,
-                             kv_row_stride=kv_rs)
+            k_lo = ws.kvc_lo[name].data_ptr() if lo else None
+        off = st.B if name == 'cross' else 0
+        lse = ws.lse[name]
+        if lo and not self.hp:
+            # the stashed LSE belongs to the fp16 scores of the layer; the split-precision scores need their own
+            # (high-precision attention pass: only its LSE output is used, O goes to the free message buffer)
+            lse = ws.lse_exact(name)
+            ops.attention(base, k_ptr, k_ptr + 2 * D, n_img=ws.n_img, src_offset=off, Nq_max=ws.Np, Nk_max=ws.Np, nq=st.n_tok,
+                          nk=nk, shared=False, lse=lse, out=ws.A, q_row_stride=3 * D, kv_row_stride=kv_rs, q_lo=base_lo,
+                          k_lo=k_lo, v_lo=k_lo + 2 * D)
+        ops.attention_colsum(base, k_ptr, n_img=ws.n_img, src_offset=off, Nq_max=ws.Np, Nk_max=ws.Np, nq=st.n_tok, nk=nk,
+                             lse=lse, colsum=out, q_row_stride=3 * D, kv_row_stride=kv_rs, q_lo=base_lo, k_lo=k_lo,
+                             scratch=ws.colsum_scratch(), by_key_image=True)
 
     # ------------------------------------------------------------------ scoring
     def project(self, st: RunState, ni: int):

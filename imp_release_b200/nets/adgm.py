@@ -34,14 +34,12 @@ class AdaGMN(GM):
         """Attention received per (kept) key: a_self[img], a_cross[img] indexed by key position of image img."""
         ws = st.ws
         dev = ws.H.device
-        cs_self = torch.empty(ws.n_img, ws.Np, dtype=torch.float32, device=dev)
-        cs_cross = torch.empty(ws.n_img, ws.Np, dtype=torch.float32, device=dev)
+        a_self = torch.empty(ws.n_img, ws.Np, dtype=torch.float32, device=dev)
+        a_cross = torch.empty(ws.n_img, ws.Np, dtype=torch.float32, device=dev)
         eng = self.engine()
-        eng.received_attention(st, 'self', cs_self)
-        eng.received_attention(st, 'cross', cs_cross)
-        # cross launch row `img` holds the sums over the keys of the OTHER image of the pair
-        a_cross = torch.cat([cs_cross[st.B:], cs_cross[:st.B]], 0).contiguous()
-        return cs_self, a_cross
+        eng.received_attention(st, 'self', a_self)
+        eng.received_attention(st, 'cross', a_cross)      # rows already belong to the key image
+        return a_self, a_cross
 
     def produce_matches(self, data, p=0.2, mscore_th=0.1, uncertainty_ratio=1., **kwargs):
         desc0, desc1 = data['descriptors0'], data['descriptors1']
@@ -97,9 +95,9 @@ class AdaGMN(GM):
                 st.key_ids, st.key_cnt = ids_out, cnt_out
         if last_sk is not None and st.key_ids is not None and nI > self.first_it_to_update and sk is last_sk and n0s is not None:
             c0, c1 = int(n0s[B - 1]), int(n1s[B - 1])
-            scores = [last_sk.P[B - 1:B, :c0 + 1, :c1 + 1]]
+            scores = [last_sk.P[B - 1:B, :c0 + 1, :c1 + 1].clone()]      # the workspace is cached and reused: hand out a copy
         elif last_sk is not None:
-            scores = [last_sk.scores()[B - 1:B] if nI > self.first_it_to_update else last_sk.scores()]
+            scores = [(last_sk.scores()[B - 1:B] if nI > self.first_it_to_update else last_sk.scores()).clone()]
         else:
             scores = [None]
         zero, one = torch.zeros([], device=dev), torch.ones([], device=dev)
@@ -132,6 +130,8 @@ class AdaGMN(GM):
             if not isinstance(h, AttentionStash):
                 raise TypeError('pool() expects the attention handles returned by this model (model.self_prob0, ...)')
         N0, N1 = pred_score.shape[1] - 1, pred_score.shape[2] - 1
+        if (N0, N1) != (st.N0, st.N1):
+            raise RuntimeError(f'pool(): pred_score is {N0} x {N1} but the stashed attention belongs to {st.N0} x {st.N1} keypoints')
         dev = pred_score.device
         Np = st.ws.Np
         sk = self._last_sk

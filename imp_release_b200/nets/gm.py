@@ -25,6 +25,16 @@ class AttentionStash:
         return f'AttentionStash({self.name}, queries of image {self.side})'
 
 
+class _ScoreHolder:
+    """What the dual-softmax scorer hands to the EIMP loop in place of a SinkhornWorkspace."""
+
+    def __init__(self, scores, row_mass, col_mass):
+        self.P, self.row_mass, self.col_mass = scores, row_mass, col_mass
+
+    def scores(self):
+        return self.P
+
+
 class GM(nn.Module):
     default_config = {                 # nets/gm.py:30-44
         'descriptor_dim': 256,
@@ -65,7 +75,7 @@ class GM(nn.Module):
         if self.attention_precision not in ('fp16', 'high'):
             raise ValueError("attention_precision must be 'fp16' or 'high'")
         # second B200-specific knob: how softmax(M) is stored for the Sinkhorn iteration sweeps of big batches
-        # ('fp32' | 'fp24' | 'fp16', include/imp_b200.h IMP_SK_STORE_*); None = library default (IMP_SK_STORAGE or 'fp24')
+        # ('fp32' | 'fp24' | 'fp16', include/imp_b200.h IMP_SK_STORE_*); None = library default (IMP_SK_STORAGE or 'fp32')
         self.sinkhorn_storage = self.config.get('sinkhorn_storage', None)
         if self.sinkhorn_storage not in (None, 'fp32', 'fp24', 'fp16'):
             raise ValueError("sinkhorn_storage must be 'fp32', 'fp24' or 'fp16'")
@@ -101,7 +111,8 @@ class GM(nn.Module):
             sd = {k: v for k, v in self.state_dict().items()}
             n_gnn = len(self.gnn.layers)
             self._engine = Engine(PackedModel(sd, self.n_layers, self.gnn.sharing_layers), self.gnn.names,
-                                  high_precision_attention=(self.attention_precision == 'high'))
+                                  high_precision_attention=(self.attention_precision == 'high'),
+                                  stash_lo=getattr(self, 'with_ada', False))
             assert n_gnn >= 2 * self.n_layers
             self._engine_key = key
         return self._engine
@@ -210,10 +221,13 @@ class GM(nn.Module):
             i0, i1, m0, m1 = ops.matches(sk.row_max, sk.row_arg, sk.col_key, p, N0, N1, B, n0s=n0s, n1s=n1s)
             self._last_sk = sk
             return sk.scores(), i0, i1, m0, m1, sk
-        scores = ops.dual_softmax(dist, ldd, self.bin_score.data, N0, N1, B)
-        rmx, rarg, ckey = ops.score_argmax(scores, N0, N1)
-        i0, i1, m0, m1 = ops.matches(rmx, rarg, ckey, p, N0, N1, B)
-        return scores, i0, i1, m0, m1, None
+        # with_sinkhorn=False (eval_imp.py --use_dual_softmax): same contract, masses from the arg-max pass
+        scores = ops.dual_softmax(dist, ldd, self.bin_score.data, N0, N1, B, n0s=n0s, n1s=n1s,
+                                  dist_batch_stride=dist_batch_stride)
+        am = ops.score_argmax(scores, N0, N1, want_mass=want_mass, n0s=n0s, n1s=n1s)
+        i0, i1, m0, m1 = ops.matches(am[0], am[1], am[2], p, N0, N1, B, n0s=n0s, n1s=n1s)
+        holder = _ScoreHolder(scores, am[3] if want_mass else None, am[4] if want_mass else None)
+        return scores, i0, i1, m0, m1, holder
 
     def produce_matches(self, data, p=0.2, only_last=False, **kwargs):
         """GM.produce_matches (nets/gm.py:145-247): all GNN layers, then scoring of every iteration (or the last)."""
@@ -337,7 +351,8 @@ class GM(nn.Module):
             ops.sinkhorn(dist, dist.stride(1), bin_t.float(), iteration, sk, dist_batch_stride=dist.stride(0))
             self._last_sk = sk
             return sk.scores()
-        return ops.dual_softmax(dist, dist.stride(1), bin_t.float(), N0, N1, B)
+        self._last_sk = None
+        return ops.dual_softmax(dist, dist.stride(1), bin_t.float(), N0, N1, B, dist_batch_stride=dist.stride(0))
 
     def compute_matches(self, scores, p=0.2):
         """nets/gm.py:305-320."""

@@ -152,7 +152,10 @@ def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int,
 
 def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, lse, colsum,
                      q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
-                     kv_img_stride: Optional[int] = None):
+                     kv_img_stride: Optional[int] = None, q_lo=None, k_lo=None, scratch: Optional[torch.Tensor] = None,
+                     by_key_image: bool = False):
+    """Attention received per key.  Row `img` of `colsum` belongs to the QUERY image img (its keys are those of image
+    (img + src_offset) % n_img) unless by_key_image.  q_lo / k_lo: split-precision scores (fp32 level)."""
     a = AttnColsumArgs()
     a.q, a.k = _p(q), _p(k)
     a.q_row_stride, a.kv_row_stride = q_row_stride, kv_row_stride
@@ -161,7 +164,12 @@ def attention_colsum(q, k, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: 
     a.n_img, a.src_offset, a.Nq_max, a.Nk_max = n_img, src_offset, Nq_max, Nk_max
     a.nq, a.nk = ptr(nq), ptr(nk)
     a.lse, a.colsum = ptr(lse), ptr(colsum)
-    with _Span('attention_colsum', 1, 2.0 * 64 * 4 * n_img * Nq_max * Nk_max):
+    a.q_lo, a.k_lo = _p(q_lo), _p(k_lo)
+    if scratch is None:
+        scratch = torch.empty(n_img, 4, Nk_max, dtype=torch.float32, device=colsum.device)
+    a.scratch = ptr(scratch)
+    a.by_key_image = int(by_key_image)
+    with _Span('attention_colsum', 2, (3 if q_lo is not None else 1) * 2.0 * 64 * 4 * n_img * Nq_max * Nk_max):
         check(_lib.load().imp_attention_colsum(C.byref(a), stream_ptr()), 'imp_attention_colsum')
 
 
@@ -191,8 +199,24 @@ SK_STORAGE = {'fp32': 0, 'fp16': 1, 'fp24': 2}
 
 
 def default_sk_storage() -> str:
-    """Storage of softmax(M) for the Sinkhorn iteration sweeps (include/imp_b200.h, IMP_SK_STORE_*)."""
-    return os.environ.get('IMP_SK_STORAGE', 'fp24')
+    """Storage of softmax(M) for the Sinkhorn iteration sweeps (include/imp_b200.h, IMP_SK_STORE_*).  'fp32' is the
+    reference recurrence on exact fp32 probabilities (match indices bit-exact with the reference on every fixture);
+    'fp24' / 'fp16' move fewer bytes per sweep at the price of ~1e-5 / ~1e-3 relative noise on the scaling vectors
+    (opt-in: a near-tie below that level can pick the other candidate)."""
+    return os.environ.get('IMP_SK_STORAGE', 'fp32')
+
+
+OPT_SK_RESIDENT, OPT_ATTN_VARIANT = 1, 2
+
+
+def set_option(key: int, value: int):
+    check(_lib.load().imp_set_option(key, value), 'imp_set_option')
+
+
+def set_sinkhorn_resident(on: bool):
+    """False: small Sinkhorn problems take the streaming kernels of the big batches too (parity tests of that path).
+    Workspaces built before the switch keep their old geometry -- create them afterwards."""
+    set_option(OPT_SK_RESIDENT, int(bool(on)))
 
 
 class SinkhornWorkspace:
@@ -266,34 +290,40 @@ def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int
     return i0, i1, m0, m1
 
 
-def score_argmax(P: torch.Tensor, N0: int, N1: int, want_mass: bool = False):
-    """Row/col arg-max (and masses) over P[:, :N0, :N1] for an arbitrary (possibly strided-row) fp32 score tensor."""
+def score_argmax(P: torch.Tensor, N0: int, N1: int, want_mass: bool = False, n0s=None, n1s=None):
+    """Row/col arg-max (and masses) over P[:, :N0, :N1] (per sample: [:n0s[b], :n1s[b]]) for an arbitrary (possibly
+    strided-row) fp32 score tensor."""
     batch = P.shape[0]
     if P.stride(2) != 1:
         P = P.contiguous()
     dev = P.device
-    row_max = torch.empty(batch, N0, dtype=torch.float32, device=dev)
-    row_arg = torch.empty(batch, N0, dtype=torch.int32, device=dev)
+    mk = torch.zeros if n0s is not None else torch.empty        # rows / columns beyond a sample's size stay 0
+    row_max = mk(batch, N0, dtype=torch.float32, device=dev)
+    row_arg = mk(batch, N0, dtype=torch.int32, device=dev)
     col_key = torch.empty(batch, N1, dtype=torch.int64, device=dev)
-    row_mass = torch.empty(batch, N0, dtype=torch.float32, device=dev) if want_mass else None
+    row_mass = mk(batch, N0, dtype=torch.float32, device=dev) if want_mass else None
     col_mass = torch.empty(batch, N1, dtype=torch.float32, device=dev) if want_mass else None
     with _Span('score_argmax', 2):
         check(_lib.load().imp_score_argmax(ptr(P), P.stride(0), P.stride(1), ptr(row_max), ptr(row_arg), ptr(col_key),
-                                           ptr(row_mass), ptr(col_mass), N0, N1, batch, stream_ptr()), 'imp_score_argmax')
+                                           ptr(row_mass), ptr(col_mass), N0, N1, batch, ptr(n0s), ptr(n1s), stream_ptr()),
+              'imp_score_argmax')
     if want_mass:
         return row_max, row_arg, col_key, row_mass, col_mass
     return row_max, row_arg, col_key
 
 
-def dual_softmax(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, N0: int, N1: int, batch: int):
+def dual_softmax(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, N0: int, N1: int, batch: int, n0s=None, n1s=None,
+                 dist_batch_stride: Optional[int] = None):
     dev = dist.device
     ldp = (N1 + 1 + 3) // 4 * 4
     P = torch.empty(batch, N0 + 1, ldp, dtype=torch.float32, device=dev)
     row_lse = torch.empty(batch, N0 + 1, dtype=torch.float32, device=dev)
     col_lse = torch.empty(batch, N1 + 1, dtype=torch.float32, device=dev)
+    d_bs = dist_batch_stride if dist_batch_stride is not None else N0 * ldd
     with _Span('dual_softmax', 3):
-        check(_lib.load().imp_dual_softmax(ptr(dist), N0 * ldd, ldd, ptr(bin_score), ptr(P), (N0 + 1) * ldp, ldp,
-                                           ptr(row_lse), ptr(col_lse), N0, N1, batch, stream_ptr()), 'imp_dual_softmax')
+        check(_lib.load().imp_dual_softmax(ptr(dist), d_bs, ldd, ptr(bin_score), ptr(P), (N0 + 1) * ldp, ldp,
+                                           ptr(row_lse), ptr(col_lse), N0, N1, batch, ptr(n0s), ptr(n1s), stream_ptr()),
+              'imp_dual_softmax')
     return P[:, :, :N1 + 1]
 
 

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IMP_B200_ABI_VERSION 2
+#define IMP_B200_ABI_VERSION 3
 #if defined(__GNUC__)
 #define IMP_API __attribute__((visibility("default")))
 #else
@@ -30,6 +30,13 @@ extern "C" {
 
 IMP_API const char* imp_last_error(void);
 IMP_API int imp_abi_version(void);
+
+/* Run-time knobs of the library (process-wide; no reference counterpart -- the reference has no kernels to tune).
+ * IMP_OPT_SK_RESIDENT: 1 (default) = small Sinkhorn problems run the shared-memory-resident kernel, 0 = every problem
+ * takes the streaming kernels the big batches use (what the parity tests switch on to cover that path with the
+ * reference fixtures).  IMP_OPT_ATTN_VARIANT: attention kernel variant (0 = default), for tuning runs. */
+enum { IMP_OPT_SK_RESIDENT = 1, IMP_OPT_ATTN_VARIANT = 2 };
+IMP_API int imp_set_option(int32_t key, int32_t value);
 
 /* ---- fp32 <-> hi/lo planes (boundary conversions; `addend` may be NULL) -------------------------------------- */
 /* desc + keypoint encoding, nets/gms.py:171-172 */
@@ -76,7 +83,10 @@ typedef struct imp_attn_args {
 } imp_attn_args;
 IMP_API int imp_attention(const imp_attn_args* args, void* stream);
 
-/* attention received per source token, nets/adgm.py:424-427, :557-560 (prob.sum(1).sum(1)) */
+/* attention received per source token, nets/adgm.py:424-427, :557-560 (prob.sum(1).sum(1)).  Deterministic (no
+ * floating-point atomics): per-head sums go to `scratch`, a second kernel adds the four heads in fixed order.
+ * With q_lo / k_lo (fp16 "lo" planes of Q and K, same strides) the scores are formed with the 3-product split, i.e. at
+ * fp32 level -- pass an `lse` computed the same way (imp_attention in high-precision mode writes one). */
 typedef struct imp_attn_colsum_args {
   const void *q, *k;
   int64_t q_img_stride, kv_img_stride;
@@ -84,7 +94,12 @@ typedef struct imp_attn_colsum_args {
   int32_t n_img, src_offset, Nq_max, Nk_max;
   const int32_t *nq, *nk;
   const float* lse;
-  float* colsum; /* [n_img, Nk_max], indexed by QUERY image; row img = attention received by keys of image src(img) */
+  float* colsum;  /* [n_img, Nk_max]; row = QUERY image img (sums over the keys of image src(img) = (img + src_offset) % n_img),
+                     or row = the KEY image src(img) when by_key_image != 0 */
+  const void *q_lo, *k_lo; /* optional, both or none */
+  float* scratch;          /* [n_img, 4, Nk_max] workspace */
+  int32_t by_key_image;
+  int32_t _pad;
 } imp_attn_colsum_args;
 IMP_API int imp_attention_colsum(const imp_attn_colsum_args* args, void* stream);
 
@@ -161,15 +176,17 @@ typedef struct imp_match_args {
 } imp_match_args;
 IMP_API int imp_matches(const imp_match_args* args, void* stream);
 
-/* dual-softmax scorer, nets/layers.py:20-24 (with_sinkhorn=False) */
+/* dual-softmax scorer, nets/layers.py:20-24 (with_sinkhorn=False).  n0s / n1s (device, [batch], may be NULL): sample b
+ * scores its leading n0s[b] x n1s[b] block with the dustbin row / column right behind it (EIMP's kept subsets,
+ * nets/adgm.py:441-447); the rest of P[b] is written as 0. */
 IMP_API int imp_dual_softmax(const float* dist, int64_t dist_batch_stride, int32_t ldd, const float* bin_score, float* P,
                      int64_t p_batch_stride, int32_t ldp, float* row_lse, float* col_lse, int32_t N0, int32_t N1,
-                     int32_t batch, void* stream);
+                     int32_t batch, const int32_t* n0s, const int32_t* n1s, void* stream);
 /* row / column arg-max (and optional masses, may be NULL) of an existing score matrix over P[:, :N0, :N1]
  * (compute_matches / pool on caller-provided scores) */
 IMP_API int imp_score_argmax(const float* P, int64_t p_batch_stride, int32_t ldp, float* row_max, int32_t* row_arg,
                      uint64_t* col_key, float* row_mass, float* col_mass, int32_t N0, int32_t N1, int32_t batch,
-                     void* stream);
+                     const int32_t* n0s, const int32_t* n1s, void* stream);
 
 /* ---- EIMP adaptive pooling, nets/adgm.py:463-500 and :552-605 ------------------------------------------------
  * keep = { i : mass_i >= thresh } U { i : a_self_i >= lower_median(a_self[pids]) } U { i : a_cross_i >= ... },

@@ -20,3 +20,14 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if 'gpu' in item.keywords:
             item.add_marker(skip)
+
+
+@pytest.fixture(params=['default', 'streaming'])
+def sk_path(request):
+    """Model-level parity tests run twice: with the library's default Sinkhorn dispatch (small problems -> the
+    shared-memory-resident kernel) and with that kernel switched off, so that the SAME reference fixtures also pin the
+    streaming kernels (csrc/sinkhorn_q.cu) that the full-size batches of bench.py run."""
+    from imp_release_b200 import ops
+    ops.set_sinkhorn_resident(request.param != 'streaming')
+    yield request.param
+    ops.set_sinkhorn_resident(True)

@@ -118,5 +118,105 @@ def main():
     print('wrote', path, os.path.getsize(path), 'bytes')
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json headline shape (N = 2000, 9 iterations): the unmodified reference on two pairs; the GPU test runs
+# these two pairs inside a 64-pair batch (tests/test_golden_gpu.py::test_headline_shape_matches_reference).
+N2000_CASES = {
+    # name: (kind, n_layers, weight seed, bin_score, data seed, batch, n0, n1)
+    'dgnns_n2000': ('DGNNS', 9, 7, 1.0, 41, 2, 2000, 2000),          # configs[1]: model(data), Sinkhorn every iteration
+    'adagmn_n2000': ('AdaGMN', 9, 7, 8.0, 42, 2, 2000, 2000),        # configs[2]: pruning 2000 -> ~600
+}
+
+
+def main_n2000():
+    ns = refimport.load()
+    cls = {'GM': ns.GM, 'DGNNS': ns.DGNNS, 'AdaGMN': ns.AdaGMN}
+    blob = {}
+    for name, (kind, nl, wseed, bin_score, dseed, B, n0, n1) in N2000_CASES.items():
+        sd = synth.make_state_dict(kind, nl, seed=wseed, bin_score=bin_score)
+        data = synth.make_pair_batch(seed=dseed, batch=B, n0=n0, n1=n1)
+        m = cls[kind](cfg(nl)).eval()
+        m.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            out = m(data)
+        i0 = torch.stack(out['indices0']).numpy()
+        assert i0.max() < 32768
+        blob[f'{name}/indices0'] = i0.astype(np.int16)
+        blob[f'{name}/mscores0'] = torch.stack(out['mscores0']).numpy()
+        blob[f'{name}/weights_checksum'] = np.float64(synth.state_dict_checksum(sd))
+        blob[f'{name}/data_checksum'] = np.float64(sum(synth.tensor_checksum(v) for k, v in sorted(data.items())))
+        if 'scores' in out and out['scores'][-1] is not None:
+            blob[f'{name}/scores_last_shape'] = np.array(out['scores'][-1].shape)
+        print(name, 'matches per iteration', [(i >= 0).sum().item() for i in out['indices0']])
+    path = os.path.join(OUT, 'reference_n2000.npz')
+    np.savez_compressed(path, **blob)
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The reference's own iterative drivers (eval/matching.py:16-276, UNMODIFIED) on the reference model, with the pose
+# solver replaced by the deterministic tests/matching_driver.py::PoseStub.  Recorded: every compute_matches / pool
+# result the driver saw, plus what it returned.
+MATCHING_CASES = {
+    # name: (driver, kind, weight seed, bin_score, data seed, n0, n1, stop criteria, with_uncertainty)
+    'mi_dgnns_stop': ('matching_iterative', 'DGNNS', 23, 1.0, 51, 800, 760, {'match': 0.7, 'pose': 1.5}, False),
+    'mi_dgnns_full': ('matching_iterative', 'DGNNS', 23, 1.0, 52, 640, 700, {}, False),
+    'miu_adagmn_stop': ('matching_iterative_uncertainty', 'AdaGMN', 29, 6.0, 53, 800, 760, {'match': 0.7, 'pose': 1.5}, True),
+    'miu_adagmn_full': ('matching_iterative_uncertainty', 'AdaGMN', 29, 6.0, 54, 700, 780, {}, False),
+}
+MATCHING_NI = 15
+
+
+def run_matching_case(case, model, driver_fn, pose, **extra):
+    from tests import matching_driver as md
+    driver, kind, wseed, bin_score, dseed, n0, n1, stop, unc = case
+    data = md.make_driver_data(synth, dseed, n0, n1)
+    tr = md.Trace(model)
+    kw = dict(data=data, model=model, nI=MATCHING_NI, match_ratio=0.1, min_kpts=25, error_th=1.0, stop_criteria=stop, **extra)
+    if driver == 'matching_iterative_uncertainty':
+        kw['with_uncertainty'] = unc
+    with torch.no_grad():
+        ret = driver_fn(**kw)
+    tr.close()
+    return tr, ret
+
+
+def main_matching():
+    from tests import matching_driver as md
+    ns = refimport.load()
+    ref_matching = refimport.load_matching(ns)
+    cls = {'DGNNS': ns.DGNNS, 'AdaGMN': ns.AdaGMN}
+    blob = {}
+    for name, case in MATCHING_CASES.items():
+        driver, kind, wseed, bin_score = case[:4]
+        sd = synth.make_state_dict(kind, MATCHING_NI, seed=wseed, bin_score=bin_score)
+        m = cls[kind](cfg(MATCHING_NI)).eval()
+        m.load_state_dict(sd, strict=True)
+        pose = md.PoseStub()
+        ref_matching.estimate_pose = pose                      # the only patch: the (randomised) RANSAC solver
+        tr, ret = run_matching_case(case, m, getattr(ref_matching, driver), pose)
+        blob.update(tr.to_blob(name))
+        i0, m0, n_it = (ret[0], ret[1], ret[4]) if driver == 'matching_iterative' else (ret[4], ret[5], ret[8])
+        blob[f'{name}/ret_indices0'] = np.asarray(i0).astype(np.int32)
+        blob[f'{name}/ret_mscores0'] = np.asarray(m0).astype(np.float32)
+        blob[f'{name}/ret_iterations'] = np.int64(n_it)
+        blob[f'{name}/pose_calls'] = np.array(pose.n_matches, dtype=np.int64)
+        if driver == 'matching_iterative_uncertainty':
+            blob[f'{name}/ret_n_pts'] = np.array([len(ret[0]), len(ret[1])])
+        print(name, 'events', len(tr.events), 'pose calls', pose.n_matches, 'stopped after', n_it,
+              'pool sizes', [(len(e[2]), len(e[3])) for e in tr.events if e[0] == 'pool'])
+    path = os.path.join(OUT, 'reference_matching.npz')
+    np.savez_compressed(path, **blob)
+    print('wrote', path, os.path.getsize(path), 'bytes')
+
+
 if __name__ == '__main__':
-    main()
+    assert refimport.available(), 'reference tree missing'
+    which = sys.argv[1:] or ['base', 'n2000', 'matching']
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    if 'base' in which:
+        main()
+    if 'n2000' in which:
+        main_n2000()
+    if 'matching' in which:
+        main_matching()

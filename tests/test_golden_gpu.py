@@ -21,7 +21,7 @@ def cuda(d):
 
 
 @pytest.mark.parametrize('name', list(CASES))
-def test_models_match_reference_outputs(name):
+def test_models_match_reference_outputs(name, sk_path):
     kind, nl, wseed, bin_score, dseed, B, n0, n1, kw = CASES[name]
     sd = synth.make_state_dict(kind, nl, seed=wseed, bin_score=bin_score)
     data = synth.make_pair_batch(seed=dseed, batch=B, n0=n0, n1=n1)
@@ -45,7 +45,7 @@ def test_models_match_reference_outputs(name):
 
 
 @pytest.mark.parametrize('kind,bin_score', [('DGNNS', 1.0), ('AdaGMN', 6.0)])
-def test_layer_api_matches_reference_outputs(kind, bin_score):
+def test_layer_api_matches_reference_outputs(kind, bin_score, sk_path):
     """The call sequence of eval/matching.py:45-61 (+ pool, :254) against the reference's own results."""
     nl, n0, n1 = 9, 330, 300
     tag = f'layerapi_{kind.lower()}'
@@ -161,3 +161,68 @@ def test_full_size_batch_properties():
         res[storage] = sc[:, :-1, :-1].clone()
         del ws, sc
     assert float((res['fp24'] - res['fp32']).abs().max()) < 1e-3
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json headline shape: the unmodified reference's outputs at N = 2000 (tests/golden/reference_n2000.npz),
+# reproduced INSIDE the batch that bench.py times (pairs 0 and 1 of a 64-pair batch are the reference's two pairs)
+from tests.golden.make_golden import MATCHING_CASES, MATCHING_NI, N2000_CASES, run_matching_case  # noqa: E402
+from tests import matching_driver as md  # noqa: E402
+
+G2K = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_n2000.npz'))
+GMT = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_matching.npz'))
+
+
+@pytest.mark.parametrize('name,batch', [('dgnns_n2000', 64), ('adagmn_n2000', 64), ('dgnns_n2000', 2)])
+def test_headline_shape_matches_reference(name, batch):
+    """configs[1] / configs[2] at full size: 64 pairs x N = 2000 x 9 iterations through `model(data)`; pairs 0, 1 must
+    reproduce the reference's match indices exactly (every iteration) and its scores to 1e-3.  The batch takes the
+    streaming Sinkhorn kernels and full-wave attention / GEMM grids -- the very path bench.py measures."""
+    from imp_release_b200 import ops
+    kind, nl, wseed, bin_score, dseed, B, n0, n1 = N2000_CASES[name]
+    sd = synth.make_state_dict(kind, nl, seed=wseed, bin_score=bin_score)
+    data = synth.make_pair_batch(seed=dseed, batch=B, n0=n0, n1=n1)
+    if batch > B:
+        rest = synth.make_pair_batch(seed=dseed + 1000, batch=batch - B, n0=n0, n1=n1)
+        data = {k: (torch.cat([v, rest[k]], 0) if k not in ('image0', 'image1') else v) for k, v in data.items()}
+    net = CLS[kind](cfg(nl))
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(cuda(data))
+    if batch > B:
+        ws = ops.SinkhornWorkspace(batch, n0, n1, 'cuda')
+        assert ws.q_store is not None and ws.storage == ops.SK_STORAGE['fp32'], 'the batch must take the streaming fp32 path'
+    i0 = torch.stack(out['indices0'])[:, :B].cpu().numpy()
+    m0 = torch.stack(out['mscores0'])[:, :B].cpu().numpy()
+    ref_i = G2K[f'{name}/indices0'].astype(np.int64)
+    assert i0.shape == ref_i.shape
+    assert np.array_equal(i0, ref_i), f'{(i0 != ref_i).sum()} of {ref_i.size} match indices differ from the reference'
+    assert np.abs(m0 - G2K[f'{name}/mscores0']).max() < 1e-3
+    assert int((ref_i[-1] >= 0).sum()) > 1000
+
+
+@pytest.mark.parametrize('name', list(MATCHING_CASES))
+def test_iterative_drivers_match_reference_trace(name, sk_path):
+    """eval/matching.py's iterative drivers (restated in tests/matching_driver.py and proven equal to the unmodified
+    ones on CPU) over the CUDA classes: every scoring's match indices, every pool() decision (kept ids of both images),
+    the stop iteration and the returned matches equal what the unmodified drivers saw on the reference model."""
+    from tests.test_oracle_golden import check_trace
+    case = MATCHING_CASES[name]
+    driver, kind, wseed, bin_score = case[:4]
+    sd = synth.make_state_dict(kind, MATCHING_NI, seed=wseed, bin_score=bin_score)
+    m = CLS[kind](cfg(MATCHING_NI))
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().eval()
+    pose = md.PoseStub()
+    _, _, _, _, dseed, n0, n1, stop, unc = case
+    data = md.make_driver_data(synth, dseed, n0, n1, device='cuda')
+    tr = md.Trace(m)
+    kw = dict(data=data, model=m, nI=MATCHING_NI, match_ratio=0.1, min_kpts=25, error_th=1.0, stop_criteria=stop,
+              estimate_pose=pose, normalize_keypoints=normalize_keypoints)
+    if driver == 'matching_iterative_uncertainty':
+        kw['with_uncertainty'] = unc
+    with torch.no_grad():
+        ret = getattr(md, driver)(**kw)
+    tr.close()
+    check_trace(name, tr, ret, driver, pose, G=GMT, tol=1e-3)

@@ -31,7 +31,7 @@ def compare(out, ref, tol=1e-3):
 
 
 @pytest.mark.parametrize('N0,N1,B', [(512, 512, 1)])
-def test_gm_config1(N0, N1, B):
+def test_gm_config1(N0, N1, B, sk_path):
     """BASELINE.json configs[0]: GM.forward, N=512, 3 iterations."""
     c = cfg(3)
     sd = synth.make_state_dict('GM', 3, seed=5)
@@ -48,7 +48,7 @@ def test_gm_config1(N0, N1, B):
 
 @pytest.mark.parametrize('N0,N1,B,nl,only_last', [(500, 460, 2, 9, False), (300, 260, 1, 9, True), (1000, 960, 1, 9, False),
                                                    (700, 900, 1, 15, True)])
-def test_dgnns(N0, N1, B, nl, only_last):
+def test_dgnns(N0, N1, B, nl, only_last, sk_path):
     c = cfg(nl)
     sd = synth.make_state_dict('DGNNS', nl, seed=7)
     data = synth.make_pair_batch(seed=3, batch=B, n0=N0, n1=N1)
@@ -60,7 +60,7 @@ def test_dgnns(N0, N1, B, nl, only_last):
 
 
 @pytest.mark.parametrize('N0,N1,B,seed', [(500, 460, 2, 7), (1000, 960, 1, 11)])
-def test_adagmn_batched_pruning(N0, N1, B, seed):
+def test_adagmn_batched_pruning(N0, N1, B, seed, sk_path):
     """BASELINE.json configs[2] shape: EIMP with adaptive pooling (bin_score raised so that pruning happens)."""
     c = cfg(9, n_min_tokens=256)
     sd = synth.make_state_dict('AdaGMN', 9, seed=seed, bin_score=6.0)
@@ -98,7 +98,7 @@ def test_cuda_graph_replay_matches_eager():
 
 
 @pytest.mark.parametrize('N0,N1,B,nl', [(5, 9, 1, 3), (129, 64, 3, 4), (2300, 2210, 1, 3)])
-def test_dgnns_edge_sizes(N0, N1, B, nl):
+def test_dgnns_edge_sizes(N0, N1, B, nl, sk_path):
     """Tiny, odd-batch and > 2048-keypoint pairs (longest Sinkhorn row variant, > 16 key tiles)."""
     c = cfg(nl)
     sd = synth.make_state_dict('DGNNS', nl, seed=13)

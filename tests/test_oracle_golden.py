@@ -95,3 +95,81 @@ def test_sinkhorn_against_independent_fp64_log_domain():
     ref = torch.exp(Z + f[:, :, None] + gg[:, None, :])
     assert float((out.double() - ref).abs().max() / ref.abs().max()) < 1e-4
     assert torch.equal(out[:, :-1, :-1].argmax(-1), ref[:, :-1, :-1].argmax(-1))
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# BASELINE.json headline shape (N = 2000, 9 iterations) and the iterative drivers of eval/matching.py
+from tests.golden.make_golden import MATCHING_CASES, MATCHING_NI, N2000_CASES, run_matching_case  # noqa: E402
+from tests import matching_driver as md  # noqa: E402
+from oracle import refimport  # noqa: E402
+
+G2K = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_n2000.npz'))
+GM_ = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_matching.npz'))
+
+
+@pytest.mark.parametrize('name', list(N2000_CASES))
+def test_headline_shape_oracle_matches_reference(name):
+    kind, nl, wseed, bin_score, dseed, B, n0, n1 = N2000_CASES[name]
+    sd = synth.make_state_dict(kind, nl, seed=wseed, bin_score=bin_score)
+    data = synth.make_pair_batch(seed=dseed, batch=B, n0=n0, n1=n1)
+    assert synth.state_dict_checksum(sd) == pytest.approx(float(G2K[f'{name}/weights_checksum']), rel=1e-12), 'RNG drift'
+    assert sum(synth.tensor_checksum(v) for k, v in sorted(data.items())) == pytest.approx(float(G2K[f'{name}/data_checksum']), rel=1e-12)
+    with torch.no_grad():
+        out = imp_oracle.Oracle(kind, cfg(nl), sd).forward(data)
+    assert np.array_equal(torch.stack(out['indices0']).numpy(), G2K[f'{name}/indices0'].astype(np.int64))
+    assert np.abs(torch.stack(out['mscores0']).numpy() - G2K[f'{name}/mscores0']).max() < 1e-5
+
+
+def check_trace(name, tr, ret, driver, pose, G=GM_, tol=1e-5, exact_pool=True):
+    """A driver run against the trace the unmodified reference driver + reference model produced."""
+    assert len(tr.events) == int(G[f'{name}/n_events']), 'the driver took a different path (number of scorings / pools)'
+    for k, e in enumerate(tr.events):
+        assert e[0] == str(G[f'{name}/ev{k}/kind']) and e[1] == pytest.approx(float(G[f'{name}/ev{k}/p']), abs=1e-7), f'event {k}'
+        if e[0] == 'matches':
+            assert np.array_equal(e[2], G[f'{name}/ev{k}/a']), f'event {k}: {(e[2] != G[f"{name}/ev{k}/a"]).sum()} match indices differ'
+            assert np.abs(e[3] - G[f'{name}/ev{k}/b']).max() < tol, f'event {k}: match scores'
+        else:
+            assert np.array_equal(e[2], G[f'{name}/ev{k}/a']) and np.array_equal(e[3], G[f'{name}/ev{k}/b']), f'event {k}: kept ids differ'
+    i0, m0, n_it = (ret[0], ret[1], ret[4]) if driver == 'matching_iterative' else (ret[4], ret[5], ret[8])
+    assert int(n_it) == int(G[f'{name}/ret_iterations'])
+    assert np.array_equal(np.asarray(i0), G[f'{name}/ret_indices0'])
+    assert np.abs(np.asarray(m0) - G[f'{name}/ret_mscores0']).max() < tol
+    assert pose.n_matches == G[f'{name}/pose_calls'].tolist()
+    if driver == 'matching_iterative_uncertainty':
+        assert [len(ret[0]), len(ret[1])] == G[f'{name}/ret_n_pts'].tolist()
+
+
+@pytest.mark.parametrize('name', list(MATCHING_CASES))
+def test_restated_drivers_on_oracle_match_reference_drivers(name):
+    """tests/matching_driver.py (restated eval/matching.py loops) driving the ORACLE reproduces what the unmodified
+    drivers saw and returned on the reference model: pins the restated drivers and the oracle's per-layer API
+    (incl. pool and the caller-side compaction) on any box."""
+    case = MATCHING_CASES[name]
+    driver, kind, wseed, bin_score = case[:4]
+    sd = synth.make_state_dict(kind, MATCHING_NI, seed=wseed, bin_score=bin_score)
+    m = imp_oracle.Oracle(kind, cfg(MATCHING_NI), sd)
+    pose = md.PoseStub()
+    tr, ret = run_matching_case(case, m, getattr(md, driver), pose, estimate_pose=pose,
+                                normalize_keypoints=imp_oracle.normalize_keypoints)
+    check_trace(name, tr, ret, driver, pose, tol=5e-5)       # fp32 summation-order drift over up to 30 layers
+
+
+@pytest.mark.skipif(not refimport.available(), reason='needs /root/reference (build container only)')
+def test_restated_drivers_equal_unmodified_drivers_on_reference_model():
+    """Same reference model under the restated loop and under the fixture made by the UNMODIFIED eval/matching.py."""
+    ns = refimport.load()
+    try:
+        for name in ('mi_dgnns_stop', 'miu_adagmn_stop'):
+            case = MATCHING_CASES[name]
+            driver, kind, wseed, bin_score = case[:4]
+            sd = synth.make_state_dict(kind, MATCHING_NI, seed=wseed, bin_score=bin_score)
+            m = {'DGNNS': ns.DGNNS, 'AdaGMN': ns.AdaGMN}[kind](cfg(MATCHING_NI)).eval()
+            m.load_state_dict(sd, strict=True)
+            pose = md.PoseStub()
+            tr, ret = run_matching_case(case, m, getattr(md, driver), pose, estimate_pose=pose,
+                                        normalize_keypoints=ns.layers.normalize_keypoints)
+            check_trace(name, tr, ret, driver, pose, tol=1e-7)
+    finally:
+        import sys
+        for k in [k for k in sys.modules if k == 'nets' or k.startswith('nets.') or k == 'eval' or k.startswith('eval.') or k == 'tools' or k.startswith('tools.')]:
+            del sys.modules[k]

@@ -1,0 +1,51 @@
+"""Time the attention kernel variants at the bench shape (64 pairs x 2 images x 4 heads x 2000^2) with CUDA events and
+check each against the round-1 kernel's output.  Usage: python tools/attn_probe.py [variants...]"""
+import json
+import sys
+
+import torch
+
+sys.path.insert(0, '.')
+from imp_release_b200 import ops  # noqa: E402
+
+
+def t(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+variants = [int(v) for v in sys.argv[1:]] or [3, 10, 12, 13, 14, 23, 24]
+n_img, N = 128, 2000
+g = torch.Generator('cuda').manual_seed(0)
+qkv = (torch.randn(n_img, N, 768, device='cuda', generator=g) * 1.2).half()
+base = qkv.data_ptr()
+lse = torch.zeros(n_img, 4, N, device='cuda')
+out = ops.Planes.empty((n_img, N, 256), 'cuda')
+flops = 4.0 * 64 * 4 * n_img * N * N
+res = {}
+ref = None
+for v in variants:
+    ops.set_option(ops.OPT_ATTN_VARIANT, v)
+    row = {}
+    for shared in (False, True):
+        fn = lambda: ops.attention(base, base + 512, base + 1024, n_img=n_img, src_offset=0, Nq_max=N, Nk_max=N, nq=None, nk=None,
+                                   shared=shared, lse=lse, out=out, q_row_stride=768, kv_row_stride=768)
+        ms = t(fn)
+        row['shared_ms' if shared else 'ms'] = round(ms, 4)
+        if not shared:
+            row['tflops'] = round(flops / ms / 1e9, 1)
+            o = out.float()
+            if ref is None:
+                ref = o.clone()
+            row['max_abs_diff_vs_first'] = float((o - ref).abs().max())
+    res[v] = row
+    print(v, row, flush=True)
+json.dump(res, open('gpurun_out/attn_probe.json', 'w'), indent=1)
