@@ -126,28 +126,178 @@ def cpu_reference_step(n_pairs=1, n=N_KPTS, iters=N_ITERS, repeats=1, seed=1):
     return best
 
 
+REFERENCE_TIME_CAP_S = 150.0
+
+
 def run_reference(args, rank, world):
+    """The reference algorithm on the host cores.  /root/reference does not exist on the GPU box, so this arm runs the
+    oracle port (kind "port": oracle/imp_oracle.py, pinned to the unmodified reference by tests/golden/).  Each step = one
+    forward of ONE pair of the 64-pair batch (per-pair CPU time is flat in batch size); --warmup and
+    --steps are honoured up to a wall-clock cap so that the run ends within a few minutes on slow hosts."""
     if rank != 0:
         return
     torch.set_num_threads(host_cores())
     cores = torch.get_num_threads()
-    for _ in range(min(args.warmup, 1)):
+    t_start = time.perf_counter()
+    n_warm = 0
+    for _ in range(max(0, args.warmup)):
         cpu_reference_step()
-    times = [cpu_reference_step() for _ in range(max(1, min(args.steps, 5)))]
+        n_warm += 1
+        if time.perf_counter() - t_start > REFERENCE_TIME_CAP_S / 5:
+            break
+    times = []
+    for _ in range(max(1, args.steps)):
+        times.append(cpu_reference_step())
+        if time.perf_counter() - t_start > REFERENCE_TIME_CAP_S:
+            break
     ms = 1e3 * sum(times) / len(times)
     value = 1.0 / (ms / 1e3)
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'pairs/s', 'n_gpus': args.gpus,
-        'steps': len(times), 'warmup': min(args.warmup, 1), 'ms_per_step': ms, 'higher_is_better': True,
+        'steps': len(times), 'warmup': n_warm, 'steps_requested': args.steps, 'warmup_requested': args.warmup,
+        'ms_per_step': ms, 'higher_is_better': True,
         'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': f'DGNNS.forward 9 iters, N={N_KPTS}, D=256; each step = a bounded sample of 1 pair of the '
-                               f'{BATCH}-pair batch (per-pair CPU time is flat in batch size, BASELINE.md section 3)'},
+        'config': {'workload': f'BASELINE.json configs[1]: DGNNS.forward (IMP), N={N_KPTS}, D=256, {N_ITERS} iters, Sinkhorn(20)+matches '
+                               f'every iteration; each step = a bounded sample of 1 pair of the {BATCH}-pair batch (per-pair CPU '
+                               f'time is flat in batch size, BASELINE.md section 3)'},
         'cpu_baseline': {'value': value, 'unit': 'pairs/s', 'cores': cores, 'kind': 'port',
-                         'sample': '1 pair per step, oracle/imp_oracle.py (torch CPU fp32, all host threads)'},
+                         'sample': f'{len(times)} steps of 1 pair each (mean), oracle/imp_oracle.py (torch CPU fp32, all host '
+                                   f'threads); time cap {REFERENCE_TIME_CAP_S:.0f} s'},
         'e2e': {'value': value, 'unit': 'pairs/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
     emit(line)
+
+
+# ----------------------------------------------------------------------------------------------- secondary configs
+def _timed(fn, warm, n):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(n):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n
+
+
+def run_secondary(dev, peaks, n_pairs=224):
+    """BASELINE.json configs[2..4] on one GPU (device-resident inputs, CUDA-event timed, >= 2 warm-ups).  configs[3] is the
+    one-pair-per-call evaluation shape of eval/eval_imp.py:155-173 on ONE rank: >= 200 pairs with distinct ragged keypoint
+    counts, 15 iterations, produce_matches(only_last=True)."""
+    out = {}
+    out.update(secondary_eimp(dev))
+    torch.cuda.empty_cache()
+    out.update(secondary_b1(dev, n_pairs))
+    torch.cuda.empty_cache()
+    out.update(secondary_sinkhorn(dev, peaks))
+    return out
+
+
+def secondary_eimp(dev):
+    from imp_release_b200 import AdaGMN
+    from oracle import synth
+    out = {}
+    # ---- configs[2]: EIMP, N = 2000 -> pruned, 9 iterations, batch 128
+    B = 128
+    net = AdaGMN(model_config(9))
+    net.load_state_dict(synth.make_state_dict('AdaGMN', 9, seed=7, bin_score=8.0))
+    net = net.to(dev).eval()
+    data = {k: v.to(dev) for k, v in synth.make_pair_batch(seed=2, batch=B, n0=N_KPTS, n1=N_KPTS).items()}
+    with torch.no_grad():
+        ms = _timed(lambda: net(data), 2, 3)
+    cnt, _ = net._kept
+    out['configs[2] EIMP batch=128 N=2000 9 iters'] = {
+        'pairs_per_s': B / ms * 1e3, 'ms_per_batch': ms, 'kept_keypoints_mean': float(cnt.float().mean()),
+        'kept_min': int(cnt.min()), 'kept_max': int(cnt.max()), 'bin_score': 8.0,
+        'note': 'AdaGMN.forward, bin_score raised to 8 so that the seeded random weights prune (SURVEY.md 8(d))'}
+    return out
+
+
+def secondary_b1(dev, n_pairs=224):
+    from imp_release_b200 import DGNNS
+    from imp_release_b200.graphed import LatencyMatcher
+    from oracle import synth
+    out = {}
+    # ---- configs[3] on one rank: DGNNS 15 iterations, one pair per call, ragged N in [1200, 2000]
+    net = DGNNS(model_config(15))
+    net.load_state_dict(synth.make_state_dict('DGNNS', 15, seed=7))
+    net = net.to(dev).eval()
+    g = torch.Generator().manual_seed(11)
+    sizes = [(int(a), int(b)) for a, b in torch.randint(1200, 2001, (n_pairs, 2), generator=g).tolist()]
+    big = {k: v.to(dev) for k, v in synth.make_pair_batch(seed=5, batch=1, n0=2000, n1=2000, width=1600, height=1200).items()}
+
+    def pair(i):
+        n0, n1 = sizes[i]
+        return {'descriptors0': big['descriptors0'][:, :n0], 'descriptors1': big['descriptors1'][:, :n1],
+                'keypoints0': big['keypoints0'][:, :n0], 'keypoints1': big['keypoints1'][:, :n1],
+                'scores0': big['scores0'][:, :n0], 'scores1': big['scores1'][:, :n1], 'image0': big['image0'], 'image1': big['image1']}
+    pairs = [pair(i) for i in range(n_pairs)]
+
+    def sweep(fn):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = [fn(d) for d in pairs]
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n_pairs, (time.perf_counter() - t0) * 1e3 / n_pairs, res
+    with torch.no_grad():
+        eager = lambda d: net.produce_matches(d, p=0.2, only_last=True)['indices0'][-1]
+        sweep(eager)                                             # warm-up: workspaces of every bucket
+        ms_eager, wall_eager, ref = sweep(eager)
+        lm1 = LatencyMatcher(net, slots=1)
+        t0 = time.perf_counter()
+        sweep(lambda d: lm1(d)['indices0'][-1])                  # builds the graphs (one per 128-keypoint bucket)
+        build_s = time.perf_counter() - t0
+        ms_g1, wall_g1, r1 = sweep(lambda d: lm1(d)['indices0'][-1])
+        lm4 = LatencyMatcher(net, slots=4)
+        sweep(lambda d: lm4.submit(d))
+        ms_g4, wall_g4, tickets = sweep(lambda d: lm4.submit(d))
+        r4 = [lm4.result(t)['indices0'][-1] for t in tickets]
+        torch.cuda.synchronize()
+        same1 = all(torch.equal(a, b) for a, b in zip(ref, r1))
+        same4 = all(torch.equal(a, b) for a, b in zip(ref, r4))
+    out['configs[3] one rank: IMP 15 iters, 1 pair per call, ragged N0,N1 in [1200,2000]'] = {
+        'pairs': n_pairs, 'distinct_shapes': len(set(sizes)),
+        'eager_ms_per_pair': ms_eager, 'eager_wall_ms_per_pair': wall_eager,
+        'graph_1_slot_ms_per_pair': ms_g1, 'graph_1_slot_wall_ms_per_pair': wall_g1,
+        'graph_4_slots_ms_per_pair': ms_g4, 'graph_4_slots_wall_ms_per_pair': wall_g4,
+        'pairs_per_s_4_slots': 1e3 / max(ms_g4, wall_g4),
+        'graphs_captured_1_slot': lm1.captures, 'graphs_captured_4_slots': lm4.captures, 'first_sweep_incl_capture_s': build_s,
+        'graph_results_equal_eager': bool(same1 and same4),
+        'note': 'DGNNS.produce_matches(only_last=True); LatencyMatcher = bucketed (128) static shapes + CUDA-graph replay, '
+                '4 slots = 4 pairs in flight on 4 streams; device-resident inputs; ms = CUDA events, wall = host clock'}
+    return out
+
+
+def secondary_sinkhorn(dev, peaks):
+    from imp_release_b200 import ops
+    out = {}
+    # ---- configs[4]: Sinkhorn only, 2048 x 2048 padded (dist 2047^2), 100 iterations
+    for Bs in (16, 1):
+        N, ld = 2047, 2048
+        dist_ = torch.randn(Bs, N, ld, device=dev, generator=torch.Generator(dev).manual_seed(3)) * 3
+        ws = ops.SinkhornWorkspace(Bs, N, N, dev)
+        bs = torch.tensor(1.0, device=dev)
+        ms = _timed(lambda: ops.sinkhorn(dist_, ld, bs, 100, ws, write_scores=True), 2, 3)
+        mat = 4.0 * Bs * 2048 * 2048
+        streaming = ws.q_store is not None
+        sweeps = 101 if streaming else None          # init + 99 iteration sweeps + final (one sweep per iteration)
+        out[f'configs[4] Sinkhorn-only 2048^2 x 100 iters, batch={Bs}'] = {
+            'ms': ms, 'path': 'streaming kernels, fp32 copy (matrix > L2)' if streaming else 'shared-memory resident, one cooperative launch',
+            'bytes_moved_GBps': (sweeps + 2) * mat / ms / 1e6 if streaming else mat * 2 / ms / 1e6,
+            'frac_of_hbm_peak': ((sweeps + 2) * mat / ms / 1e6 / peaks['hbm_gbs']) if streaming else None,
+            'reference_counting_GBps': 2 * 100 * mat / ms / 1e6,
+            'note': 'bytes_moved = one 4-byte read of the matrix per sweep (+ the init write and the final score write); '
+                    'reference_counting = 2 sweeps per iteration as SURVEY.md 8(d) counts the reference formulation'
+                    if streaming else 'the 16.8 MB matrix is read from HBM once and lives in shared memory for all 100 iterations: '
+                                      'grid-barrier latency bound, HBM traffic is 2 passes'}
+        del ws, dist_
+    return out
 
 
 # ----------------------------------------------------------------------------------------------- GPU arm
@@ -293,32 +443,29 @@ def run_gpu(args, rank, world, local_rank):
         tot, n, work = prof[name]
         avg_s = tot / n / 1e3
         if name.startswith('sinkhorn'):
-            # dominant kernel of the group: skq_iter_kernel, one launch per Sinkhorn iteration.  Its algorithmic traffic
-            #  is ONE sweep of the [B, N0+1, N1+1] fp32 matrix per launch (the reference formulation,
-            # SURVEY.md 8(d), counts two sweeps per iteration; this kernel fuses them).
-            mat = 4.0 * BATCH * (N_KPTS + 1) * (N_KPTS + 1)
+            # dominant kernel of the group: skq_iter_kernel, one launch per Sinkhorn iteration = ONE sweep over the stored
+            # copy of softmax(M) [B, N0+1, roundup16(N1+1)].  `achieved` = bytes that sweep moves / its CUDA-event duration.
+            # With the default fp32 copy this equals the algorithmic figure of SURVEY.md 8(d) per sweep (4 B x (N0+1)(N1+1))
+            # up to 0.7 % of row padding.
             sk_bytes = {'fp32': 4, 'fp24': 3, 'fp16': 2}[sk_storage]
+            ldq = (N_KPTS + 1 + 15) // 16 * 16
+            moved = float(sk_bytes) * BATCH * (N_KPTS + 1) * ldq
+            algo = 4.0 * BATCH * (N_KPTS + 1) * (N_KPTS + 1)
             n_launch = 21           # init + 19 iterations + final (the column arg-max is fused into the final pass)
             it_s = (sk_iter_ms if sk_iter_ms > 0 else (tot / n) / n_launch) / 1e3
-            ach = mat / it_s / 1e9
-            moved = ach * sk_bytes / 4.0 * (2016.0 / 2001.0)       # rows are padded to 16 columns in the stored copy
+            ach = moved / it_s / 1e9
             return {'kernel': f'skq_iter_kernel<{sk_storage}> (one Sinkhorn iteration, 19 of the {n_launch} launches of a scoring)',
                     'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
                     'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'launch_ms': it_s * 1e3,
-                    'storage': {'format': sk_storage, 'bytes_per_element': sk_bytes, 'moved_GBps': moved,
-                                'moved_frac_of_peak': moved / peaks['hbm_gbs'],
-                                'note': 'the iteration sweeps stream a %d-byte copy of softmax(M) (DESIGN.md section 2): `achieved` '
-                                        'counts the ALGORITHMIC 4 B per element, so frac can exceed 1; `moved_GBps` counts the bytes '
-                                        'actually requested from HBM and is the figure to hold against the copy peak' % sk_bytes},
-                    'reference_counting': {'achieved': 2 * ach, 'frac': 2 * ach / peaks['hbm_gbs'],
-                                           'note': '2 sweeps per iteration as the reference algorithm is counted in SURVEY.md 8(d)'},
-                    'whole_scoring': {'ms': tot / n, 'launches': n_launch,
-                                      'algorithmic_GBps': (2 * 20 + 4) * mat / (tot / n / 1e3) / 1e9,
-                                      'note': 'SURVEY.md 8(d) bytes of one scoring (2 sweeps x 20 iterations + init + final) over '
-                                              'the CUDA-event time of the whole imp_sinkhorn call'},
-                    'note': 'achieved = 4 B x B x (N0+1) x (N1+1) per launch / mean CUDA-event duration of the 19 iteration '
-                            'launches of each scoring (events recorded inside libimp_b200.so on the launching stream); '
-                            'peak = STREAM-style copy of ' + peak_src}
+                    'bytes_per_launch': moved, 'algorithmic_bytes_per_launch': algo,
+                    'storage': {'format': sk_storage, 'bytes_per_element': sk_bytes},
+                    'reference_counting': {'GBps': 2 * algo / it_s / 1e9,
+                                           'note': 'side note only: the reference formulation (SURVEY.md 8(d)) sweeps the matrix '
+                                                   'twice per iteration (row pass + column pass); this kernel fuses both into one'},
+                    'whole_scoring': {'ms': tot / n, 'launches': n_launch},
+                    'note': 'achieved = bytes of the stored copy one sweep reads (%d B x B x (N0+1) x roundup16(N1+1)) / mean '
+                            'CUDA-event duration of the 19 iteration launches of each scoring (events recorded inside '
+                            'libimp_b200.so on the launching stream); peak = STREAM-style copy of ' % sk_bytes + peak_src}
         pk = peaks.get('bf16_tflops_sustained', peaks['bf16_tflops'])
         ach = work / n / avg_s / 1e12
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': pk, 'unit': 'TFLOP/s', 'frac': ach / pk,
@@ -334,6 +481,12 @@ def run_gpu(args, rank, world, local_rank):
             key = ('sinkhorn_' + sk_storage) if r['kernel'].startswith('sk') else r['kernel']
             if key in t:
                 r['traffic'] = t[key]
+    secondary = None
+    if world == 1 and not args.no_secondary:
+        del resident, feeder
+        net._engine = None
+        torch.cuda.empty_cache()
+        secondary = run_secondary(dev, peaks)
 
     torch.set_num_threads(host_cores())
     cpu_s = cpu_reference_step(repeats=2) if world == 1 and not args.no_cpu_baseline else None
@@ -348,7 +501,7 @@ def run_gpu(args, rank, world, local_rank):
         'ms_per_step': ms_dev, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
         'dtype': 'f16x3 split (fp32-equivalent) projections/scores, '
                  + ('f16x3 split' if args.attention_precision == 'high' else 'f16') +
-                 ' attention operands, f32 accumulate/softmax/Sinkhorn (iteration sweeps read a ' + sk_storage + ' copy of softmax(M))',
+                 ' attention operands, f32 accumulate/softmax/Sinkhorn (Sinkhorn sweeps read a ' + sk_storage + ' copy of softmax(M))',
         'data': 'synthetic',
         'config': {'workload': f'BASELINE.json configs[1]: DGNNS.forward (IMP), batch={BATCH} pairs/GPU, N={N_KPTS}, D=256, '
                                f'{N_ITERS} iters, Sinkhorn(20)+matches every iteration',
@@ -367,6 +520,7 @@ def run_gpu(args, rank, world, local_rank):
         'attention_tflops_whole_step': att * n_pairs_total / (ms_dev / 1e3) / 1e12,
         'kernels': kernels,
         'cpu_baseline': cpu_baseline,
+        'secondary': secondary,
     }
     emit(line)
     if world > 1:
@@ -397,6 +551,7 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-secondary', action='store_true', help='skip BASELINE.json configs[2..4] (run by default at N=1)')
     ap.add_argument('--attention-precision', default='fp16', choices=['fp16', 'high'],
                     help="'high' = split-precision attention (DESIGN.md section 2); default = the fast fp16 mode")
     ap.add_argument('--sinkhorn-storage', default=None, choices=['fp32', 'fp24', 'fp16'],

@@ -30,7 +30,8 @@ class GemmArgs(C.Structure):
                 ('M', c_i32), ('N', c_i32), ('K1', c_i32), ('K2', c_i32), ('batch', c_i32), ('b_batched', c_i32),
                 ('nsplit', c_i32), ('alpha', c_f32), ('bias', c_vp), ('out_mode', c_i32), ('_pad', c_i32),
                 ('out0', c_vp), ('out1', c_vp), ('out_row_stride', c_i64), ('out_batch_stride', c_i64),
-                ('res_hi', c_vp), ('res_lo', c_vp)]
+                ('res_hi', c_vp), ('res_lo', c_vp), ('stat_partial', c_vp), ('stat_straddle', c_vp), ('stat_ns', c_vp),
+                ('stat_np', c_i32), ('_pad2', c_i32)]
 
 
 class AttnArgs(C.Structure):
@@ -81,6 +82,7 @@ SIGNATURES = {
     'imp_attention_colsum': (C.c_int, [C.POINTER(AttnColsumArgs), c_vp]),
     'imp_instnorm_relu': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp,
                                     c_i64, c_i32, c_vp]),
+    'imp_instnorm_apply': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_f32, c_i32, c_vp, c_vp, c_vp, c_vp]),
     'imp_kenc_input': (C.c_int, [c_vp, c_vp, c_vp, c_i64, c_vp]),
     'imp_small_linear': (C.c_int, [c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i64, c_i32, c_i32, c_vp]),
     'imp_sinkhorn': (C.c_int, [C.POINTER(SinkhornArgs), c_vp]),

@@ -194,8 +194,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           tmem_ld_x32(s_addr + cb, r);
           tmem_wait_ld();
           if (!ragged) {
+            float mx1 = -INFINITY;  // two chains of 3-input maxima (FMNMX3): 16 instructions per 32 columns instead of 32
 #pragma unroll
-            for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(r[c]));
+            for (int c = 0; c < 32; c += 4) {
+              mx = fmaxf(fmaxf(mx, __uint_as_float(r[c])), __uint_as_float(r[c + 1]));
+              mx1 = fmaxf(fmaxf(mx1, __uint_as_float(r[c + 2])), __uint_as_float(r[c + 3]));
+            }
+            mx = fmaxf(mx, mx1);
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c) mx = fmaxf(mx, (cb + c < nvalid) ? __uint_as_float(r[c]) : -INFINITY);
@@ -345,318 +350,6 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 
-// ===============================================================================================================
-// v2 kernel (default for single-fp16 operands).  Same roles as above, restructured around what ncu showed for the first
-// version (tensor pipe 32 %, MUFU 65 %, issue 55 %: CTAs sharing one score buffer fall into lock step, so the MUFU idles
-// while the MMAs of all of them run):
-//  * the score tile is DOUBLE-BUFFERED in TMEM (S0 | S1 | O = 64 + 64 + 64 columns, 256 allocated, 2 CTAs per SM): the
-//    issuer launches S(j+1) = Q K(j+1)^T before it waits for P(j), so the softmax warps always find their next tile ready;
-//  * the score row is read from TMEM ONCE (64 registers): row max with 3-input FMNMX, then the exponentials;
-//  * the softmax warps wait for O += P(j-1) V(j-1) only when a lazy rescale is actually due (max grew by > 2^8);
-//  * EMU of every 16 exponentials are evaluated on the FMA pipe (Cody-Waite range reduction + degree-4 minimax polynomial,
-//    relative error 2.9e-6 -- far below the fp16 rounding of P) instead of MUFU.EX2: at head dim 64 a tile costs twice as
-//    many MUFU cycles as tensor cycles, so the MUFU is the roof; moving ~1/5 of the exponentials balances it against the
-//    issue slots.
-static constexpr int A2_BN = 64;
-static constexpr int A2_STG = 4;
-static constexpr int A2_KV_BYTES = A2_BN * AT_D * 2;
-static constexpr int A2_STAGE_BYTES = 2 * A2_KV_BYTES;
-static constexpr uint32_t A2_COL_O = 2 * A2_BN;
-static constexpr uint32_t A2_TMEM_COLS = 256;
-
-// 2^x for x <= ~8 on the FMA pipe.  t = x + 1.5*2^23 holds round(x) in its low mantissa bits; f = x - round(x) in
-// [-0.5, 0.5]; 2^f by a minimax polynomial with p(0) = 1; the integer part goes straight into the exponent field.
-template <int DEG>
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -125.f);  // below: exponent field would wrap; 2^-125 rounds to 0 in fp16 anyway
-  const float t = x + 12582912.f;
-  const float f = x - (t - 12582912.f);
-  float r;
-  if (DEG == 3) {
-    r = fmaf(0.05500893294811249f, f, 0.24221095442771912f);
-    r = fmaf(r, f, 0.6932829022407532f);
-  } else {
-    r = fmaf(0.009582852013409138f, f, 0.055906426161527634f);
-    r = fmaf(r, f, 0.24024099111557007f);
-    r = fmaf(r, f, 0.6931241750717163f);
-  }
-  r = fmaf(r, f, 1.0f);
-  return __uint_as_float(__float_as_uint(r) + (__float_as_uint(t) << 23));
-}
-__device__ __forceinline__ float fmax3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
-
-template <int EMU, int DEG, bool SHARED>
-__global__ void __launch_bounds__(AT_THREADS, 2)
-attention_v2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                    const __grid_constant__ CUtensorMap tm_v, const AttnKernelParams p) {
-  constexpr int BN = A2_BN, STG = A2_STG;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint8_t* s_q = smem;
-  uint8_t* s_kv = smem + AT_TILE_BYTES;  // stage s: K tile, V tile
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_kv + STG * A2_STAGE_BYTES);
-  uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;
-  uint64_t* kv_empty = kv_full + STG;
-  uint64_t* s_full = kv_empty + STG;  // [2]
-  uint64_t* p_full = s_full + 2;      // [2]
-  uint64_t* o_done = p_full + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(o_done + 1);
-
-  if (smem_u32(smem) & 1023u) __trap();
-  const int warp = threadIdx.x >> 5;
-  const int q0 = blockIdx.x * AT_BM;
-  const int h = blockIdx.y;
-  const int img = blockIdx.z;
-  const int src = (img + p.src_offset) % p.n_img;
-  const int nq = p.nq ? p.nq[img] : p.Nq_max;
-  const int nk = p.nk ? p.nk[src] : p.Nk_max;
-  if (q0 >= nq) return;
-  const int T = (nk + BN - 1) / BN;
-
-  if (warp == 0 && elect_one()) {
-    tma_prefetch_desc(&tm_q);
-    tma_prefetch_desc(&tm_k);
-    tma_prefetch_desc(&tm_v);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < STG; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
-    }
-    for (int b = 0; b < 2; ++b) {
-      mbar_init(&s_full[b], 1);
-      mbar_init(&p_full[b], 128);
-    }
-    mbar_init(o_done, 1);
-    fence_barrier_init();
-  }
-  if (warp == 1) {
-    tmem_alloc(tmem_ptr_smem, A2_TMEM_COLS);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr_smem;
-
-  if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
-    if (elect_one() && T > 0) {
-      mbar_arrive_expect_tx(q_full, AT_TILE_BYTES);
-      tma_load_3d(s_q, &tm_q, q_full, h * AT_D, q0, img);
-      for (int j = 0; j < T; ++j) {
-        const int s = j % STG;
-        mbar_wait(&kv_empty[s], ((j / STG) & 1) ^ 1);
-        uint8_t* st = s_kv + s * A2_STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[s], A2_STAGE_BYTES);
-        tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * BN, src);
-        tma_load_3d(st + A2_KV_BYTES, &tm_v, &kv_full[s], h * AT_D, j * BN, src);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ UMMA issuer
-    if (elect_one() && T > 0) {
-      constexpr uint32_t idesc_qk = make_idesc(FMT_F16, AT_BM, BN, 0, 0);
-      constexpr uint32_t idesc_pv = make_idesc(FMT_F16, AT_BM, AT_D, 0, 1);  // B = V, MN-major
-      const uint32_t q_addr = smem_u32(s_q);
-      mbar_wait(q_full, 0);
-      auto issue_qk = [&](int j) {
-        const int st = j % STG;
-        mbar_wait(&kv_full[st], (j / STG) & 1);
-        tc_fence_after();
-        const uint32_t k_addr = smem_u32(s_kv + st * A2_STAGE_BYTES);
-        const uint32_t d = tmem_base + (j & 1) * BN;
-        // S(j) overwrites the buffer that held P(j-2): the tensor pipe runs this thread's MMAs in issue order, so
-        // O += P(j-2) V(j-2) has read it before
-#pragma unroll
-        for (int kk = 0; kk < AT_D / 16; ++kk)
-          umma_f16_ss(d, make_smem_desc_sw128(q_addr + kk * 32, 16, 1024), make_smem_desc_sw128(k_addr + kk * 32, 16, 1024),
-                      idesc_qk, kk > 0 ? 1u : 0u);
-        umma_commit(&s_full[j & 1]);
-      };
-      issue_qk(0);
-      for (int j = 0; j < T; ++j) {
-        if (j + 1 < T) issue_qk(j + 1);  // runs on the tensor pipe while the softmax warps work on tile j
-        mbar_wait(&p_full[j & 1], (j >> 1) & 1);
-        tc_fence_after();
-        const uint32_t v_addr = smem_u32(s_kv + (j % STG) * A2_STAGE_BYTES) + A2_KV_BYTES;
-        const uint32_t pcol = tmem_base + (j & 1) * BN;
-#pragma unroll
-        for (int kk = 0; kk < BN / 16; ++kk)  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
-          umma_f16_ts(tmem_base + A2_COL_O, pcol + kk * 8, make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024), idesc_pv,
-                      (j > 0 || kk > 0) ? 1u : 0u);
-        umma_commit(&kv_empty[j % STG]);
-        umma_commit(o_done);
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ softmax / correction / epilogue
-    const int quarter = warp & 3;
-    const int row = quarter * 32 + lane_id();
-    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
-    const int qrow = q0 + row;
-    const bool row_ok = qrow < nq;
-    float m_run = -INFINITY, l_run = 0.f;
-    float neg_ref = 0.f;
-    if (SHARED) neg_ref = row_ok ? -p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow] : 0.f;
-
-    for (int j = 0; j < T; ++j) {
-      const uint32_t s_addr = tmem_base + lane_off + (j & 1) * BN;
-      mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-      tc_fence_after();
-      uint32_t r[BN];
-      tmem_ld_x32(s_addr, r);
-      tmem_ld_x32(s_addr + 32, r + 32);
-      tmem_wait_ld();
-      const int nvalid = nk - j * BN;
-      const bool ragged = nvalid < BN;  // warp-uniform: only the last tile of a ragged key set needs masking
-      if (ragged) {
-#pragma unroll
-        for (int c = 0; c < BN; ++c)
-          if (c >= nvalid) r[c] = 0xff800000u;  // -inf: exp -> 0, never the max
-      }
-      if (!SHARED) {
-        float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-        for (int c = 0; c < BN; c += 4) {
-          mx0 = fmax3(mx0, __uint_as_float(r[c]), __uint_as_float(r[c + 1]));
-          mx1 = fmax3(mx1, __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-        }
-        const float m_new = fmaxf(m_run, fmaxf(mx0, mx1) * AT_SCALE_LOG2);
-        const bool need = m_new > m_run + AT_RESCALE_TAU;  // first tile: m_run = -inf
-        if (__any_sync(0xffffffffu, need)) {
-          const float alpha = need ? fast_exp2(m_run - m_new) : 1.f;
-          if (need) {
-            l_run *= alpha;
-            m_run = m_new;
-          }
-          if (j > 0) {
-            // O += P(j-1) V(j-1) must have landed.  o_done has completed at most j phases at this point (PV(j) needs
-            // the P written below), so the parity of phase j-1 is unambiguous even though earlier phases went unobserved.
-            mbar_wait(o_done, (j - 1) & 1);
-            tc_fence_after();
-            const uint32_t o_addr = tmem_base + lane_off + A2_COL_O;
-#pragma unroll
-            for (int cb = 0; cb < AT_D; cb += 32) {
-              uint32_t o[32];
-              tmem_ld_x32(o_addr + cb, o);
-              tmem_wait_ld();
-#pragma unroll
-              for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * alpha);
-              tmem_st_x32(o_addr + cb, o);
-            }
-          }
-        }
-        neg_ref = -m_run;
-      }
-      float ls0 = 0.f, ls1 = 0.f, ls2 = 0.f, ls3 = 0.f;
-      uint32_t pk[BN / 2];
-#pragma unroll
-      for (int c = 0; c < BN; c += 4) {
-        const float x0 = fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref);
-        const float x1 = fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref);
-        const float x2 = fmaf(__uint_as_float(r[c + 2]), AT_SCALE_LOG2, neg_ref);
-        const float x3 = fmaf(__uint_as_float(r[c + 3]), AT_SCALE_LOG2, neg_ref);
-        // columns c % 16 < EMU take the FMA-pipe exponential (compile-time pattern, same for every lane)
-        const float p0 = ((c + 0) % 16 < EMU) ? poly_exp2<DEG>(x0) : fast_exp2(x0);
-        const float p1 = ((c + 1) % 16 < EMU) ? poly_exp2<DEG>(x1) : fast_exp2(x1);
-        const float p2 = ((c + 2) % 16 < EMU) ? poly_exp2<DEG>(x2) : fast_exp2(x2);
-        const float p3 = ((c + 3) % 16 < EMU) ? poly_exp2<DEG>(x3) : fast_exp2(x3);
-        if (!SHARED) {
-          ls0 += p0;
-          ls1 += p1;
-          ls2 += p2;
-          ls3 += p3;
-        }
-        pk[c >> 1] = pack_half2(p0, p1);
-        pk[(c >> 1) + 1] = pack_half2(p2, p3);
-      }
-      // packed fp16 P over the first half of this score buffer (all 64 score columns already sit in registers)
-      tmem_st_x32(s_addr, pk);
-      if (!SHARED) l_run += (ls0 + ls1) + (ls2 + ls3);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(&p_full[j & 1]);
-    }
-
-    // epilogue: O / l -> fp16 hi/lo planes; LSE for the sharing layers / column sums
-    __half* oh = p.out_hi + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
-    __half* ol = p.out_lo + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
-    float v[AT_D];
-    if (T > 0) {
-      mbar_wait(o_done, (T - 1) & 1);
-      tc_fence_after();
-      uint32_t o[AT_D];
-      const uint32_t o_addr = tmem_base + lane_off + A2_COL_O;
-      tmem_ld_x32(o_addr, o);
-      tmem_ld_x32(o_addr + 32, o + 32);
-      tmem_wait_ld();
-      const float inv = SHARED ? 1.f : 1.f / l_run;
-#pragma unroll
-      for (int c = 0; c < AT_D; ++c) v[c] = __uint_as_float(o[c]) * inv;
-    } else {
-#pragma unroll
-      for (int c = 0; c < AT_D; ++c) v[c] = 0.f;
-    }
-    if (row_ok) {
-#pragma unroll
-      for (int c = 0; c < AT_D; c += 8) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          __half h0, l0, h1, l1;
-          split_f16x2(v[c + 2 * t], h0, l0);
-          split_f16x2(v[c + 2 * t + 1], h1, l1);
-          __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-          hi[t] = *reinterpret_cast<uint32_t*>(&hh);
-          lo[t] = *reinterpret_cast<uint32_t*>(&ll);
-        }
-        *reinterpret_cast<uint4*>(oh + c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(ol + c) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      if (!SHARED) p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow] = m_run + log2f(l_run);
-    }
-    tc_fence_before();
-  }
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, A2_TMEM_COLS);
-  }
-}
-
-template <int EMU, int DEG>
-static int launch_attention_v2(const AttnArgs& a, cudaStream_t st) {
-  CUtensorMap tq, tk, tv;
-  if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
-  if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, A2_BN)) return 3;
-  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, A2_BN)) return 3;
-  AttnKernelParams p;
-  p.n_img = a.n_img;
-  p.src_offset = a.src_offset;
-  p.Nq_max = a.Nq_max;
-  p.Nk_max = a.Nk_max;
-  p.shared = a.shared;
-  p.nq = a.nq;
-  p.nk = a.nk;
-  p.lse = a.lse;
-  p.out_hi = reinterpret_cast<__half*>(a.out_hi);
-  p.out_lo = reinterpret_cast<__half*>(a.out_lo);
-  p.out_img_stride = a.out_img_stride;
-  const size_t smem = AT_TILE_BYTES + A2_STG * A2_STAGE_BYTES + 256;
-  static DeviceOnce configured;
-  if (configured.first()) {
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_v2_kernel<EMU, DEG, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_v2_kernel<EMU, DEG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_v2_kernel<EMU, DEG, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    IMP_CUDA_OK(cudaFuncSetAttribute(attention_v2_kernel<EMU, DEG, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-  }
-  dim3 grid((a.Nq_max + AT_BM - 1) / AT_BM, AT_HEADS, a.n_img);
-  if (a.shared) attention_v2_kernel<EMU, DEG, true><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  else attention_v2_kernel<EMU, DEG, false><<<grid, AT_THREADS, smem, st>>>(tq, tk, tv, p);
-  IMP_CUDA_OK(cudaGetLastError());
-  return 0;
-}
-
 template <int BN, int STG, int MINB, bool SPLIT>
 static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   CUtensorMap tq, tk, tv, tql, tkl, tvl;
@@ -717,14 +410,7 @@ int launch_attention(const AttnArgs& a, cudaStream_t st) {
   switch (g_attn_variant) {
     case 1: return launch_attention_impl<128, 3, 2, false>(a, st);
     case 2: return launch_attention_impl<64, 2, 3, false>(a, st);
-    case 3: return launch_attention_impl<64, 2, 4, false>(a, st);  // round-1 default
-    case 10: return launch_attention_v2<0, 4>(a, st);              // v2, every exponential on the MUFU
-    case 12: return launch_attention_v2<2, 4>(a, st);
-    case 13: return launch_attention_v2<3, 4>(a, st);
-    case 14: return launch_attention_v2<4, 4>(a, st);
-    case 23: return launch_attention_v2<3, 3>(a, st);
-    case 24: return launch_attention_v2<4, 3>(a, st);
-    default: return launch_attention_v2<3, 4>(a, st);
+    default: return launch_attention_impl<64, 2, 4, false>(a, st);
   }
 }
 

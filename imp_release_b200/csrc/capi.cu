@@ -57,6 +57,12 @@ IMP_API int imp_instnorm_relu(const float* H, int64_t h_bs, int32_t ldh, const i
   return imp::launch_instnorm_relu_split(H, h_bs, ldh, ns, Nmax, C, batch, eps, relu, out_hi, out_lo, out_f32, o_bs, ldo,
                                          ST(stream));
 }
+IMP_API int imp_instnorm_apply(const float* H, const float* stat_partial, const float* stat_straddle, const int32_t* ns,
+                       int32_t Np, int32_t C, int32_t images, float eps, int32_t relu, float* stats, void* out_hi,
+                       void* out_lo, void* stream) {
+  return imp::launch_instnorm_apply(H, stat_partial, stat_straddle, ns, Np, C, images, eps, relu, stats, out_hi, out_lo,
+                                    ST(stream));
+}
 IMP_API int imp_kenc_input(const float* norm_kpts, const float* scores, float* out_xyz4, int64_t tokens, void* stream) {
   return imp::launch_kenc_input(norm_kpts, scores, out_xyz4, tokens, ST(stream));
 }

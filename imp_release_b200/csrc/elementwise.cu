@@ -244,6 +244,90 @@ int launch_instnorm_relu_split(const float* H, long long h_bs, int ldh, const in
 }
 
 // ---------------------------------------------------------------------------------------------
+// Fused instance norm, second half (the first half -- per-tile column sums -- is the epilogue of the GEMM that produced H,
+// gemm.cu).  finalize: one thread per (image, channel) adds the image's tile partials in tile order in fp64 (plain sums
+// are fine at that precision: the relative error of the variance is ~1e-7 (1 + mean^2/var)) -> (mean, rstd).
+__global__ void instnorm_finalize_kernel(const float2* __restrict__ partial, const float2* __restrict__ straddle,
+                                         const int* __restrict__ ns, int Np, int C, float eps, float2* __restrict__ stats) {
+  const int img = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const int n = ns[img];
+  const long long r0 = (long long)img * Np;
+  const int t0 = (int)(r0 / 128), t1 = (int)((r0 + Np - 1) / 128);
+  double s1 = 0.0, s2 = 0.0;
+  for (int t = t0; t <= t1; ++t) {
+    if ((long long)t * 128 >= r0) {  // a tile whose first image is this one
+      const float2 v = partial[(long long)t * C + c];
+      s1 += v.x;
+      s2 += v.y;
+    } else {                         // the tile that starts in the previous image and reaches into this one
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 v = straddle[((long long)img * 4 + q) * C + c];
+        s1 += v.x;
+        s2 += v.y;
+      }
+    }
+  }
+  const double inv_n = n > 0 ? 1.0 / n : 0.0;
+  const double m = s1 * inv_n;
+  const double var = fmax(s2 * inv_n - m * m, 0.0);  // biased variance
+  stats[(long long)img * C + c] = make_float2((float)m, (float)(1.0 / sqrt(var + (double)eps)));
+}
+
+// apply: pure streaming pass, 8 channels per thread (2 x 16 B in, 2 x 16 B out); the (mean, rstd) pairs of a thread's fixed
+// channel group stay in registers across its grid-stride rows
+__global__ void __launch_bounds__(256)
+instnorm_apply_kernel(const float* __restrict__ H, const float2* __restrict__ stats, int Np, int C, int relu,
+                      __half* __restrict__ out_hi, __half* __restrict__ out_lo) {
+  const int img = blockIdx.y;
+  const int cg = C >> 3;                        // channel groups of 8 per row
+  const int rows_per_pass = blockDim.x / cg;    // host guarantees blockDim.x % cg == 0
+  const int g = threadIdx.x % cg, r_in = threadIdx.x / cg;
+  const float2* st = stats + (long long)img * C + g * 8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int k = 0; k < 8; k += 2) {
+    const float4 m = *reinterpret_cast<const float4*>(st + k);  // (mean, rstd) x 2
+    mean[k] = m.x; rstd[k] = m.y; mean[k + 1] = m.z; rstd[k + 1] = m.w;
+  }
+  for (int row = blockIdx.x * rows_per_pass + r_in; row < Np; row += gridDim.x * rows_per_pass) {
+    const long long e = ((long long)img * Np + row) * C + g * 8;
+    const float4 a = *reinterpret_cast<const float4*>(H + e);
+    const float4 b = *reinterpret_cast<const float4*>(H + e + 4);
+    float y[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    __half hh[8], ll[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      y[k] = (y[k] - mean[k]) * rstd[k];
+      if (relu) y[k] = fmaxf(y[k], 0.f);
+      split_f16x2(y[k], hh[k], ll[k]);
+    }
+    *reinterpret_cast<uint4*>(out_hi + e) = *reinterpret_cast<uint4*>(hh);
+    *reinterpret_cast<uint4*>(out_lo + e) = *reinterpret_cast<uint4*>(ll);
+  }
+}
+
+int launch_instnorm_apply(const float* H, const float* stat_partial, const float* stat_straddle, const int* ns, int Np, int C,
+                          int images, float eps, int relu, float* stats, void* out_hi, void* out_lo, cudaStream_t st) {
+  IMP_REQUIRE(Np >= 128 && images > 0, "instnorm_apply: needs images of >= 128 rows");
+  instnorm_finalize_kernel<<<dim3((C + 127) / 128, images), 128, 0, st>>>(
+      reinterpret_cast<const float2*>(stat_partial), reinterpret_cast<const float2*>(stat_straddle), ns, Np, C, eps,
+      reinterpret_cast<float2*>(stats));
+  const int cg = C / 8;
+  IMP_REQUIRE(C % 8 == 0 && cg <= 256 && 256 % cg == 0, "instnorm_apply: C / 8 must divide 256 (C = %d)", C);
+  const int rows_per_pass = 256 / cg;
+  int bx = (Np + rows_per_pass - 1) / rows_per_pass;
+  const int cap = (num_sms() * 8 + images - 1) / images;  // ~8 CTAs per SM in total: grid-stride above that
+  if (bx > cap) bx = cap < 1 ? 1 : cap;
+  instnorm_apply_kernel<<<dim3(bx, images), 256, 0, st>>>(H, reinterpret_cast<const float2*>(stats), Np, C, relu,
+                                                          reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo));
+  IMP_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
 // Small fp32 linear layer for the keypoint encoder's narrow layers (Cin <= 64): y[t, o] = b[o] + sum_c x[t,c] w[o,c].
 // The 3->32 and 32->64 layers are <2% of the encoder FLOPs; wider layers go through the tensor-core GEMM.
 __global__ void small_linear_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ W,

@@ -24,6 +24,12 @@ struct GemmKernelParams {
   void *out0, *out1;
   const __half *res_hi, *res_lo;
   long long out_row_stride, out_batch_stride;
+  // instance-norm statistics of the fp32 output (per image of stat_np rows: column sums / sums of squares over the
+  // first stat_ns[img] rows), see GemmArgs
+  float2* stat_partial;   // [tiles_m][N]
+  float2* stat_straddle;  // [images][4][N]
+  const int* stat_ns;
+  int stat_np;
 };
 
 // BK = K elements per pipeline stage = one swizzle span (64 fp16 = 128 B, or 32 fp16 = 64 B).  The mainloop is bound by
@@ -54,6 +60,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [ACC][BN] bias slice of the tile being drained
   // per-epilogue-warp staging tile: 32 rows x 128 B payload, 144 B pitch (conflict-free for 16-byte accesses)
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + ACC * BN);
+  float2* s_stat = reinterpret_cast<float2*>(s_stage + 4 * 32 * 144);  // [4 warps][BN] (sum, sum of squares), stats mode only
 
   const int warp = threadIdx.x >> 5;
   const bool split = p.nsplit == 3;
@@ -165,6 +172,24 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       const int a = lt % ACC;
       const long long gm = m0 + row;
       const bool row_ok = gm < p.M;
+      // Instance-norm statistics (stats mode): rows of this warp's 32-row slab that are valid tokens of the tile's first
+      // image (segment A: [sa0, sa1)) and of the image the tile straddles into (segment B: [sb0, sb1)).  Warp-uniform.
+      const bool stats = p.stat_partial != nullptr;
+      int sa0 = 0, sa1 = 0, sb0 = 0, sb1 = 0, img_b = -1;
+      if (stats) {
+        const int r0 = m0 + q * 32;                 // first global row of the slab
+        const int img_a = m0 / p.stat_np;
+        const int end_a = (img_a + 1) * p.stat_np;  // first row of the next image
+        sa1 = min(32, img_a * p.stat_np + p.stat_ns[img_a] - r0);
+        sa1 = max(sa1, 0);
+        if (end_a < m0 + GEMM_BM && end_a < p.M) {  // the tile reaches into image img_a + 1
+          img_b = img_a + 1;
+          sb0 = max(0, end_a - r0);
+          sb1 = min(32, end_a + p.stat_ns[img_b] - r0);
+          if (sb1 < sb0) sb1 = sb0;
+          if (sb0 >= 32) sb0 = sb1 = 0;
+        }
+      }
       // stage this tile's bias slice in shared memory (one coalesced load instead of 256 broadcast LDGs per thread)
       float* bias_t = s_bias + a * BN;
       for (int j = threadIdx.x - 128; j < BN; j += 128)
@@ -241,6 +266,25 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
             for (int j = 0; j < 32; j += 4)
               *reinterpret_cast<float4*>(stg + l * 144 + j * 4) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
             __syncwarp();
+            if (stats) {
+              // lane l owns column nc + l of the 32 x 32 sub-tile sitting in the staging tile (pitch 36 words: conflict-free)
+              float s1 = 0.f, s2 = 0.f;
+              for (int rr = sa0; rr < sa1; ++rr) {
+                const float x = *reinterpret_cast<const float*>(stg + rr * 144 + l * 4);
+                s1 += x;
+                s2 = fmaf(x, x, s2);
+              }
+              s_stat[q * BN + c * 32 + l] = make_float2(s1, s2);
+              if (img_b >= 0) {
+                float t1 = 0.f, t2 = 0.f;
+                for (int rr = sb0; rr < sb1; ++rr) {
+                  const float x = *reinterpret_cast<const float*>(stg + rr * 144 + l * 4);
+                  t1 += x;
+                  t2 = fmaf(x, x, t2);
+                }
+                p.stat_straddle[((long long)img_b * 4 + q) * p.N + nc + l] = make_float2(t1, t2);
+              }
+            }
             float* o = reinterpret_cast<float*>(p.out0) + wrow0;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {  // 4 rows x 128 B per pass
@@ -331,6 +375,16 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
       }
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);  // 128 arrivals: the accumulator may be overwritten
+      if (stats) {
+        // the four slabs of the tile, added in fixed order (deterministic): one (sum, sum of squares) per tile and column
+        asm volatile("bar.sync 2, 128;" ::: "memory");
+        for (int j = threadIdx.x - 128; j < BN && n0 + j < p.N; j += 128) {
+          const float2 a0 = s_stat[j], a1 = s_stat[BN + j], a2 = s_stat[2 * BN + j], a3 = s_stat[3 * BN + j];
+          p.stat_partial[(long long)(m0 / GEMM_BM) * p.N + n0 + j] =
+              make_float2(((a0.x + a1.x) + a2.x) + a3.x, ((a0.y + a1.y) + a2.y) + a3.y);
+        }
+        // (the next tile writes s_stat only after its bias-staging barrier, which every thread reaches after this loop)
+      }
     }
   }
   __syncthreads();
@@ -378,8 +432,13 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.res_lo = reinterpret_cast<const __half*>(g.res_lo);
   p.out_row_stride = g.out_row_stride;
   p.out_batch_stride = g.out_batch_stride;
+  p.stat_partial = reinterpret_cast<float2*>(g.stat_partial);
+  p.stat_straddle = reinterpret_cast<float2*>(g.stat_straddle);
+  p.stat_ns = g.stat_ns;
+  p.stat_np = g.stat_np;
 
-  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float) + 4 * 32 * 144;
+  const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float) + 4 * 32 * 144 +
+                      (BN == 256 ? 4 * BN * sizeof(float2) : 0);
   auto kern = gemm_f16split_kernel<BN, STAGES, BK>;
   static DeviceOnce configured;
   if (configured.first()) {
@@ -399,6 +458,10 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
   IMP_REQUIRE(g.K1 > 0 && g.K1 % 64 == 0 && g.K2 % 64 == 0, "gemm: K segments must be multiples of 64 (got %d, %d)", g.K1, g.K2);
   IMP_REQUIRE(g.M > 0 && g.N > 0 && g.batch > 0, "gemm: empty problem");
   IMP_REQUIRE(g.out_row_stride % 8 == 0, "gemm: output row stride must be a multiple of 8 elements");
+  if (g.stat_partial != nullptr)
+    IMP_REQUIRE(g.out_mode == IMP_GEMM_OUT_F32 && g.N > 128 && g.N % 32 == 0 && g.batch == 1 && g.stat_np >= GEMM_BM &&
+                    g.stat_ns != nullptr && g.stat_straddle != nullptr && g.M % g.stat_np == 0,
+                "gemm: instance-norm statistics need fp32 output, 128 < N (multiple of 32), batch 1 and images of >= 128 rows");
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("IMP_GEMM_VARIANT");

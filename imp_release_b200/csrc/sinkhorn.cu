@@ -368,6 +368,13 @@ __global__ void sk_matches_kernel(const float* __restrict__ row_max, const int* 
     const float ms = mutual ? rm[t] : 0.f;
     mscores0[b * out0_bs + t] = ms;
     indices0[b * out0_bs + t] = (mutual && ms > p_thresh) ? (long long)j : -1ll;
+  } else if (t < N0max) {  // beyond this sample's keypoints: the "no match" defaults (outputs need no pre-fill)
+    mscores0[b * out0_bs + t] = 0.f;
+    indices0[b * out0_bs + t] = -1ll;
+  }
+  if (t >= n1 && t < N1max && indices1 != nullptr) {
+    mscores1[b * out1_bs + t] = 0.f;
+    indices1[b * out1_bs + t] = -1ll;
   }
   if (t < n1 && indices1 != nullptr) {
     const int i = (int)(0xFFFFFFFFu - (unsigned)(ck[t] & 0xFFFFFFFFull));

@@ -23,6 +23,9 @@ from .ops import Planes
 
 HEADS = 4
 D = 256
+# instance-norm statistics fused into the epilogue of the first MLP GEMM (IMP_FUSED_INSTNORM=0: stand-alone slab kernel)
+import os as _os
+FUSED_INSTNORM = _os.environ.get('IMP_FUSED_INSTNORM', '1') != '0'
 
 
 def head_perm(device) -> torch.Tensor:
@@ -95,6 +98,8 @@ class Workspace:
         # high-precision attention: "lo" planes of the Q|K|V projections (and of the compacted K|V)
         self.qkv_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
         self.kvc_lo: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
+        # fused instance norm of the MLP hidden layer (statistics come out of the first MLP GEMM's epilogue)
+        self.in_stats = ops.InstNormStats(n_img, Np, 2 * D, device) if Np >= 128 else None
         # EIMP pooling: fp32-level row LSE of the stashed attention + per-head scratch of the column sums
         self.lse_x: Dict[str, Optional[torch.Tensor]] = {'self': None, 'cross': None}
         self.cs_scratch: Optional[torch.Tensor] = None
@@ -138,6 +143,7 @@ class RunState:
         self.key_ids: Optional[torch.Tensor] = None   # [2B, Np] int32 sorted kept ids
         self.stash_cnt = {'self': None, 'cross': None}  # key counts the stashed K (and LSE) were built with
         self.stash_ok = {'self': False, 'cross': False}   # a non-sharing layer of this type has run on THIS state
+        self.ragged = False             # n_tok came from the caller (padded inputs): scoring must mask by it too
 
 
 class Engine:
@@ -151,10 +157,13 @@ class Engine:
         self.stash_lo = stash_lo and not high_precision_attention
         self._ws: Dict[tuple, Workspace] = {}
 
+    WS_BUDGET_BYTES = 24 << 30      # cached workspaces (all shapes) stay below this; ~5.5 KB per token
+
     def workspace(self, n_img: int, Np: int, device) -> Workspace:
         key = (n_img, Np, str(device))
         if key not in self._ws:
-            if len(self._ws) > 4:
+            tokens = sum(k[0] * k[1] for k in self._ws) + n_img * Np
+            if len(self._ws) >= 32 or tokens * 5632 > self.WS_BUDGET_BYTES:
                 self._ws.clear()
             self._ws[key] = Workspace(n_img, Np, device)
         return self._ws[key]
@@ -242,9 +251,14 @@ class Engine:
                       nq=st.n_tok, nk=nk, shared=L['sharing'], lse=lse, out=ws.A, q_row_stride=3 * D,
                       kv_row_stride=kv_rs, q_lo=base_lo, k_lo=k_lo, v_lo=v_lo)
         ops.ATTN_WORK_HINT = None
+        fused = ws.in_stats is not None and FUSED_INSTNORM
         ops.gemm(ws.X, L['W0'], M=T, N=2 * D, K1=D, K2=D, a2=ws.A, a_row_stride=D, a2_row_stride=D, b_row_stride=2 * D,
-                 bias=L['b0'], out_mode=ops.OUT_F32, out0=ws.H, out_row_stride=2 * D)
-        ops.instnorm_relu(ws.H, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=ws.Hn)
+                 bias=L['b0'], out_mode=ops.OUT_F32, out0=ws.H, out_row_stride=2 * D,
+                 stats=ws.in_stats if fused else None, ns=st.n_tok, Np=Np)
+        if fused:
+            ops.instnorm_apply(ws.H, ws.in_stats, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=ws.Hn)
+        else:
+            ops.instnorm_relu(ws.H, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=ws.Hn)
         ops.gemm(ws.Hn, L['W3'], M=T, N=D, K1=2 * D, a_row_stride=2 * D, b_row_stride=2 * D, bias=L['b3'],
                  out_mode=ops.OUT_SPLIT_RESID, out0=ws.X.hi, out1=ws.X.lo, out_row_stride=D, res=ws.X)
 

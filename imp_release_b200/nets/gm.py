@@ -127,6 +127,23 @@ class GM(nn.Module):
             self._sk_cache[key] = SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage)
         return self._sk_cache[key]
 
+    def replica(self):
+        """A second handle on the same weights (parameters and packed kernel weights are shared, nothing is copied) with
+        its OWN workspaces and per-call state, so that several pairs can be in flight on different CUDA streams
+        (imp_release_b200.graphed.LatencyMatcher).  The reference model is not re-entrant either (stateful attributes)."""
+        import copy
+        eng = self.engine()
+        r = copy.copy(self)                       # shares _parameters / _modules
+        r._engine = Engine(eng.pk, eng.names, high_precision_attention=eng.hp, stash_lo=eng.stash_lo)
+        r._engine_key = self._engine_key
+        r._st, r._io, r._last_sk = None, None, None
+        r._sk_cache = {}
+        r.__dict__.pop('_n_tok_cache', None)
+        r.__dict__.pop('_dist', None)
+        r.__dict__.pop('_dist_key', None)
+        r.__dict__.pop('_side', None)
+        return r
+
     # ------------------------------------------------------------------ batched entry points
     def forward(self, data, mode=0):
         if self.training:
@@ -155,29 +172,56 @@ class GM(nn.Module):
                     normalize_keypoints(data['keypoints1'], data['image1'].shape))
         raise ValueError('Require image shape for keypoint coordinate normalization')
 
-    def _begin(self, desc0, desc1, nk0, nk1, sc0, sc1) -> RunState:
+    @staticmethod
+    def _bucket(B: int, n: int) -> int:
+        """Token capacity of the workspace for n keypoints per image.  Small problems (the one-pair-per-call evaluation,
+        eval/eval_imp.py:155-173, where every pair has its own keypoint counts) round up to a multiple of 128 so that
+        workspaces -- and captured CUDA graphs -- are shared by all pairs of a bucket; the kernels mask by the per-image
+        counts.  Big batches keep the exact size (no padded rows in the GEMMs)."""
+        return (n + 127) // 128 * 128 if 2 * B * n <= 32768 else n
+
+    @staticmethod
+    def _counts(data, dev):
+        """B200 extension of the data dict: optional 'n_keypoints0' / 'n_keypoints1' ([B] integer tensors) declare that
+        the keypoint tensors are zero-padded and only the first n_keypoints*[b] entries of pair b are real (ragged pairs
+        in one batch, static-shape graph replay).  The reference has no such key; without it nothing changes."""
+        c0, c1 = data.get('n_keypoints0'), data.get('n_keypoints1')
+        if c0 is None or c1 is None:
+            return None
+        return torch.cat([c0.reshape(-1), c1.reshape(-1)]).to(device=dev, dtype=torch.int32)
+
+    def _begin(self, desc0, desc1, nk0, nk1, sc0, sc1, counts: Optional[torch.Tensor] = None) -> RunState:
         """Stack both images token-major, run the keypoint encoder, x = desc + enc (nets/gms.py:158-172)."""
         eng = self.engine()
         self._io = None            # the workspace state is about to be overwritten
         B, N0, N1 = desc0.shape[0], desc0.shape[1], desc1.shape[1]
         dev = desc0.device
-        Np = max(N0, N1)
+        Np = self._bucket(B, max(N0, N1))
         ws = eng.workspace(2 * B, Np, dev)
-        if N0 == N1:
-            desc = torch.cat([desc0, desc1], 0).float().contiguous()
+        n_tok = counts if counts is not None else self._n_tok(B, N0, N1, dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        if N0 == N1 == Np:
             nk = torch.cat([nk0, nk1], 0).float().contiguous()
             sc = torch.cat([sc0, sc1], 0).float().contiguous()
         else:
-            desc = desc0.new_zeros(2 * B, Np, D, dtype=torch.float32)
-            nk = desc0.new_zeros(2 * B, Np, 2, dtype=torch.float32)
-            sc = desc0.new_zeros(2 * B, Np, dtype=torch.float32)
-            desc[:B, :N0], desc[B:, :N1] = desc0, desc1
+            nk = torch.zeros(2 * B, Np, 2, **f32)
+            sc = torch.zeros(2 * B, Np, **f32)
             nk[:B, :N0], nk[B:, :N1] = nk0, nk1
             sc[:B, :N0], sc[B:, :N1] = sc0, sc1
-        n_tok = self._n_tok(B, N0, N1, dev)
         eng.encode_keypoints(ws, nk, sc, n_tok, ws.tok_f32)
-        ops.split_planes(desc.view(-1, D), out=ws.X, addend=ws.tok_f32)
-        return RunState(ws, B, N0, N1, n_tok)
+        if N0 == N1 == Np and desc0.dtype == torch.float32 and desc0.is_contiguous() and desc1.is_contiguous():
+            # descriptors go straight from the caller's tensors into the hi/lo planes (no stacked fp32 copy)
+            h = B * Np
+            for side, d in ((0, desc0), (1, desc1)):
+                ops.split_planes(d.view(-1, D), out=Planes(ws.X.hi[side * h:(side + 1) * h], ws.X.lo[side * h:(side + 1) * h]),
+                                 addend=ws.tok_f32[side * h:(side + 1) * h])
+        else:
+            desc = torch.zeros(2 * B, Np, D, **f32)
+            desc[:B, :N0], desc[B:, :N1] = desc0, desc1
+            ops.split_planes(desc.view(-1, D), out=ws.X, addend=ws.tok_f32)
+        st = RunState(ws, B, N0, N1, n_tok)
+        st.ragged = counts is not None
+        return st
 
     def _n_tok(self, B, N0, N1, dev) -> torch.Tensor:
         """Per-image token counts [2B] (cached: no host-to-device copy on the hot path, CUDA-graph capturable)."""
@@ -198,7 +242,9 @@ class GM(nn.Module):
         ldd = (N1 + 7) // 8 * 8
         dist = self._dist_buffer(B, N0, ldd, dev)
         eng.distance(st, st.ws.Y, N0, N1, dist, ldd)
-        return self._score_from_dist(dist, ldd, B, N0, N1, p, keep_scores, want_mass, write_scores=write_scores)
+        n0s, n1s = (st.n_tok[:B], st.n_tok[B:]) if st.ragged else (None, None)
+        return self._score_from_dist(dist, ldd, B, N0, N1, p, keep_scores, want_mass, n0s=n0s, n1s=n1s,
+                                     write_scores=write_scores)
 
     def _dist_buffer(self, B, N0, ldd, dev):
         key = (B, N0, ldd, str(dev))
@@ -236,7 +282,7 @@ class GM(nn.Module):
         if kpts0.shape[1] == 0 or kpts1.shape[1] == 0:
             return self._empty_result(kpts0, kpts1)
         nk0, nk1 = self._norm_kpts(data)
-        st = self._begin(desc0, desc1, nk0, nk1, data['scores0'], data['scores1'])
+        st = self._begin(desc0, desc1, nk0, nk1, data['scores0'], data['scores1'], self._counts(data, desc0.device))
         eng = self.engine()
         nI = len(eng.names) // 2
         all_scores, all_i0, all_m0 = [], [], []
@@ -271,7 +317,7 @@ class GM(nn.Module):
         eng = self.engine()
         B, N0, N1 = norm_kpts0.shape[0], norm_kpts0.shape[1], norm_kpts1.shape[1]
         dev = norm_kpts0.device
-        Np = max(N0, N1)
+        Np = self._bucket(B, max(N0, N1))
         ws = eng.workspace(2 * B, Np, dev)
         nk = norm_kpts0.new_zeros(2 * B, Np, 2, dtype=torch.float32)
         sc = norm_kpts0.new_zeros(2 * B, Np, dtype=torch.float32)
@@ -294,7 +340,7 @@ class GM(nn.Module):
         eng = self.engine()
         B, N0, N1 = desc0.shape[0], desc0.shape[2], desc1.shape[2]
         dev = desc0.device
-        Np = max(N0, N1)
+        Np = self._bucket(B, max(N0, N1))
         ws = eng.workspace(2 * B, Np, dev)
         x = desc0.new_zeros(2 * B, Np, D, dtype=torch.float32)
         x[:B, :N0] = desc0.transpose(1, 2)

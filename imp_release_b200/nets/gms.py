@@ -31,7 +31,7 @@ class DGNNS(GM):
         if kpts0.shape[1] == 0 or kpts1.shape[1] == 0:
             return self._empty_result(kpts0, kpts1)
         nk0, nk1 = self._norm_kpts(data)
-        st = self._begin(desc0, desc1, nk0, nk1, data['scores0'], data['scores1'])
+        st = self._begin(desc0, desc1, nk0, nk1, data['scores0'], data['scores1'], self._counts(data, desc0.device))
         eng = self.engine()
         nI = self.config['n_layers']
         all_i0, all_m0 = [], []
@@ -70,7 +70,8 @@ class DGNNS(GM):
                     eng.distance(st, st.ws.Y, N0, N1, dist, ldd)
                     dist_done = torch.cuda.Event()
                     dist_done.record(side)
-                    _, i0, _, m0, _, _ = self._score_from_dist(dist, ldd, B, N0, N1, p, False)
+                    n0s, n1s = (st.n_tok[:B], st.n_tok[B:]) if st.ragged else (None, None)
+                    _, i0, _, m0, _, _ = self._score_from_dist(dist, ldd, B, N0, N1, p, False, n0s=n0s, n1s=n1s)
                 all_i0.append(i0); all_m0.append(m0)
             main.wait_stream(side)
             for t in all_i0 + all_m0:

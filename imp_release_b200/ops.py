@@ -94,8 +94,10 @@ def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row
          a2_row_stride: int = 0, a2_batch_stride: int = 0, nsplit: int = 3, alpha: float = 1.0,
          bias: Optional[torch.Tensor] = None, out_mode: int = OUT_F32, out0: torch.Tensor = None,
          out1: Optional[torch.Tensor] = None, out_row_stride: int = 0, out_batch_stride: int = 0,
-         res: Optional[Planes] = None, a_offset: int = 0, a2_offset: int = 0, b_offset: int = 0, out_offset: int = 0):
-    """D = alpha * A.B^T (+bias)(+res).  Offsets are in elements from the start of the plane tensors."""
+         res: Optional[Planes] = None, a_offset: int = 0, a2_offset: int = 0, b_offset: int = 0, out_offset: int = 0,
+         stats: Optional['InstNormStats'] = None, ns: Optional[torch.Tensor] = None, Np: int = 0):
+    """D = alpha * A.B^T (+bias)(+res).  Offsets are in elements from the start of the plane tensors.
+    stats / ns / Np: fused instance-norm statistics of the fp32 output (see imp_gemm_args)."""
     g = GemmArgs()
     esz = 2
     g.a_hi = a.hi.data_ptr() + a_offset * esz
@@ -119,6 +121,8 @@ def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row
     if res is not None:
         g.res_hi = res.hi.data_ptr() + out_offset * esz
         g.res_lo = res.lo.data_ptr() + out_offset * esz
+    if stats is not None:
+        g.stat_partial, g.stat_straddle, g.stat_ns, g.stat_np = ptr(stats.partial), ptr(stats.straddle), ptr(ns), Np
     with _Span(f'gemm_n{N}_k{K1 + K2}' + ('_b' if b_batched else ''), 1, 2.0 * M * N * (K1 + K2) * batch):
         check(_lib.load().imp_gemm(C.byref(g), stream_ptr()), 'imp_gemm')
 
@@ -181,6 +185,26 @@ def instnorm_relu(H: torch.Tensor, *, batch: int, Nmax: int, C_: int, ns=None, e
                                             ptr(out.hi) if out is not None else None,
                                             ptr(out.lo) if out is not None else None, ptr(out_f32), Nmax * C_, C_,
                                             stream_ptr()), 'imp_instnorm_relu')
+
+
+class InstNormStats:
+    """Workspace of the fused instance norm: per-tile partial sums written by the GEMM epilogue, reduced by
+    instnorm_apply into (mean, rstd) per (image, channel)."""
+
+    def __init__(self, n_img: int, Np: int, C_: int, device):
+        tiles = (n_img * Np + 127) // 128
+        f32 = dict(dtype=torch.float32, device=device)
+        self.partial = torch.zeros(tiles, C_, 2, **f32)
+        self.straddle = torch.zeros(n_img, 4, C_, 2, **f32)
+        self.stats = torch.zeros(n_img, C_, 2, **f32)
+
+
+def instnorm_apply(H: torch.Tensor, st: InstNormStats, *, batch: int, Nmax: int, C_: int, ns, out: Planes, eps: float = 1e-3,
+                   relu: bool = True):
+    """Second half of the fused instance norm: statistics left by gemm(..., stats=st) -> normalise + ReLU + hi/lo split."""
+    with _Span(f'instnorm_apply_c{C_}', 2, 8.0 * batch * Nmax * C_):
+        check(_lib.load().imp_instnorm_apply(ptr(H), ptr(st.partial), ptr(st.straddle), ptr(ns), Nmax, C_, batch, eps, int(relu),
+                                             ptr(st.stats), ptr(out.hi), ptr(out.lo), stream_ptr()), 'imp_instnorm_apply')
 
 
 def kenc_input(norm_kpts: torch.Tensor, scores: torch.Tensor, out: torch.Tensor):
@@ -274,10 +298,11 @@ def sinkhorn(dist: torch.Tensor, ldd: int, bin_score: torch.Tensor, iters: int, 
 def matches(ws_row_max, ws_row_arg, ws_col_key, p: float, N0max: int, N1max: int, batch: int, n0s=None, n1s=None,
             want1: bool = True) -> Tuple[torch.Tensor, Optional[torch.Tensor], torch.Tensor, Optional[torch.Tensor]]:
     dev = ws_row_max.device
-    i0 = torch.full((batch, N0max), -1, dtype=torch.int64, device=dev)
-    m0 = torch.zeros(batch, N0max, dtype=torch.float32, device=dev)
-    i1 = torch.full((batch, N1max), -1, dtype=torch.int64, device=dev) if want1 else None
-    m1 = torch.zeros(batch, N1max, dtype=torch.float32, device=dev) if want1 else None
+    # the kernel writes every entry (-1 / 0 beyond a sample's size): no fill launches
+    i0 = torch.empty((batch, N0max), dtype=torch.int64, device=dev)
+    m0 = torch.empty(batch, N0max, dtype=torch.float32, device=dev)
+    i1 = torch.empty((batch, N1max), dtype=torch.int64, device=dev) if want1 else None
+    m1 = torch.empty(batch, N1max, dtype=torch.float32, device=dev) if want1 else None
     m = MatchArgs()
     m.row_max, m.row_arg, m.col_key = ptr(ws_row_max), ptr(ws_row_arg), ptr(ws_col_key)
     m.p_thresh = p

@@ -54,3 +54,29 @@ def match_sharded(match_fn: Callable[[Sequence[int]], Tuple[torch.Tensor, torch.
         i0 = torch.empty(0, n_max, dtype=torch.int64, device=dev)
         s0 = torch.empty(0, n_max, dtype=torch.float32, device=dev)
     return gather_matches(i0, s0, n_pairs, rank, world, n_max)
+
+
+def evaluate_sharded(model, get_pair: Callable[[int], dict], n_pairs: int, n_max: int, rank: int, world: int,
+                     slots: int = 4, p: float = 0.2):
+    """BASELINE.json configs[3]: the one-pair-per-call evaluation of eval/eval_imp.py:155-173
+    (``produce_matches(only_last=True)`` per pair, ragged keypoint counts) sharded over ranks.  Every rank replays bucketed
+    CUDA graphs with ``slots`` pairs in flight (graphed.LatencyMatcher); ``get_pair(i)`` returns pair i's data dict
+    (device tensors, or pinned host tensors -- they are staged on the slot's stream).  Rank 0 gets
+    ([n_pairs, n_max] indices0, [n_pairs, n_max] mscores0), -1 / 0 padded."""
+    from .graphed import LatencyMatcher
+    dev = next(model.parameters()).device
+    lm = LatencyMatcher(model, slots=slots, p=p, only_last=True)
+
+    def match_fn(ids: Sequence[int]):
+        i0 = torch.full((len(ids), n_max), -1, dtype=torch.int64, device=dev)
+        s0 = torch.zeros(len(ids), n_max, dtype=torch.float32, device=dev)
+        tickets = [lm.submit(get_pair(i)) for i in ids]
+        for k, t in enumerate(tickets):
+            out = lm.result(t)
+            n = out['indices0'][-1].shape[1]
+            i0[k, :n] = out['indices0'][-1][0]
+            s0[k, :n] = out['mscores0'][-1][0]
+        return i0, s0
+
+    with torch.no_grad():
+        return match_sharded(match_fn, n_pairs, n_max, rank, world)

@@ -62,6 +62,16 @@ typedef struct imp_gemm_args {
   void *out0, *out1; /* F32: out0 fp32 | F16: out0 fp16 | SPLIT*: out0 = hi plane, out1 = lo plane */
   int64_t out_row_stride, out_batch_stride;
   const void *res_hi, *res_lo; /* SPLIT_RESID: residual planes, same strides as out (may alias out) */
+  /* Optional fused InstanceNorm1d statistics of the output (nets/layers.py:68-72; OUT_F32, N > 128, batch = 1): the M rows
+   * are images of stat_np >= 128 rows each, of which the first stat_ns[img] are real tokens.  The epilogue leaves, per
+   * 128-row tile and column, (sum, sum of squares) over the tile's valid rows of its FIRST image in stat_partial
+   * [ceil(M/128)][N][2], and for tiles reaching into the next image the four 32-row slab sums over that image's rows in
+   * stat_straddle [images][4][N][2].  Plain stores in fixed order: imp_instnorm_apply reduces them deterministically. */
+  float* stat_partial;
+  float* stat_straddle;
+  const int32_t* stat_ns;
+  int32_t stat_np;
+  int32_t _pad2;
 } imp_gemm_args;
 IMP_API int imp_gemm(const imp_gemm_args* args, void* stream);
 
@@ -108,6 +118,13 @@ IMP_API int imp_attention_colsum(const imp_attn_colsum_args* args, void* stream)
 IMP_API int imp_instnorm_relu(const float* H, int64_t h_batch_stride, int32_t ldh, const int32_t* ns, int32_t Nmax, int32_t C,
                       int32_t batch, float eps, int32_t relu, void* out_hi, void* out_lo, float* out_f32,
                       int64_t o_batch_stride, int32_t ldo, void* stream);
+
+/* second half of the fused instance norm: reduce the statistics imp_gemm left (fp64, fixed order) to mean / 1/sqrt(var+eps)
+ * per (image, channel) in `stats` [images][C][2], then stream H -> relu((H - mean) * rstd) -> fp16 hi/lo planes.
+ * H [images * Np, C] fp32 contiguous; Np >= 128. */
+IMP_API int imp_instnorm_apply(const float* H, const float* stat_partial, const float* stat_straddle, const int32_t* ns,
+                       int32_t Np, int32_t C, int32_t images, float eps, int32_t relu, float* stats, void* out_hi,
+                       void* out_lo, void* stream);
 
 /* ---- keypoint encoder narrow layers (3->32, 32->64), nets/layers.py:80-90 ----------------------------------- */
 IMP_API int imp_kenc_input(const float* norm_kpts, const float* scores, float* out_xyz4, int64_t tokens, void* stream);
@@ -161,7 +178,8 @@ IMP_API int64_t imp_sinkhorn_q_store_bytes(int32_t batch, int32_t N0max, int32_t
 IMP_API int imp_set_profiling(int32_t on);
 IMP_API float imp_sinkhorn_iter_ms(void);
 
-/* mutual-NN matches, GM.compute_matches nets/gm.py:305-320 (int64 indices like torch) */
+/* mutual-NN matches, GM.compute_matches nets/gm.py:305-320 (int64 indices like torch).  Every entry of the outputs is
+ * written: rows / columns beyond a sample's n0s[b] / n1s[b] get the "no match" defaults (-1, 0). */
 typedef struct imp_match_args {
   const float* row_max;
   const int32_t* row_arg;

@@ -97,3 +97,37 @@ def tensor_checksum(t: torch.Tensor) -> float:
 
 def state_dict_checksum(sd: Dict[str, torch.Tensor]) -> float:
     return float(sum(tensor_checksum(v) for v in sd.values()))
+
+
+def make_scene_pair(seed: int, n0: int, n1: int, width: int = 1600, height: int = 1200, noise: float = 0.3, d: int = 256):
+    """One synthetic pair WITH epipolar geometry (for the host pose / RANSAC leg): random 3-D
+    points seen by two pinhole cameras; keypoints = their projections (+ 0.5 px noise), descriptors = one unit vector per
+    3-D point (+ noise in image 1), image 1 in permuted order.  Returns the reference's feed dict (eval/eval_imp.py:59-78)
+    incl. 'K0', 'K1', 'T_0to1', 'pts0_cpu', 'pts1_cpu'."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    n = max(n0, n1)
+    f = 0.9 * width
+    K = np.array([[f, 0., width / 2], [0., f, height / 2], [0., 0., 1.]])
+    uv0 = torch.rand(n, 2, generator=g) * torch.tensor([float(width), float(height)])
+    depth = 4.0 + 4.0 * torch.rand(n, generator=g)
+    x0 = torch.stack([(uv0[:, 0] - width / 2) / f * depth, (uv0[:, 1] - height / 2) / f * depth, depth], 1).double()
+    ang = 0.15
+    R = torch.tensor([[np.cos(ang), 0., np.sin(ang)], [0., 1., 0.], [-np.sin(ang), 0., np.cos(ang)]], dtype=torch.float64)
+    t = torch.tensor([-0.8, 0.05, 0.1], dtype=torch.float64)
+    x1 = x0 @ R.T + t
+    uv1 = torch.stack([x1[:, 0] / x1[:, 2] * f + width / 2, x1[:, 1] / x1[:, 2] * f + height / 2], 1).float()
+    uv1 = uv1 + 0.5 * torch.randn(n, 2, generator=g)
+    desc = torch.nn.functional.normalize(torch.randn(n, d, generator=g), dim=-1)
+    perm = torch.randperm(n, generator=g)
+    d1 = torch.nn.functional.normalize(desc[perm] + noise * torch.randn(n, d, generator=g) / 16.0, dim=-1)
+    s = torch.rand(n, generator=g)
+    k0, k1 = uv0[:n0], uv1[perm][:n1]
+    return {
+        'descriptors0': desc[:n0][None].contiguous(), 'descriptors1': d1[:n1][None].contiguous(),
+        'keypoints0': k0[None].contiguous(), 'keypoints1': k1[None].contiguous(),
+        'scores0': s[:n0][None].contiguous(), 'scores1': s[perm][:n1][None].contiguous(),
+        'image0': torch.zeros(1, 1, height, width), 'image1': torch.zeros(1, 1, height, width),
+        'K0': K, 'K1': K.copy(), 'T_0to1': np.hstack([R.numpy(), t.numpy().reshape(3, 1)]),
+        'pts0_cpu': k0.numpy(), 'pts1_cpu': k1.numpy(), 'perm': perm,
+    }

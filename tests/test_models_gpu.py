@@ -199,3 +199,104 @@ def test_pose_overlap_async_d2h_of_matches():
         for (idx, sc), f in zip(pairs, futs):
             gi, gs = f.result()
             assert np.array_equal(gi, idx.numpy()) and np.array_equal(gs, sc.numpy())
+
+
+def test_adagmn_dual_softmax_with_pruning():
+    """eval_imp.py --use_dual_softmax with EIMP (with_sinkhorn=False): the dual-softmax scorer must honour the kept
+    subsets and feed the pooling with row / column masses (crashed in round 1)."""
+    c = cfg(9, with_sinkhorn=False, n_min_tokens=64)
+    sd = synth.make_state_dict('AdaGMN', 9, seed=31, bin_score=1.0)
+    data = synth.make_pair_batch(seed=32, batch=2, n0=300, n1=280)
+    ref = imp_oracle.Oracle('AdaGMN', c, sd).forward(data)
+    net = AdaGMN(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(to_cuda(data))
+    cnt, _ = net._kept
+    kept = cnt.cpu().tolist()
+    assert kept[:2] == ref['kept0'][-1] and kept[2:] == ref['kept1'][-1], (kept, ref['kept0'][-1], ref['kept1'][-1])
+    assert min(kept) < 280, 'test vector must actually prune'
+    compare(out, ref)
+
+
+@pytest.mark.parametrize('kind', ['GM', 'AdaGMN'])
+def test_run_adapters_gm_adagmn(kind):
+    """mode=1 `run` adapters of GM (nets/gm.py:322-364: returns the score matrix 'p') and AdaGMN (nets/adgm.py:607-635:
+    matched index pairs)."""
+    nl = 3 if kind == 'GM' else 5
+    c = cfg(nl, match_threshold=0.2)
+    sd = synth.make_state_dict(kind, nl, seed=41, bin_score=1.0)
+    data = synth.make_pair_batch(seed=42, batch=1, n0=210, n1=190)
+    nk0 = imp_oracle.normalize_keypoints(data['keypoints0'], data['image0'].shape)
+    nk1 = imp_oracle.normalize_keypoints(data['keypoints1'], data['image1'].shape)
+    rd = {'desc1': data['descriptors0'], 'desc2': data['descriptors1'],
+          'x1': torch.cat([nk0, data['scores0'][..., None]], -1), 'x2': torch.cat([nk1, data['scores1'][..., None]], -1)}
+    net = (GM if kind == 'GM' else AdaGMN)(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    with torch.no_grad():
+        out = net(to_cuda(rd), mode=1)
+    orc = imp_oracle.Oracle(kind, c, sd)
+    nd = {**data, 'norm_keypoints0': nk0, 'norm_keypoints1': nk1}
+    if kind == 'GM':
+        ref = orc.produce_matches(nd, p=0.2, only_last=True)
+        assert out['p'].shape == ref['scores'][-1].shape
+        assert float((out['p'].cpu() - ref['scores'][-1])[:, :-1, :-1].abs().max()) < 1e-3
+    else:
+        ref = orc.produce_matches(nd, p=0.2)
+        ri = ref['indices0'][-1][0]
+        idx0 = torch.where(ri >= 0)[0]
+        assert torch.equal(out['index0'].cpu(), idx0) and torch.equal(out['index1'].cpu(), ri[idx0])
+
+
+def test_ragged_pairs_in_one_batch():
+    """B200 extension: 'n_keypoints0/1' declare zero-padded inputs, so pairs with different keypoint counts share a
+    batch.  Every pair must come out exactly as when it is matched alone."""
+    c = cfg(9)
+    sd = synth.make_state_dict('DGNNS', 9, seed=7)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    sizes = [(700, 640), (512, 700), (333, 401), (690, 690)]
+    Nmax = 704
+    singles = [synth.make_pair_batch(seed=60 + i, batch=1, n0=a, n1=b) for i, (a, b) in enumerate(sizes)]
+    batch = {'image0': singles[0]['image0'], 'image1': singles[0]['image1']}
+    for k, width in (('descriptors', 256), ('keypoints', 2), ('scores', None)):
+        for s in '01':
+            shape = (len(sizes), Nmax) + ((width,) if width else ())
+            t = torch.zeros(shape)
+            for i, d in enumerate(singles):
+                t[i, :d[k + s].shape[1]] = d[k + s][0]
+            batch[k + s] = t
+    batch['n_keypoints0'] = torch.tensor([a for a, _ in sizes], dtype=torch.int32)
+    batch['n_keypoints1'] = torch.tensor([b for _, b in sizes], dtype=torch.int32)
+    with torch.no_grad():
+        out = net.produce_matches(to_cuda(batch), p=0.2, only_last=True)
+        i_b, m_b = out['indices0'][-1].cpu(), out['mscores0'][-1].cpu()
+        for i, (d, (a, b)) in enumerate(zip(singles, sizes)):
+            o = net.produce_matches(to_cuda(d), p=0.2, only_last=True)
+            assert torch.equal(i_b[i, :a], o['indices0'][-1][0].cpu()), f'pair {i}'
+            assert float((m_b[i, :a] - o['mscores0'][-1][0].cpu()).abs().max()) < 1e-5
+            assert bool((i_b[i, a:] == -1).all()) and float(m_b[i, a:].abs().max()) == 0.0
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches(singles[2], p=0.2, only_last=True)
+    assert torch.equal(i_b[2, :sizes[2][0]], ref['indices0'][-1][0])
+
+
+def test_latency_matcher_bucketed_graph_replay():
+    """One pair per call with ragged keypoint counts (eval/eval_imp.py:155-173): bucketed static shapes + CUDA-graph replay
+    with several pairs in flight must reproduce the eager model (identical matches), with one graph per (slot, 128-bucket)."""
+    from imp_release_b200.graphed import LatencyMatcher
+    c = cfg(15)
+    sd = synth.make_state_dict('DGNNS', 15, seed=7)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    sizes = [(700, 640), (641, 700), (760, 655), (650, 767), (512, 300), (700, 700), (705, 640), (300, 512)]
+    pairs = [to_cuda(synth.make_pair_batch(seed=70 + i, batch=1, n0=a, n1=b)) for i, (a, b) in enumerate(sizes)]
+    lm = LatencyMatcher(net, slots=2, p=0.2, only_last=True)
+    with torch.no_grad():
+        tickets = [lm.submit(d) for d in pairs]                 # all in flight before the first result is read
+        outs = [lm.result(t) for t in tickets]
+        torch.cuda.synchronize()
+        for d, o, (a, b) in zip(pairs, outs, sizes):
+            e = net.produce_matches(d, p=0.2, only_last=True)
+            assert o['indices0'][-1].shape == (1, a)
+            assert torch.equal(o['indices0'][-1], e['indices0'][-1])
+            # (the padded problem splits the Sinkhorn rows over CTAs differently: column sums round differently)
+            assert float((o['mscores0'][-1] - e['mscores0'][-1]).abs().max()) < 1e-5
+    assert lm.captures <= 2 * 3                                  # buckets 512, 768 (+ 640 -> 640): at most 3 per slot
+    ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches({k: v.cpu() for k, v in pairs[2].items()}, only_last=True)
+    assert torch.equal(outs[2]['indices0'][-1].cpu(), ref['indices0'][-1])

@@ -46,6 +46,9 @@ for v in variants:
             if ref is None:
                 ref = o.clone()
             row['max_abs_diff_vs_first'] = float((o - ref).abs().max())
+            # determinism / race check: a second run must reproduce the output bit for bit
+            fn()
+            row['rerun_bit_exact'] = bool(torch.equal(out.float(), o))
     res[v] = row
     print(v, row, flush=True)
 json.dump(res, open('gpurun_out/attn_probe.json', 'w'), indent=1)
