@@ -193,6 +193,11 @@ def run_secondary(dev, peaks, n_pairs=224):
     out.update(secondary_b1(dev, n_pairs))
     torch.cuda.empty_cache()
     out.update(secondary_sinkhorn(dev, peaks))
+    torch.cuda.empty_cache()
+    try:
+        out.update(secondary_pose(dev))
+    except ImportError as e:             # no OpenCV on the box
+        out['eval loop with host pose'] = {'skipped': str(e)}
     return out
 
 
@@ -236,7 +241,10 @@ def secondary_b1(dev, n_pairs=224):
                 'scores0': big['scores0'][:, :n0], 'scores1': big['scores1'][:, :n1], 'image0': big['image0'], 'image1': big['image1']}
     pairs = [pair(i) for i in range(n_pairs)]
 
-    def sweep(fn):
+    def sweep(fn, tag=''):
+        if os.environ.get('IMP_BENCH_DEBUG'):
+            torch.cuda.synchronize()
+            print('[secondary_b1] sweep', tag, file=sys.stderr, flush=True)
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -247,31 +255,78 @@ def secondary_b1(dev, n_pairs=224):
         return e0.elapsed_time(e1) / n_pairs, (time.perf_counter() - t0) * 1e3 / n_pairs, res
     with torch.no_grad():
         eager = lambda d: net.produce_matches(d, p=0.2, only_last=True)['indices0'][-1]
-        sweep(eager)                                             # warm-up: workspaces of every bucket
-        ms_eager, wall_eager, ref = sweep(eager)
+        sweep(eager, 'eager warm')                               # warm-up: workspaces of every bucket
+        ms_eager, wall_eager, ref = sweep(eager, 'eager')
         lm1 = LatencyMatcher(net, slots=1)
         t0 = time.perf_counter()
-        sweep(lambda d: lm1(d)['indices0'][-1])                  # builds the graphs (one per 128-keypoint bucket)
+        sweep(lambda d: lm1(d)['indices0'][-1], 'graph1 build')  # builds the graphs (one per 128-keypoint bucket)
         build_s = time.perf_counter() - t0
-        ms_g1, wall_g1, r1 = sweep(lambda d: lm1(d)['indices0'][-1])
-        lm4 = LatencyMatcher(net, slots=4)
-        sweep(lambda d: lm4.submit(d))
-        ms_g4, wall_g4, tickets = sweep(lambda d: lm4.submit(d))
-        r4 = [lm4.result(t)['indices0'][-1] for t in tickets]
-        torch.cuda.synchronize()
+        ms_g1, wall_g1, r1 = sweep(lambda d: lm1(d)['indices0'][-1], 'graph1')
+        multi = {}
+        same4 = True
+        for n_slots in (4, 8):
+            lm4 = LatencyMatcher(net, slots=n_slots)
+            sweep(lambda d: lm4.submit(d), f'graph{n_slots} build')
+            _, wall_g4, tickets = sweep(lambda d: lm4.submit(d), f'graph{n_slots}')
+            r4 = [lm4.result(t)['indices0'][-1] for t in tickets]
+            torch.cuda.synchronize()
+            same4 = same4 and all(torch.equal(a, b) for a, b in zip(ref, r4))
+            multi[n_slots] = (wall_g4, lm4.captures)
+            del lm4, tickets, r4
         same1 = all(torch.equal(a, b) for a, b in zip(ref, r1))
-        same4 = all(torch.equal(a, b) for a, b in zip(ref, r4))
+        best_slots = min(multi, key=lambda k: multi[k][0])
     out['configs[3] one rank: IMP 15 iters, 1 pair per call, ragged N0,N1 in [1200,2000]'] = {
         'pairs': n_pairs, 'distinct_shapes': len(set(sizes)),
         'eager_ms_per_pair': ms_eager, 'eager_wall_ms_per_pair': wall_eager,
         'graph_1_slot_ms_per_pair': ms_g1, 'graph_1_slot_wall_ms_per_pair': wall_g1,
-        'graph_4_slots_ms_per_pair': ms_g4, 'graph_4_slots_wall_ms_per_pair': wall_g4,
-        'pairs_per_s_4_slots': 1e3 / max(ms_g4, wall_g4),
-        'graphs_captured_1_slot': lm1.captures, 'graphs_captured_4_slots': lm4.captures, 'first_sweep_incl_capture_s': build_s,
+        'graph_4_slots_wall_ms_per_pair': multi[4][0], 'graph_8_slots_wall_ms_per_pair': multi[8][0],
+        'pairs_per_s_in_flight': 1e3 / multi[best_slots][0], 'best_slots': best_slots,
+        'graphs_captured_1_slot': lm1.captures, 'graphs_captured_4_slots': multi[4][1], 'first_sweep_incl_capture_s': build_s,
         'graph_results_equal_eager': bool(same1 and same4),
         'note': 'DGNNS.produce_matches(only_last=True); LatencyMatcher = bucketed (128) static shapes + CUDA-graph replay, '
-                '4 slots = 4 pairs in flight on 4 streams; device-resident inputs; ms = CUDA events, wall = host clock'}
+                'k slots = k pairs in flight on k streams (wall clock incl. the final synchronize: CUDA events on one stream do not see the '
+                'others); device-resident inputs; ms = CUDA events, wall = host clock'}
     return out
+
+
+def secondary_pose(dev, n_pairs=32):
+    """SURVEY.md 8(f) rank 1, measured: the one-pair-per-call evaluation loop INCLUDING the host-side pose step
+    (cv2 essential-matrix RANSAC + cheirality, imp_release_b200/host_pose.py = the reference's eval/pose_estimation.py:92-115)
+    on synthetic two-view scenes.  serial = what eval/eval_imp.py:155-173 does (match, blocking copy, RANSAC, next pair);
+    overlapped = LatencyMatcher (4 pairs in flight) + PoseOverlap (RANSAC in worker threads on async-copied matches)."""
+    import cv2  # noqa: F401
+    from imp_release_b200 import DGNNS, host_pose
+    from imp_release_b200.graphed import LatencyMatcher
+    from oracle import synth
+    net = DGNNS(model_config(15))
+    net.load_state_dict(synth.make_state_dict('DGNNS', 15, seed=7))
+    net = net.to(dev).eval()
+    scenes = [synth.make_scene_pair(300 + i, 1400 + 17 * (i % 20), 1500 - 13 * (i % 20)) for i in range(n_pairs)]
+    feed = [{k: (v.to(dev) if torch.is_tensor(v) and k != 'perm' and not k.startswith('image') else v) for k, v in sc.items()}
+            for sc in scenes]
+    workers = min(8, host_cores())
+    with torch.no_grad():
+        for d in feed[:3]:
+            net.produce_matches(d, p=0.2, only_last=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        n_match = 0
+        for d in feed:
+            o = net.produce_matches(d, p=0.2, only_last=True)
+            i0 = o['indices0'][-1][0].cpu().numpy()
+            n_match += int((i0 > -1).sum())
+            host_pose.pose_from_matches(i0, None, d['pts0_cpu'], d['pts1_cpu'], d['K0'], d['K1'])
+        serial = time.perf_counter() - t0
+        lm = LatencyMatcher(net, slots=4)
+        host_pose.evaluate_pairs(lm, feed, workers=workers)            # builds the graphs
+        t0 = time.perf_counter()
+        res = host_pose.evaluate_pairs(lm, feed, workers=workers)
+        overlapped = time.perf_counter() - t0
+    return {'eval loop with host pose (SURVEY 8(f) rank 1): IMP 15 iters + cv2 RANSAC per pair': {
+        'pairs': n_pairs, 'matches_per_pair_mean': n_match / n_pairs, 'poses_found': sum(r is not None for r in res),
+        'serial_pairs_per_s': n_pairs / serial, 'overlapped_pairs_per_s': n_pairs / overlapped, 'pose_workers': workers,
+        'note': 'serial = match -> blocking D2H -> RANSAC -> next pair (the reference loop); overlapped = 4 pairs in flight on '
+                'the GPU, RANSAC in worker threads; wall clock, device-resident inputs'}}
 
 
 def secondary_sinkhorn(dev, peaks):

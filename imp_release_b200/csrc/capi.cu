@@ -22,6 +22,7 @@ long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage);
 void sinkhorn_set_profiling(int on);
 void sinkhorn_set_resident(int on);
 void attention_set_variant(int v);
+void gemm_set_variant(int v);
 float sinkhorn_iter_ms();
 }  // namespace imp
 
@@ -36,6 +37,7 @@ IMP_API int imp_set_option(int32_t key, int32_t value) {
   switch (key) {
     case IMP_OPT_SK_RESIDENT: imp::sinkhorn_set_resident(value); return 0;
     case IMP_OPT_ATTN_VARIANT: imp::attention_set_variant(value); return 0;
+    case IMP_OPT_GEMM_VARIANT: imp::gemm_set_variant(value); return 0;
     default: imp::set_error("imp_set_option: unknown key %d", key); return 2;
   }
 }

@@ -639,7 +639,9 @@ void sinkhorn_set_resident(int on) { g_sk_resident = on ? 1 : 0; }
 long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage) {
   const int R = N0max + 1, C = N1max + 1;
   if (batch <= 0 || N0max <= 0 || N1max <= 0 || C < 64 || C > 4096) return 0;
-  if (sk_resident_enabled() && sk_resident_geometry(batch, R, (C + 3) & ~3, nullptr, nullptr, nullptr)) return 0;
+  const bool allow_resident = sk_resident_enabled() && !(storage & IMP_SK_NO_RESIDENT);
+  storage &= ~IMP_SK_NO_RESIDENT;
+  if (allow_resident && sk_resident_geometry(batch, R, (C + 3) & ~3, nullptr, nullptr, nullptr)) return 0;
   const int bpe = storage == IMP_SK_STORE_F16 ? 2 : (storage == IMP_SK_STORE_F24 ? 3 : 4);
   return (long long)R * ((C + 15) & ~15) * bpe;
 }
@@ -691,7 +693,7 @@ static int run_sinkhorn(const SinkhornArgs& a, cudaStream_t st) {
 
   {  // small problems: everything resident in shared memory, one cooperative launch
     static bool coop_ok = true;  // cleared when a cooperative launch is refused (profiler / MPS)
-    const bool use_resident = sk_resident_enabled() && coop_ok;
+    const bool use_resident = sk_resident_enabled() && coop_ok && !(a.storage & IMP_SK_NO_RESIDENT);
     int rpc, ctas_per_mat;
     size_t smem_res;
     const bool fits = sk_resident_geometry(a.batch, R, a.ldp, &rpc, &ctas_per_mat, &smem_res);

@@ -903,9 +903,10 @@ static int dispatch_nv(const SinkhornArgs& a, cudaStream_t st) {
 }
 
 int run_sinkhorn_compact(const SinkhornArgs& a, cudaStream_t st) {
-  if (a.storage == IMP_SK_STORE_F32) return dispatch_nv<QF32>(a, st);
-  if (a.storage == IMP_SK_STORE_F16) return dispatch_nv<QF16>(a, st);
-  if (a.storage == IMP_SK_STORE_F24) return dispatch_nv<QF24>(a, st);
+  const int storage = a.storage & ~IMP_SK_NO_RESIDENT;
+  if (storage == IMP_SK_STORE_F32) return dispatch_nv<QF32>(a, st);
+  if (storage == IMP_SK_STORE_F16) return dispatch_nv<QF16>(a, st);
+  if (storage == IMP_SK_STORE_F24) return dispatch_nv<QF24>(a, st);
   set_error("sinkhorn: unknown storage format %d", a.storage);
   return 2;
 }

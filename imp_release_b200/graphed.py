@@ -64,8 +64,14 @@ class LatencyMatcher:
         self.model, self.p, self.only_last, self.bucket = model, p, only_last, bucket
         dev = next(model.parameters()).device
         self.device = dev
-        self.slots = [dict(model=(model if i == 0 else model.replica()), stream=torch.cuda.Stream(device=dev), graphs={},
-                           busy=None) for i in range(slots)]
+        # every slot works on a replica (shared weights, own workspaces): the caller's model object stays free for eager use
+        self.slots = [dict(model=model.replica(), stream=torch.cuda.Stream(device=dev), graphs={}) for i in range(slots)]
+        if slots > 1:
+            # several Sinkhorn problems in flight: no cooperative launches (grids of different streams could wait for each
+            # other's SMs); measured on B200 the streaming kernels are also the faster choice here (1.16 vs 1.20 ms per pair
+            # with 8 pairs in flight; a single stream prefers the resident kernel: 3.30 vs 3.51 ms)
+            for sl in self.slots:
+                sl['model'].sinkhorn_resident = False
         self._next = 0
         self.captures = 0
 
@@ -77,6 +83,15 @@ class LatencyMatcher:
               'scores0': torch.zeros(1, Nb, device=dev), 'scores1': torch.zeros(1, Nb, device=dev),
               'n_keypoints0': torch.full((1,), Nb, dtype=torch.int32, device=dev),
               'n_keypoints1': torch.full((1,), Nb, dtype=torch.int32, device=dev)}
+        # A captured graph bakes in the ADDRESSES of every buffer the model caches between calls (Sinkhorn workspaces, the
+        # dist buffer, the engine workspace of this bucket).  Those caches are bounded and evict: start from empty caches,
+        # and after the capture move their contents into the graph entry, which then owns them for its lifetime.
+        def reset_caches():
+            m._sk_cache = {}
+            m._last_sk = None
+            for k in ('_dist', '_dist_key', '_n_tok_cache'):
+                m.__dict__.pop(k, None)
+        reset_caches()
         with torch.no_grad():
             for _ in range(2):                      # warm-up on this stream: weight packing, workspaces, func attributes
                 m.produce_matches(st, p=self.p, only_last=self.only_last)
@@ -84,8 +99,10 @@ class LatencyMatcher:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=slot['stream']):
                 out = m.produce_matches(st, p=self.p, only_last=self.only_last)
+        keep = (m._sk_cache, m.__dict__.get('_dist'), m.__dict__.get('_last_sk'), list(m.engine()._ws.values()))
+        reset_caches()
         self.captures += 1
-        return {'graph': g, 'static': st, 'out': out}
+        return {'graph': g, 'static': st, 'out': out, 'keep': keep}
 
     def submit(self, data: Dict[str, torch.Tensor]):
         from .nets.layers import normalize_keypoints

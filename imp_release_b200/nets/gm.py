@@ -118,13 +118,14 @@ class GM(nn.Module):
         return self._engine
 
     def _sinkhorn_ws(self, B, N0, N1, device, want_mass=False, fresh=False) -> SinkhornWorkspace:
+        res = getattr(self, 'sinkhorn_resident', True)
         if fresh:
-            return SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage)
+            return SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage, resident=res)
         key = (B, N0, N1, str(device), want_mass)
         if key not in self._sk_cache:
             if len(self._sk_cache) > 8:
                 self._sk_cache.clear()
-            self._sk_cache[key] = SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage)
+            self._sk_cache[key] = SinkhornWorkspace(B, N0, N1, device, want_mass, storage=self.sinkhorn_storage, resident=res)
         return self._sk_cache[key]
 
     def replica(self):

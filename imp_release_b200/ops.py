@@ -220,6 +220,7 @@ def small_linear(X, ldx, W, bias, Y, ldy, rows, cin, cout):
 
 
 SK_STORAGE = {'fp32': 0, 'fp16': 1, 'fp24': 2}
+SK_NO_RESIDENT = 0x100
 
 
 def default_sk_storage() -> str:
@@ -230,7 +231,7 @@ def default_sk_storage() -> str:
     return os.environ.get('IMP_SK_STORAGE', 'fp32')
 
 
-OPT_SK_RESIDENT, OPT_ATTN_VARIANT = 1, 2
+OPT_SK_RESIDENT, OPT_ATTN_VARIANT, OPT_GEMM_VARIANT = 1, 2, 3
 
 
 def set_option(key: int, value: int):
@@ -246,10 +247,13 @@ def set_sinkhorn_resident(on: bool):
 class SinkhornWorkspace:
     """Buffers for one Sinkhorn + matching call on [batch, N0max, N1max] problems."""
 
-    def __init__(self, batch: int, N0max: int, N1max: int, device, want_mass: bool = False, storage: Optional[str] = None):
+    def __init__(self, batch: int, N0max: int, N1max: int, device, want_mass: bool = False, storage: Optional[str] = None,
+                 resident: bool = True):
         self.batch, self.N0max, self.N1max = batch, N0max, N1max
         self.ldp = (N1max + 1 + 3) // 4 * 4
         self.storage = SK_STORAGE[storage if storage is not None else default_sk_storage()]
+        if not resident:
+            self.storage |= SK_NO_RESIDENT      # streaming kernels only (no cooperative launch)
         f32 = dict(dtype=torch.float32, device=device)
         self.P = torch.zeros(batch, N0max + 1, self.ldp, **f32)
         self.u = torch.empty(batch, N0max + 1, **f32)

@@ -34,8 +34,8 @@ IMP_API int imp_abi_version(void);
 /* Run-time knobs of the library (process-wide; no reference counterpart -- the reference has no kernels to tune).
  * IMP_OPT_SK_RESIDENT: 1 (default) = small Sinkhorn problems run the shared-memory-resident kernel, 0 = every problem
  * takes the streaming kernels the big batches use (what the parity tests switch on to cover that path with the
- * reference fixtures).  IMP_OPT_ATTN_VARIANT: attention kernel variant (0 = default), for tuning runs. */
-enum { IMP_OPT_SK_RESIDENT = 1, IMP_OPT_ATTN_VARIANT = 2 };
+ * reference fixtures).  IMP_OPT_ATTN_VARIANT / IMP_OPT_GEMM_VARIANT: kernel variants (0 = default), for tuning runs. */
+enum { IMP_OPT_SK_RESIDENT = 1, IMP_OPT_ATTN_VARIANT = 2, IMP_OPT_GEMM_VARIANT = 3 };
 IMP_API int imp_set_option(int32_t key, int32_t value);
 
 /* ---- fp32 <-> hi/lo planes (boundary conversions; `addend` may be NULL) -------------------------------------- */
@@ -164,9 +164,13 @@ typedef struct imp_sinkhorn_args {
   int32_t storage; /* IMP_SK_STORE_* */
   int32_t _pad2;
 } imp_sinkhorn_args;
-#define IMP_SK_STORE_F32 0 /* iterate on the fp32 matrix in P (bit-for-bit the reference recurrence) */
+#define IMP_SK_STORE_F32 0 /* exact fp32 copy of softmax(M): the reference recurrence on fp32 probabilities (default) */
 #define IMP_SK_STORE_F16 1 /* p * 2^14 as IEEE fp16: 2 bytes per element */
 #define IMP_SK_STORE_F24 2 /* top 16 bits of the fp32 word + one byte of mantissa extension (planar): 3 bytes per element */
+/* flag OR-ed into `storage`: never take the shared-memory-resident kernel (a COOPERATIVE launch) for this problem -- for
+ * callers that keep several Sinkhorn problems in flight on different streams, where cooperative grids could wait for each
+ * other's resources */
+#define IMP_SK_NO_RESIDENT 0x100
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream);
 /* Workspace query (the library never allocates): bytes PER MATRIX of q_store that imp_sinkhorn wants for this problem size
  * and storage format, or 0 when it will not use one (small problems run a shared-memory-resident kernel, N1 outside

@@ -197,3 +197,27 @@ def test_pose_overlap_matches_sequential_execution():
     assert peak[0] > 1, 'the pose calls never overlapped'
     for a, b in zip(got, seq):
         assert a[0] == b[0] and a[1] == b[1] and np.allclose(a[2], b[2], rtol=0, atol=0)
+
+
+def test_host_pose_recovers_synthetic_geometry():
+    """host_pose.estimate_pose (restatement of the reference's host-side eval/pose_estimation.py:92-115) on a synthetic
+    two-view scene with 15 % wrong matches: the planted rotation / translation come back, outliers are rejected."""
+    import numpy as np
+    from imp_release_b200 import host_pose
+    from oracle import synth
+    d = synth.make_scene_pair(0, 900, 850)
+    perm = d['perm']
+    inv = torch.empty_like(perm)
+    inv[perm] = torch.arange(len(perm))
+    idx = inv[:900].clone()
+    idx[idx >= 850] = -1
+    wrong = torch.arange(0, 900, 7)
+    idx[wrong] = torch.randint(0, 850, (len(wrong),), generator=torch.Generator().manual_seed(1))
+    E, R, t, inl = host_pose.pose_from_matches(idx.numpy(), None, d['pts0_cpu'], d['pts1_cpu'], d['K0'], d['K1'])
+    Rgt, tgt = d['T_0to1'][:, :3], d['T_0to1'][:, 3]
+    ang = np.rad2deg(np.arccos(np.clip((np.trace(R.T @ Rgt) - 1) / 2, -1, 1)))
+    tang = np.rad2deg(np.arccos(np.clip(np.dot(t, tgt) / np.linalg.norm(tgt) / np.linalg.norm(t), -1, 1)))
+    assert ang < 0.5 and tang < 2.0, (ang, tang)
+    n_valid = int((idx >= 0).sum())
+    assert 0.7 * n_valid < inl.sum() <= n_valid
+    assert host_pose.estimate_pose(d['pts0_cpu'][:4], d['pts1_cpu'][:4], d['K0'], d['K1'], 1.0) is None

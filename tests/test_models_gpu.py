@@ -300,3 +300,33 @@ def test_latency_matcher_bucketed_graph_replay():
     assert lm.captures <= 2 * 3                                  # buckets 512, 768 (+ 640 -> 640): at most 3 per slot
     ref = imp_oracle.Oracle('DGNNS', c, sd).produce_matches({k: v.cpu() for k, v in pairs[2].items()}, only_last=True)
     assert torch.equal(outs[2]['indices0'][-1].cpu(), ref['indices0'][-1])
+
+
+def test_evaluate_pairs_overlaps_gpu_matching_with_host_pose():
+    """the evaluation loop with several pairs in flight on the GPU (LatencyMatcher) and the
+    reference's host-side pose step running in worker threads on asynchronously copied matches (PoseOverlap).  Results
+    come back in order and equal the serial loop."""
+    import numpy as np
+    from imp_release_b200 import host_pose
+    from imp_release_b200.graphed import LatencyMatcher
+    c = cfg(9)
+    sd = synth.make_state_dict('DGNNS', 9, seed=7)
+    net = DGNNS(c); net.load_state_dict(sd, strict=True); net = net.cuda().eval()
+    scenes = [synth.make_scene_pair(100 + i, 600 + 20 * i, 640 - 10 * i) for i in range(6)]
+    feed = [{k: (v.cuda() if torch.is_tensor(v) and k != 'perm' and not k.startswith('image') else v) for k, v in s.items()} for s in scenes]
+    calls = []
+
+    def pose_fn(k0, k1, K0, K1, th):
+        calls.append(len(k0))
+        return host_pose.estimate_pose(k0, k1, K0, K1, th)
+    lm = LatencyMatcher(net, slots=2, p=0.2, only_last=True)
+    res = host_pose.evaluate_pairs(lm, feed, pose_fn=pose_fn, workers=2)
+    assert len(res) == 6 and len(calls) == 6
+    with torch.no_grad():
+        for d, r in zip(feed, res):
+            out = net.produce_matches(d, p=0.2, only_last=True)
+            i0 = out['indices0'][-1][0].cpu().numpy()
+            n = int((i0 > -1).sum())
+            assert n in calls
+            if r is not None:
+                assert r[3].shape == (n,) and r[1].shape == (3, 3)

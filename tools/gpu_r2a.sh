@@ -1,0 +1,18 @@
+#!/bin/bash
+# GPU session (round 2): full GPU test-suite, smoke, default bench (with secondary configs), reference arm, ncu evidence (tag r02a)
+mkdir -p gpurun_out
+timeout 1500 python -m pytest tests -m gpu -q --no-header -p no:cacheprovider > gpurun_out/t_all.log 2>&1
+echo "all gpu tests rc=$?"; tail -n 6 gpurun_out/t_all.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
+timeout 1200 python bench.py --steps 10 --warmup 3 > gpurun_out/bench_r02a.json 2> gpurun_out/bench_r02a.err
+echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/bench_r02a.json').read().strip().splitlines()[-1])
+print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}, d['e2e']['value'], d['roofline']['kernel'][:40], round(d['roofline']['frac'],3), d['clocks'])
+print({k:(v['ms_per_step_share'], v['avg_ms']) for k,v in list(d['kernels'].items())[:10]})
+print({k: round(v['frac'],3) for k,v in d['roofline_other'].items()})
+print(d['cpu_baseline'])
+print(json.dumps(d['secondary'], indent=1))
+PY
+timeout 400 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_r02a_ref.json 2>/dev/null; cat gpurun_out/bench_r02a_ref.json | cut -c1-300
+bash tools/ncu_capture.sh r02a 2>&1 | tail -8

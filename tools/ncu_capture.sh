@@ -2,7 +2,7 @@
 # Round evidence: ncu --set full of the top kernels inside the bench workload + a launch list.  usage: ncu_capture.sh <tag>
 tag=${1:-cur}
 mkdir -p gpurun_out
-for spec in "attention_kernel:3" "skq_iter_kernel:6" "gemm_f16split:40" "instnorm_slab:3"; do
+for spec in "attention_kernel:3" "skq_iter_kernel:6" "gemm_f16split:40" "instnorm_apply:3"; do
   k=${spec%%:*}; skip=${spec##*:}
   timeout 500 ncu --set full --clock-control none --import-source on -k "regex:$k" -s $skip -c 2 -f -o gpurun_out/${tag}_$k python bench.py --ncu --warmup 1 > gpurun_out/${tag}_ncu_$k.log 2>&1
   tail -1 gpurun_out/${tag}_ncu_$k.log

@@ -30,7 +30,9 @@ for rep in sorted(f for f in os.listdir('gpurun_out') if f.startswith(tag + '_')
         tb = to_bytes(r[idx['dram__bytes_read.sum']], units[idx['dram__bytes_read.sum']]) + to_bytes(r[idx['dram__bytes_write.sum']], units[idx['dram__bytes_write.sum']])
         out.append(f'| **dram traffic (read+write)** | {tb/1e6:.1f} | MB |\n')
         fmt = {'0': 'fp32', '1': 'fp16', '2': 'fp24'}
-        key = 'attention' if 'attention_kernel' in name else (('sinkhorn_' + fmt.get(r[idx['Kernel Name']].split('<')[1][:1] if '<' in r[idx['Kernel Name']] else '', 'fp32')) if 'skq_iter' in name or 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
+        full = r[idx['Kernel Name']]
+        first_arg = full.split('<')[1].split(',')[0].replace('(int)', '').strip() if '<' in full else ''
+        key = 'attention' if 'attention_kernel' in name else (('sinkhorn_' + fmt.get(first_arg, 'fp32')) if 'skq_iter' in name or 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
         traffic.setdefault(key, []).append(tb)
     src = subprocess.run(['ncu', '-i', os.path.join('gpurun_out', rep), '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     p = subprocess.run([sys.executable, 'tools/ncu_src.py', '0', '12'], input=src, capture_output=True, text=True).stdout
