@@ -31,7 +31,7 @@ class GemmArgs(C.Structure):
                 ('nsplit', c_i32), ('alpha', c_f32), ('bias', c_vp), ('out_mode', c_i32), ('_pad', c_i32),
                 ('out0', c_vp), ('out1', c_vp), ('out_row_stride', c_i64), ('out_batch_stride', c_i64),
                 ('res_hi', c_vp), ('res_lo', c_vp), ('stat_partial', c_vp), ('stat_straddle', c_vp), ('stat_ns', c_vp),
-                ('stat_np', c_i32), ('_pad2', c_i32)]
+                ('stat_np', c_i32), ('a_np', c_i32), ('a_f32', c_vp), ('a_stats', c_vp)]
 
 
 class AttnArgs(C.Structure):

@@ -57,6 +57,23 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                     uint64_t batch_stride, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  IMP_REQUIRE(fn != nullptr, "cuTensorMapEncodeTiled not available (no CUDA driver?)");
+  IMP_REQUIRE((reinterpret_cast<uintptr_t>(base) & 15) == 0 && (row_stride * 4) % 16 == 0, "fp32 tensor map: 16-byte alignment");
+  cuuint64_t gdim[3] = {inner, rows, batch};
+  cuuint64_t gstr[2] = {row_stride * 4, batch_stride * 4};
+  if (batch == 1 && gstr[1] == 0) gstr[1] = gstr[0] * rows;
+  cuuint32_t box[3] = {32, box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), gdim, gstr, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  IMP_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed (%d)", (int)r);
+  return 0;
+}
+
 int num_sms() {
   static int n = 0;
   if (n == 0) {

@@ -33,6 +33,10 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
                      uint64_t row_stride, uint64_t batch_stride, uint32_t box_inner, uint32_t box_rows,
                      int swizzle_bytes = 128);
 
+// 3-D fp32 tensor map {inner, rows, batch}, box = {32 floats = one 128-byte swizzle span, box_rows, 1}
+int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
+                     uint64_t batch_stride, uint32_t box_rows);
+
 int num_sms();
 
 // cudaFuncSetAttribute state (dynamic shared memory limit, carve-out) is PER DEVICE: a launcher configures its kernels the

@@ -315,6 +315,10 @@ int launch_instnorm_apply(const float* H, const float* stat_partial, const float
   instnorm_finalize_kernel<<<dim3((C + 127) / 128, images), 128, 0, st>>>(
       reinterpret_cast<const float2*>(stat_partial), reinterpret_cast<const float2*>(stat_straddle), ns, Np, C, eps,
       reinterpret_cast<float2*>(stats));
+  if (out_hi == nullptr) {  // statistics only: the consumer GEMM normalises its A operand itself
+    IMP_CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   const int cg = C / 8;
   IMP_REQUIRE(C % 8 == 0 && cg <= 256 && 256 % cg == 0, "instnorm_apply: C / 8 must divide 256 (C = %d)", C);
   const int rows_per_pass = 256 / cg;

@@ -30,6 +30,9 @@ struct GemmKernelParams {
   float2* stat_straddle;  // [images][4][N]
   const int* stat_ns;
   int stat_np;
+  // NORM_A: A = relu((H - mean) * rstd) formed in the kernel from an fp32 H tile (tensor map tm_a_hi) and a_stats
+  const float2* a_stats;  // [images][K] (mean, rstd)
+  int a_np;               // rows per image
 };
 
 // Epilogue of one 128 x BN accumulator tile by the four epilogue warps of a CTA (warp quarter q, TMEM lane = row):
@@ -257,6 +260,57 @@ __device__ __forceinline__ void gemm_epilogue_stats_flush(const GemmKernelParams
   // (the next tile writes s_stat only after its bias-staging barrier, which every thread reaches after this loop)
 }
 
+// NORM_A transform of one staged K block (64 wide) by 128 threads: row r of the fp32 tile at `st` (two 128-byte-swizzled
+// boxes of 32 floats x 128 rows, 16 KB each) becomes relu((x - mean) * rstd) as fp16 hi / lo planes in place.
+__device__ __forceinline__ void gemm_norm_a_row(const GemmKernelParams& p, uint8_t* st, const float2* s_ms, int r, int m0,
+                                                int img_a, int K, int kb) {
+  constexpr int A_BYTES = GEMM_BM * 64 * 2;
+  {
+    const int which = ((m0 + r) / p.a_np > img_a) ? 1 : 0;
+    const float2* stp = s_ms + which * K + kb * 64;
+    uint8_t* row_lo = st + r * 128;            // fp32 floats 0..31 of the K block, later the hi plane
+    uint8_t* row_hi = st + A_BYTES + r * 128;  // fp32 floats 32..63, later the lo plane
+    const int sw = r & 7;
+    float x[64];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float4 a = *reinterpret_cast<const float4*>(row_lo + ((c ^ sw) << 4));
+      const float4 b = *reinterpret_cast<const float4*>(row_hi + ((c ^ sw) << 4));
+      x[4 * c] = a.x; x[4 * c + 1] = a.y; x[4 * c + 2] = a.z; x[4 * c + 3] = a.w;
+      x[32 + 4 * c] = b.x; x[32 + 4 * c + 1] = b.y; x[32 + 4 * c + 2] = b.z; x[32 + 4 * c + 3] = b.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {  // output chunk c = K elements 8c .. 8c+7
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float4 ms = *reinterpret_cast<const float4*>(stp + 8 * c + 2 * e);  // (mean, rstd) x 2, broadcast
+        const float y0 = fmaxf((x[8 * c + 2 * e] - ms.x) * ms.y, 0.f);
+        const float y1 = fmaxf((x[8 * c + 2 * e + 1] - ms.z) * ms.w, 0.f);
+        __half h0, l0, h1, l1;
+        split_f16x2(y0, h0, l0);
+        split_f16x2(y1, h1, l1);
+        __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+        hi[e] = *reinterpret_cast<uint32_t*>(&hh);
+        lo[e] = *reinterpret_cast<uint32_t*>(&ll);
+      }
+      *reinterpret_cast<uint4*>(row_lo + ((c ^ sw) << 4)) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<uint4*>(row_hi + ((c ^ sw) << 4)) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+}
+// (mean, rstd) of the (at most two) images a 128-row tile touches -> shared memory [2][K] float2, by 128 threads
+__device__ __forceinline__ void gemm_norm_a_stage_stats(const GemmKernelParams& p, float2* s_ms, int tid, int img_a, int K) {
+  const int n_img = p.M / p.a_np;
+  asm volatile("bar.sync 3, 128;" ::: "memory");  // every thread is done with the previous tile's statistics
+  for (int i = tid; i < 2 * K / 2; i += 128) {    // float4 = two (mean, rstd) pairs
+    const int which = i / (K / 2), j = i - which * (K / 2);
+    const int img = min(img_a + which, n_img - 1);
+    reinterpret_cast<float4*>(s_ms)[i] = __ldg(reinterpret_cast<const float4*>(p.a_stats + (long long)img * K) + j);
+  }
+  asm volatile("bar.sync 3, 128;" ::: "memory");
+}
+
 // BK = K elements per pipeline stage = one swizzle span (64 fp16 = 128 B, or 32 fp16 = 64 B).  The mainloop is bound by
 // the latency of the TMA fetches, not by their bandwidth, so four 48 KB stages (BK = 32) beat two 96 KB stages (BK = 64).
 template <int BN, int BK>
@@ -267,8 +321,13 @@ struct GemmSmem {
   static constexpr int SBO = 8 * BK * 2;  // bytes between 8-row groups
 };
 
-template <int BN, int STAGES, int BK>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+// NORM_A (the second half of the instance norm disappears into the next GEMM): the A operand is not read
+// as fp16 planes but as the fp32 pre-norm tile H (two 128-byte-swizzled TMA boxes of 32 floats x 128 rows per 64-wide K
+// block, landing exactly where A_hi | A_lo live); warps 2-3 turn every row IN PLACE into relu((H - mean) * rstd) split into
+// the hi / lo planes (row r of both fp32 boxes occupies the same bytes as row r of A_hi and A_lo, and the 16-byte chunks
+// of both layouts are XOR-swizzled by (r & 7)), fence to the async proxy and signal the issuer.
+template <int BN, int STAGES, int BK, bool NORM_A = false>
+__global__ void __launch_bounds__(NORM_A ? GEMM_THREADS + 64 : GEMM_THREADS, 1)
 gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_constant__ CUtensorMap tm_a_lo,
                      const __grid_constant__ CUtensorMap tm_a2_hi, const __grid_constant__ CUtensorMap tm_a2_lo,
                      const __grid_constant__ CUtensorMap tm_b_hi, const __grid_constant__ CUtensorMap tm_b_lo,
@@ -281,8 +340,10 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;   // [ACC]
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC;  // [ACC]
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);  // [ACC][BN] bias slice of the tile being drained
+  uint64_t* a_ready_bar = tmem_empty_bar + ACC;    // [STAGES] NORM_A: the A planes of the stage have been produced
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(a_ready_bar + STAGES);
+  // [ACC][BN] bias slice of the tile being drained; 16-byte aligned (the staging tiles behind it take uint4 accesses)
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));
   // per-epilogue-warp staging tile: 32 rows x 128 B payload, 144 B pitch (conflict-free for 16-byte accesses)
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + ACC * BN);
   float2* s_stat = reinterpret_cast<float2*>(s_stage + 4 * 32 * 144);  // [4 warps][BN] (sum, sum of squares), stats mode only
@@ -302,6 +363,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
+      mbar_init(&a_ready_bar[s], 128);
     }
     for (int a = 0; a < ACC; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -341,10 +403,15 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
           mbar_arrive_expect_tx(&full_bar[s], tx);
           const bool seg2 = kb >= p.KB1;
           const int ka = (seg2 ? kb - p.KB1 : kb) * BK;
-          tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
+          if (NORM_A) {  // fp32 H tile: floats ka .. ka+31 and ka+32 .. ka+63 of 128 rows
+            tma_load_3d(st, &tm_a_hi, &full_bar[s], ka, m0, z);
+            tma_load_3d(st + S::A_BYTES, &tm_a_hi, &full_bar[s], ka + 32, m0, z);
+          } else {
+            tma_load_3d(st, seg2 ? &tm_a2_hi : &tm_a_hi, &full_bar[s], ka, m0, z);
+          }
           tma_load_3d(st + 2 * S::A_BYTES, &tm_b_hi, &full_bar[s], kb * BK, n0, p.b_batched ? z : 0);
           if (split) {
-            tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
+            if (!NORM_A) tma_load_3d(st + S::A_BYTES, seg2 ? &tm_a2_lo : &tm_a_lo, &full_bar[s], ka, m0, z);
             tma_load_3d(st + 2 * S::A_BYTES + S::B_BYTES, &tm_b_lo, &full_bar[s], kb * BK, n0,
                         p.b_batched ? z : 0);
           }
@@ -362,7 +429,7 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         const uint32_t d_tmem = tmem_base + a * BN;
         for (int kb = 0; kb < p.KB; ++kb, ++it) {
           const int s = it % STAGES;
-          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          mbar_wait(NORM_A ? &a_ready_bar[s] : &full_bar[s], (it / STAGES) & 1);  // a_ready implies full (B landed too)
           tc_fence_after();
           const uint32_t a_hi = smem_u32(smem + s * S::STAGE_BYTES);
           const uint32_t a_lo = a_hi + S::A_BYTES;
@@ -387,6 +454,31 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
         umma_commit(&tmem_full_bar[a]);
       }
     }
+  } else if (NORM_A && (warp == 2 || warp == 3 || warp >= 8)) {
+    // ------------------------------------------------------------------ A-operand producer (normalise + ReLU + split)
+    // four warps (2, 3 and the two extra warps 8, 9 of the 320-thread NORM_A instantiation): one tile row per thread
+    if constexpr (NORM_A && BK == 64) {
+      const int tid = warp < 4 ? threadIdx.x - 64 : threadIdx.x - 192;  // 0..127
+      // (mean, rstd) of the tile's (at most two) images, staged once per tile in the shared memory the statistics
+      // epilogue would use (the two modes never meet in one GEMM): [2][K] float2, K <= 512
+      float2* s_ms = s_stat;
+      const int K = p.KB * BK;
+      int it = 0;
+      for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x) {
+        int m0, n0, z;
+        tile_coords(t, m0, n0, z);
+        const int img_a = min(m0, p.M - 1) / p.a_np;
+        gemm_norm_a_stage_stats(p, s_ms, tid, img_a, K);
+        for (int kb = 0; kb < p.KB; ++kb, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          uint8_t* st = smem + s * S::STAGE_BYTES;
+          gemm_norm_a_row(p, st, s_ms, tid, m0, img_a, K, kb);
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the UMMA (async proxy) reads
+          mbar_arrive(&a_ready_bar[s]);
+        }
+      }
+    }
   } else if (warp >= 4) {
     int lt = 0;
     for (int t = blockIdx.x; t < p.tiles_total; t += gridDim.x, ++lt) {
@@ -408,16 +500,20 @@ gemm_f16split_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __grid_c
   }
 }
 
-template <int BN, int STAGES, int BK>
+template <int BN, int STAGES, int BK, bool NORM_A = false>
 static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   using S = GemmSmem<BN, BK>;
   constexpr int SWZ = BK * 2;
   const bool split = g.nsplit == 3;
   CUtensorMap ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo;
   const int Kt = g.K1 + g.K2;
-  if (make_tmap_f16_3d(&ta_hi, g.a_hi, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
+  if (NORM_A) {
+    if (make_tmap_f32_3d(&ta_hi, g.a_f32, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, GEMM_BM)) return 3;
+  } else {
+    if (make_tmap_f16_3d(&ta_hi, g.a_hi, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
+  }
   ta_lo = ta_hi;
-  if (split && make_tmap_f16_3d(&ta_lo, g.a_lo, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
+  if (!NORM_A && split && make_tmap_f16_3d(&ta_lo, g.a_lo, g.K1, g.M, g.batch, g.a_row_stride, g.a_batch_stride, BK, GEMM_BM, SWZ)) return 3;
   ta2_hi = ta_hi;
   ta2_lo = ta_lo;
   if (g.K2 > 0) {
@@ -450,10 +546,12 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.stat_straddle = reinterpret_cast<float2*>(g.stat_straddle);
   p.stat_ns = g.stat_ns;
   p.stat_np = g.stat_np;
+  p.a_stats = reinterpret_cast<const float2*>(g.a_stats);
+  p.a_np = g.a_np;
 
   const size_t smem = STAGES * S::STAGE_BYTES + 1024 + 256 + 2 * BN * sizeof(float) + 4 * 32 * 144 +
                       (BN == 256 ? 4 * BN * sizeof(float2) : 0);
-  auto kern = gemm_f16split_kernel<BN, STAGES, BK>;
+  auto kern = gemm_f16split_kernel<BN, STAGES, BK, NORM_A>;
   static DeviceOnce configured;
   if (configured.first()) {
     IMP_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -462,7 +560,7 @@ static int launch_impl(const GemmArgs& g, cudaStream_t stream) {
   p.tiles_m = (g.M + GEMM_BM - 1) / GEMM_BM;
   p.tiles_total = p.tiles_n * p.tiles_m * g.batch;
   const int grid = p.tiles_total < num_sms() ? p.tiles_total : num_sms();
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo, p);
+  kern<<<grid, NORM_A ? GEMM_THREADS + 64 : GEMM_THREADS, smem, stream>>>(ta_hi, ta_lo, ta2_hi, ta2_lo, tb_hi, tb_lo, p);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -498,7 +596,7 @@ gemm_f16split_pair_kernel(const __grid_constant__ CUtensorMap tm_a_hi, const __g
   uint64_t* tmem_full_bar = empty_bar + STAGES;                                    // [ACC] one per CTA
   uint64_t* tmem_empty_bar = tmem_full_bar + ACC;                                  // [ACC] used in the leader
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + ACC);
-  float* s_bias = reinterpret_cast<float*>(tmem_ptr_smem + 4);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_ptr_smem + 4) + 15) & ~uintptr_t(15));
   uint8_t* s_stage = reinterpret_cast<uint8_t*>(s_bias + ACC * BN);
   float2* s_stat = reinterpret_cast<float2*>(s_stage + 4 * 32 * 144);
 
@@ -667,6 +765,8 @@ static int launch_pair(const GemmArgs& g, cudaStream_t stream) {
   p.stat_straddle = reinterpret_cast<float2*>(g.stat_straddle);
   p.stat_ns = g.stat_ns;
   p.stat_np = g.stat_np;
+  p.a_stats = reinterpret_cast<const float2*>(g.a_stats);
+  p.a_np = g.a_np;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.tiles_m = (g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM);  // 256-row tiles of a pair
   p.tiles_total = p.tiles_n * p.tiles_m * g.batch;
@@ -706,15 +806,29 @@ int launch_gemm(const GemmArgs& g, cudaStream_t stream) {
     IMP_REQUIRE(g.out_mode == IMP_GEMM_OUT_F32 && g.N > 128 && g.N % 32 == 0 && g.batch == 1 && g.stat_np >= GEMM_BM &&
                     g.stat_ns != nullptr && g.stat_straddle != nullptr && g.M % g.stat_np == 0,
                 "gemm: instance-norm statistics need fp32 output, 128 < N (multiple of 32), batch 1 and images of >= 128 rows");
+  if (g.a_f32 != nullptr) {
+    IMP_REQUIRE(g.a_stats != nullptr && g.a_np >= GEMM_BM && g.M % g.a_np == 0 && g.K2 == 0 && g.K1 <= 512 && g.nsplit == 3 &&
+                    g.N > 128 && g.batch == 1,
+                "gemm: the normalising A path needs a_stats, images of >= 128 rows, one K segment <= 512, nsplit 3, N > 128, batch 1");
+    // (a CTA-pair version of this path -- 64 KB stages, three of them -- measured slower: 0.376 vs 0.350 ms; removed)
+    return launch_impl<256, 2, 64, true>(g, stream);
+  }
   if (g_gemm_variant < 0) {
     const char* e = getenv("IMP_GEMM_VARIANT");
     g_gemm_variant = e ? atoi(e) : 0;
   }
   const int variant = g_gemm_variant;
-  // variant 2: CTA pairs (cta_group::2), 256 x 256 tiles
+  // CTA pairs (cta_group::2, 256 x 256 tiles) where they measured faster and the problem fills the 74 pairs at least twice:
+  // the wide, tensor-bound projections (QKV N = 768: 0.289 -> 0.273 ms, MLP0 N = 512: 0.346 -> 0.316 ms at 256 k rows; bit-identical
+  // results).  N = 256 GEMMs (HBM-bound) and the batched score GEMM measure the same either way and stay on the single-CTA
+  // kernel, as do small problems (one pair per call).  IMP_GEMM_VARIANT: 2 = pairs wherever N > 128, 3 = never.
   if (g.N > 128 && variant == 2) return launch_pair(g, stream);
+  if (variant == 0 && g.N >= 512 && !g.b_batched) {
+    const long long pair_tiles = (long long)((g.N + GP_BN - 1) / GP_BN) * ((g.M + 2 * GEMM_BM - 1) / (2 * GEMM_BM)) * g.batch;
+    if (pair_tiles >= 2LL * (num_sms() / 2)) return launch_pair(g, stream);
+  }
   // two 96 KB stages (BK = 64) and four 48 KB stages (BK = 32) measure the same on B200 (tools/gemm_probe.py)
-  if (g.N > 128) return variant == 0 ? launch_impl<256, 2, 64>(g, stream) : launch_impl<256, 4, 32>(g, stream);
+  if (g.N > 128) return variant != 1 ? launch_impl<256, 2, 64>(g, stream) : launch_impl<256, 4, 32>(g, stream);
   return launch_impl<128, 3, 64>(g, stream);
 }
 

@@ -299,6 +299,30 @@ __device__ __forceinline__ void skq_produce_dist(const SkqParams& p, const SkqSm
   }
 }
 
+// producer warp for a pass that streams the stored fp32 copy (final pass with fp32 storage): T rows per slot
+template <int T>
+__device__ __forceinline__ void skq_produce_q32(const SkqParams& p, const SkqSmem& s) {
+  if (lane_id() != 0) return;
+  int n = 0, slot = 0;
+  uint32_t phase = 0;
+  const size_t stride = (size_t)p.ldq * 4;
+  for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    SkqCta c;
+    if (!skq_item(p, item, c)) continue;
+    const unsigned char* q0 = p.Q + c.b * p.q_bs;
+    const uint32_t bytes = (uint32_t)c.Cq * 4;
+    const int nbatch = (c.nrows + T - 1) / T;
+    for (int j = 0; j < nbatch; ++j, ++n, skq_ring_next(slot, phase, p.nslots)) {
+      skq_wait(&s.empty_bar[slot], phase ^ 1u);
+      const int i0 = c.row0 + j * T;
+      const int nb = min(T, c.nrows - j * T);
+      mbar_arrive_expect_tx(&s.full_bar[slot], bytes * nb);
+      unsigned char* dst = s.ring + (size_t)slot * p.slot_bytes;
+      for (int t = 0; t < nb; ++t) bulk_copy_g2s(dst + (size_t)t * p.row_bytes, q0 + (size_t)(i0 + t) * stride, bytes, &s.full_bar[slot]);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // init: p = softmax_rows(pad(dist)) -> stored copy + row statistics (+ first half-iteration: u with v = 1 and the
 // column sums with that u, from the exact fp32 p).  Lanes own NG = 2 * NVW float4 column groups.
@@ -627,14 +651,18 @@ __device__ __forceinline__ SkqBest skq_tr_reduce_best(SkqBest (&a)[T], int lane)
   return r;
 }
 
-template <int NVW, int T, bool WRITE, bool MASS>
+// FROM_Q (fp32 storage): the stored copy IS the exact p = e * (1 / sum) the init pass derived, so the final pass streams it
+// instead of dist and skips the re-derivation (exp, dustbin / pad case analysis): same bits, ~1/3 fewer instructions in a
+// pass that is instruction-bound (3 TB/s with the re-derivation).
+template <int NVW, int T, bool WRITE, bool MASS, bool FROM_Q>
 __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqParams p) {
   extern __shared__ __align__(16) unsigned char skq_smem[];
   constexpr int NG = 2 * NVW;
   const SkqSmem s = skq_smem_setup(skq_smem, p);
   const int warp = threadIdx.x >> 5, lane = lane_id();
   if (warp == SKQ_CW) {
-    skq_produce_dist<T>(p, s);
+    if (FROM_Q) skq_produce_q32<T>(p, s);
+    else skq_produce_dist<T>(p, s);
     return;
   }
   const float bin = *p.bin_score;
@@ -672,8 +700,10 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
     float my_m = 0.f, my_inv = 0.f, my_u = 1.f;
     if (lane < nb) {
       const long long o = (long long)b * p.Rmax + i0 + lane;
-      my_m = p.row_m[o];
-      my_inv = p.row_inv[o];
+      if (!FROM_Q) {
+        my_m = p.row_m[o];
+        my_inv = p.row_inv[o];
+      }
       if (p.do_iter) my_u = p.u[o];
     }
     skq_wait(&s.full_bar[slot], phase);
@@ -685,7 +715,10 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
         const bool bin_row = (i0 + t == c.R - 1);
         const float* srow = reinterpret_cast<const float*>(sb + (size_t)t * p.row_bytes);
 #pragma unroll
-        for (int k = 0; k < NG; ++k) x[t][k] = skq_logits_fast(srow, c0s[k], c.C, interior[k], bin_row, bin);
+        for (int k = 0; k < NG; ++k) {
+          if (FROM_Q) x[t][k] = c0s[k] < c.Cq ? *reinterpret_cast<const float4*>(srow + c0s[k]) : make_float4(0.f, 0.f, 0.f, 0.f);
+          else x[t][k] = skq_logits_fast(srow, c0s[k], c.C, interior[k], bin_row, bin);
+        }
       }
 
     SkqBest rb[T];
@@ -704,10 +737,12 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
 #pragma unroll
         for (int k = 0; k < NG; ++k) {
           // (p u) v like the reference's p * u * v, with p = e * (1 / sum); groups beyond C evaluate to exactly 0
-          const float o[4] = {__fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].x, mL), inv), ui), v[k].x),
-                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].y, mL), inv), ui), v[k].y),
-                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].z, mL), inv), ui), v[k].z),
-                              __fmul_rn(__fmul_rn(__fmul_rn(skq_exp(x[t][k].w, mL), inv), ui), v[k].w)};
+          const float pp[4] = {FROM_Q ? x[t][k].x : __fmul_rn(skq_exp(x[t][k].x, mL), inv),
+                               FROM_Q ? x[t][k].y : __fmul_rn(skq_exp(x[t][k].y, mL), inv),
+                               FROM_Q ? x[t][k].z : __fmul_rn(skq_exp(x[t][k].z, mL), inv),
+                               FROM_Q ? x[t][k].w : __fmul_rn(skq_exp(x[t][k].w, mL), inv)};
+          const float o[4] = {__fmul_rn(__fmul_rn(pp[0], ui), v[k].x), __fmul_rn(__fmul_rn(pp[1], ui), v[k].y),
+                              __fmul_rn(__fmul_rn(pp[2], ui), v[k].z), __fmul_rn(__fmul_rn(pp[3], ui), v[k].w)};
           if (WRITE && c0s[k] < c.C) *reinterpret_cast<float4*>(prow + c0s[k]) = make_float4(o[0], o[1], o[2], o[3]);
           if (inner_row) {
             // column trackers: rows ascend, so a strict > keeps the lowest row (the dustbin column is never flushed)
@@ -801,6 +836,8 @@ __global__ void __launch_bounds__(SKQ_THREADS, 2) skq_final_kernel(const SkqPara
 template <int FMT, int NVW, int T_ITER, int T_DIST>
 static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   constexpr int BPE = QFmt<FMT>::BPE;
+  constexpr bool FQ = FMT == QF32;                  // final pass streams the exact fp32 copy instead of dist
+  constexpr int T_FIN = FQ ? T_ITER : T_DIST;
   const int R = a.N0max + 1, C = a.N1max + 1;
   const int ldq = (C + 15) & ~15;
   const size_t q_row = (size_t)ldq * BPE;
@@ -818,10 +855,10 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
     };
     IMP_CUDA_OK(conf((const void*)skq_init_kernel<FMT, NVW, T_DIST>));
     IMP_CUDA_OK(conf((const void*)skq_iter_kernel<FMT, NVW, T_ITER>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, false, false>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, false, true>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, false>));
-    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_DIST, true, true>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_FIN, false, false, FQ>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_FIN, false, true, FQ>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_FIN, true, false, FQ>));
+    IMP_CUDA_OK(conf((const void*)skq_final_kernel<NVW, T_FIN, true, true, FQ>));
   }
   SkqParams p;
   p.dist = a.dist; p.dist_bs = a.dist_batch_stride; p.ldd = a.ldd; p.bin_score = a.bin_score;
@@ -872,21 +909,27 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   }
   if (prof) sk_profile_end(st, iters - 1);
 
-  p.nslots = slots_d;
-  p.row_bytes = (int)d_row;
-  p.slot_bytes = (int)(T_DIST * d_row);
+  if (FQ) {  // slot geometry of the iteration sweeps (rows of the stored copy)
+    p.nslots = slots_q;
+    p.row_bytes = (int)q_row;
+    p.slot_bytes = (int)(T_ITER * q_row);
+  } else {
+    p.nslots = slots_d;
+    p.row_bytes = (int)d_row;
+    p.slot_bytes = (int)(T_DIST * d_row);
+  }
   p.col_prev = col[(iters > 0 ? iters - 1 : 0) % 3];
   p.col_acc = nullptr;
   p.col_zero = nullptr;
   {
-    const size_t smem = (size_t)slots_d * p.slot_bytes + SKQ_FIXED_SMEM;
+    const size_t smem = (size_t)p.nslots * p.slot_bytes + SKQ_FIXED_SMEM;
     const bool mass = a.col_mass != nullptr || a.row_mass != nullptr;
     if (a.write_scores) {
-      if (mass) skq_final_kernel<NVW, T_DIST, true, true><<<grid, SKQ_THREADS, smem, st>>>(p);
-      else skq_final_kernel<NVW, T_DIST, true, false><<<grid, SKQ_THREADS, smem, st>>>(p);
+      if (mass) skq_final_kernel<NVW, T_FIN, true, true, FQ><<<grid, SKQ_THREADS, smem, st>>>(p);
+      else skq_final_kernel<NVW, T_FIN, true, false, FQ><<<grid, SKQ_THREADS, smem, st>>>(p);
     } else {
-      if (mass) skq_final_kernel<NVW, T_DIST, false, true><<<grid, SKQ_THREADS, smem, st>>>(p);
-      else skq_final_kernel<NVW, T_DIST, false, false><<<grid, SKQ_THREADS, smem, st>>>(p);
+      if (mass) skq_final_kernel<NVW, T_FIN, false, true, FQ><<<grid, SKQ_THREADS, smem, st>>>(p);
+      else skq_final_kernel<NVW, T_FIN, false, false, FQ><<<grid, SKQ_THREADS, smem, st>>>(p);
     }
   }
   IMP_CUDA_OK(cudaGetLastError());

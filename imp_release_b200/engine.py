@@ -26,6 +26,8 @@ D = 256
 # instance-norm statistics fused into the epilogue of the first MLP GEMM (IMP_FUSED_INSTNORM=0: stand-alone slab kernel)
 import os as _os
 FUSED_INSTNORM = _os.environ.get('IMP_FUSED_INSTNORM', '1') != '0'
+# ... and the normalisation itself folded into the A-operand path of the second MLP GEMM (IMP_FUSED_NORM_A=0: apply pass)
+FUSED_NORM_A = _os.environ.get('IMP_FUSED_NORM_A', '1') != '0'
 
 
 def head_perm(device) -> torch.Tensor:
@@ -255,6 +257,13 @@ class Engine:
         ops.gemm(ws.X, L['W0'], M=T, N=2 * D, K1=D, K2=D, a2=ws.A, a_row_stride=D, a2_row_stride=D, b_row_stride=2 * D,
                  bias=L['b0'], out_mode=ops.OUT_F32, out0=ws.H, out_row_stride=2 * D,
                  stats=ws.in_stats if fused else None, ns=st.n_tok, Np=Np)
+        if fused and FUSED_NORM_A:
+            # statistics -> (mean, rstd); the normalisation itself happens in the A-operand path of the next GEMM
+            ops.instnorm_apply(ws.H, ws.in_stats, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=None)
+            ops.gemm(ws.Hn, L['W3'], M=T, N=D, K1=2 * D, a_row_stride=2 * D, b_row_stride=2 * D, bias=L['b3'],
+                     out_mode=ops.OUT_SPLIT_RESID, out0=ws.X.hi, out1=ws.X.lo, out_row_stride=D, res=ws.X,
+                     a_f32=ws.H, a_stats=ws.in_stats, Np=Np)
+            return
         if fused:
             ops.instnorm_apply(ws.H, ws.in_stats, batch=n_img, Nmax=Np, C_=2 * D, ns=st.n_tok, out=ws.Hn)
         else:

@@ -95,13 +95,18 @@ def gemm(a: Planes, b: Planes, *, M: int, N: int, K1: int, batch: int = 1, a_row
          bias: Optional[torch.Tensor] = None, out_mode: int = OUT_F32, out0: torch.Tensor = None,
          out1: Optional[torch.Tensor] = None, out_row_stride: int = 0, out_batch_stride: int = 0,
          res: Optional[Planes] = None, a_offset: int = 0, a2_offset: int = 0, b_offset: int = 0, out_offset: int = 0,
-         stats: Optional['InstNormStats'] = None, ns: Optional[torch.Tensor] = None, Np: int = 0):
+         stats: Optional['InstNormStats'] = None, ns: Optional[torch.Tensor] = None, Np: int = 0,
+         a_f32: Optional[torch.Tensor] = None, a_stats: Optional['InstNormStats'] = None):
     """D = alpha * A.B^T (+bias)(+res).  Offsets are in elements from the start of the plane tensors.
-    stats / ns / Np: fused instance-norm statistics of the fp32 output (see imp_gemm_args)."""
+    stats / ns / Np: fused instance-norm statistics of the fp32 output (see imp_gemm_args).
+    a_f32 / a_stats (+ Np): A = relu(instance_norm(a_f32)) formed inside the kernel (`a` is ignored)."""
     g = GemmArgs()
     esz = 2
-    g.a_hi = a.hi.data_ptr() + a_offset * esz
-    g.a_lo = a.lo.data_ptr() + a_offset * esz
+    if a_f32 is not None:
+        g.a_f32, g.a_stats, g.a_np = ptr(a_f32), ptr(a_stats.stats), Np
+    else:
+        g.a_hi = a.hi.data_ptr() + a_offset * esz
+        g.a_lo = a.lo.data_ptr() + a_offset * esz
     if a2 is not None:
         g.a2_hi = a2.hi.data_ptr() + a2_offset * esz
         g.a2_lo = a2.lo.data_ptr() + a2_offset * esz
@@ -199,12 +204,16 @@ class InstNormStats:
         self.stats = torch.zeros(n_img, C_, 2, **f32)
 
 
-def instnorm_apply(H: torch.Tensor, st: InstNormStats, *, batch: int, Nmax: int, C_: int, ns, out: Planes, eps: float = 1e-3,
-                   relu: bool = True):
-    """Second half of the fused instance norm: statistics left by gemm(..., stats=st) -> normalise + ReLU + hi/lo split."""
-    with _Span(f'instnorm_apply_c{C_}', 2, 8.0 * batch * Nmax * C_):
+def instnorm_apply(H: torch.Tensor, st: InstNormStats, *, batch: int, Nmax: int, C_: int, ns, out: Optional[Planes],
+                   eps: float = 1e-3, relu: bool = True):
+    """Second half of the fused instance norm: statistics left by gemm(..., stats=st) -> (mean, rstd) in st.stats, then
+    normalise + ReLU + hi/lo split into `out` -- or, with out=None, nothing more (the consumer GEMM normalises its A operand
+    itself: gemm(..., a_f32=H, a_stats=st))."""
+    name = f'instnorm_apply_c{C_}' if out is not None else 'instnorm_finalize'
+    with _Span(name, 2 if out is not None else 1, 8.0 * batch * Nmax * C_ if out is not None else 0.0):
         check(_lib.load().imp_instnorm_apply(ptr(H), ptr(st.partial), ptr(st.straddle), ptr(ns), Nmax, C_, batch, eps, int(relu),
-                                             ptr(st.stats), ptr(out.hi), ptr(out.lo), stream_ptr()), 'imp_instnorm_apply')
+                                             ptr(st.stats), ptr(out.hi) if out is not None else None,
+                                             ptr(out.lo) if out is not None else None, stream_ptr()), 'imp_instnorm_apply')
 
 
 def kenc_input(norm_kpts: torch.Tensor, scores: torch.Tensor, out: torch.Tensor):

@@ -71,7 +71,13 @@ typedef struct imp_gemm_args {
   float* stat_straddle;
   const int32_t* stat_ns;
   int32_t stat_np;
-  int32_t _pad2;
+  /* Optional normalising A operand (the consumer side of the fused instance norm, nets/layers.py:68-72 -> :73): with a_f32
+   * != NULL the A planes are ignored and A = relu((a_f32 - mean) * rstd), formed in the kernel from the fp32 matrix
+   * a_f32 [M, K1] (row stride a_row_stride floats) and a_stats [M / a_np][K1][2] = (mean, rstd) per image and channel
+   * (what imp_instnorm_apply's finalize step leaves in `stats`).  One K segment, nsplit = 3, N > 128, batch = 1. */
+  int32_t a_np;
+  const float* a_f32;
+  const float* a_stats;
 } imp_gemm_args;
 IMP_API int imp_gemm(const imp_gemm_args* args, void* stream);
 
@@ -125,6 +131,8 @@ IMP_API int imp_instnorm_relu(const float* H, int64_t h_batch_stride, int32_t ld
 IMP_API int imp_instnorm_apply(const float* H, const float* stat_partial, const float* stat_straddle, const int32_t* ns,
                        int32_t Np, int32_t C, int32_t images, float eps, int32_t relu, float* stats, void* out_hi,
                        void* out_lo, void* stream);
+/* (out_hi == NULL: only the reduction to `stats` runs -- the normalisation then happens inside the consuming imp_gemm,
+ * see imp_gemm_args.a_f32) */
 
 /* ---- keypoint encoder narrow layers (3->32, 32->64), nets/layers.py:80-90 ----------------------------------- */
 IMP_API int imp_kenc_input(const float* norm_kpts, const float* scores, float* out_xyz4, int64_t tokens, void* stream);

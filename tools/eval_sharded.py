@@ -1,0 +1,82 @@
+"""BASELINE.json configs[3]: YFCC-shape evaluation (4000 ragged pairs, N0, N1 ~ U{1200..2000}, IMP 15 iterations,
+produce_matches(only_last=True), one pair per call as in eval/eval_imp.py:155-173) sharded over the ranks of one node.
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 tools/eval_sharded.py
+Prints one JSON object on rank 0: pairs/s (wall clock between barriers, max over ranks), device-resident and pinned-host inputs."""
+import json
+import os
+import sys
+import time
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, '.')
+from imp_release_b200 import DGNNS, shard  # noqa: E402
+from oracle import synth  # noqa: E402
+
+rank, world, local = int(os.environ.get('RANK', 0)), int(os.environ.get('WORLD_SIZE', 1)), int(os.environ.get('LOCAL_RANK', 0))
+torch.cuda.set_device(local)
+dev = torch.device('cuda', local)
+if world > 1:
+    dist.init_process_group('nccl', device_id=dev)
+n_pairs = int(sys.argv[1]) if len(sys.argv) > 1 else 4000
+slots = int(sys.argv[2]) if len(sys.argv) > 2 else 8
+cfg = dict(n_layers=15, GNN_layers=['self', 'cross'] * 15, norm_fn='in', ac_fn='relu', sinkhorn_iterations=20, with_sinkhorn=True,
+           descriptor_dim=256, n_min_tokens=256)
+net = DGNNS(cfg)
+net.load_state_dict(synth.make_state_dict('DGNNS', 15, seed=7))
+net = net.to(dev).eval()
+ids = shard.shard_indices(n_pairs, rank, world)
+g = torch.Generator(device=dev)
+pairs = {}
+for i in ids:                                   # synthetic pair i: seed = pair index, generated on the device
+    g.manual_seed(1000 + i)
+    n0, n1 = [int(v) for v in torch.randint(1200, 2001, (2,), generator=torch.Generator().manual_seed(i)).tolist()]
+    n = max(n0, n1)
+    d0 = torch.nn.functional.normalize(torch.randn(1, n, 256, device=dev, generator=g), dim=-1)
+    perm = torch.randperm(n, device=dev, generator=g)
+    d1 = torch.nn.functional.normalize(d0[:, perm] + 0.3 * torch.randn(1, n, 256, device=dev, generator=g) / 16, dim=-1)
+    k0 = torch.rand(1, n, 2, device=dev, generator=g) * torch.tensor([1600., 1200.], device=dev)
+    k1 = k0[:, perm] + 2 * torch.randn(1, n, 2, device=dev, generator=g)
+    s0 = torch.rand(1, n, device=dev, generator=g)
+    pairs[i] = {'descriptors0': d0[:, :n0].contiguous(), 'descriptors1': d1[:, :n1].contiguous(), 'keypoints0': k0[:, :n0].contiguous(),
+                'keypoints1': k1[:, :n1].contiguous(), 'scores0': s0[:, :n0].contiguous(), 'scores1': s0[:, perm][:, :n1].contiguous(),
+                'image0': torch.zeros(1, 1, 1200, 1600), 'image1': torch.zeros(1, 1, 1200, 1600)}
+
+
+def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run(get_pair):
+    barrier()
+    t0 = time.perf_counter()
+    out = shard.evaluate_sharded(net, get_pair, n_pairs, 2000, rank, world, slots=slots)
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    return float(dt), out
+
+
+res = {}
+t_cold, _ = run(lambda i: pairs[i])             # includes graph capture (7 buckets x slots per rank)
+t_dev, out = run(lambda i: pairs[i])
+keys = ('descriptors0', 'descriptors1', 'keypoints0', 'keypoints1', 'scores0', 'scores1')
+host = {i: {k: (v.cpu().pin_memory() if k in keys else v) for k, v in d.items()} for i, d in pairs.items()}
+t_host, out_h = run(lambda i: host[i])
+if rank == 0:
+    i0, s0 = out
+    same = bool(torch.equal(i0, out_h[0]))
+    print(json.dumps({'config': 'BASELINE.json configs[3]: %d ragged pairs (N0, N1 ~ U{1200..2000}), IMP 15 iters, '
+                                'produce_matches(only_last=True), one pair per call, rank-strided over %d GPUs, %d pairs in flight per GPU'
+                                % (n_pairs, world, slots),
+                      'n_gpus': world, 'pairs_per_s_device_resident': n_pairs / t_dev, 'pairs_per_s_pinned_host_inputs': n_pairs / t_host,
+                      'first_pass_incl_graph_capture_pairs_per_s': n_pairs / t_cold, 'seconds': {'cold': t_cold, 'device': t_dev, 'host': t_host},
+                      'matched_keypoints_total': int((i0 >= 0).sum()), 'host_equals_device_inputs': same,
+                      'gathered_shape': list(i0.shape)}))
+if world > 1:
+    dist.destroy_process_group()

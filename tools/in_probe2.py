@@ -45,3 +45,21 @@ print('max |slab - fused| over valid rows: %.3e' % err)
 h = H.view(n_img, Np, C)[3, :int(ns[3])].double()
 ref = torch.relu((h - h.mean(0)) / torch.sqrt(h.var(0, unbiased=False) + 1e-3))
 print('fused vs fp64 reference (image 3): %.3e ; slab vs fp64: %.3e' % (float((b[3, :int(ns[3])].double() - ref).abs().max()), float((a[3, :int(ns[3])].double() - ref).abs().max())))
+
+# ---- consumer side (K5): second MLP GEMM with the normalisation in its A-operand path vs apply pass + plain GEMM
+W3 = planes(256, 512, 0.05); b3 = torch.randn(256, device='cuda', generator=g)
+Xr = planes(T, 256)
+def mlp1_plain(o):
+    ops.instnorm_apply(H, st, batch=n_img, Nmax=Np, C_=C, ns=ns, out=out_b)
+    ops.gemm(out_b, W3, M=T, N=256, K1=512, a_row_stride=512, b_row_stride=512, bias=b3, out_mode=ops.OUT_SPLIT_RESID,
+             out0=o.hi, out1=o.lo, out_row_stride=256, res=Xr)
+def mlp1_fused(o):
+    ops.instnorm_apply(H, st, batch=n_img, Nmax=Np, C_=C, ns=ns, out=None)
+    ops.gemm(out_b, W3, M=T, N=256, K1=512, a_row_stride=512, b_row_stride=512, bias=b3, out_mode=ops.OUT_SPLIT_RESID,
+             out0=o.hi, out1=o.lo, out_row_stride=256, res=Xr, a_f32=H, a_stats=st, Np=Np)
+gem(st)
+o1, o2 = ops.Planes.empty((T, 256), 'cuda'), ops.Planes.empty((T, 256), 'cuda')
+mlp1_plain(o1); mlp1_fused(o2); torch.cuda.synchronize()
+print('MLP1 fused-A vs apply+GEMM: max |diff| = %.3e (max |out| %.2f)' % (float((o1.float() - o2.float()).abs().max()), float(o1.float().abs().max())))
+print('apply + gemm      %.4f ms' % t(lambda: mlp1_plain(o1)))
+print('finalize + gemm(A=norm(H)) %.4f ms' % t(lambda: mlp1_fused(o2)))
