@@ -262,11 +262,16 @@ def secondary_b1(dev, n_pairs=224):
         sweep(lambda d: lm1(d)['indices0'][-1], 'graph1 build')  # builds the graphs (one per 128-keypoint bucket)
         build_s = time.perf_counter() - t0
         ms_g1, wall_g1, r1 = sweep(lambda d: lm1(d)['indices0'][-1], 'graph1')
-        multi = {}
+        multi, host_ms = {}, {}
         same4 = True
         for n_slots in (4, 8):
             lm4 = LatencyMatcher(net, slots=n_slots)
             sweep(lambda d: lm4.submit(d), f'graph{n_slots} build')
+            torch.cuda.synchronize()
+            t_h = time.perf_counter()
+            for d in pairs[:64]:                                   # host cost of a submit (no synchronisation inside)
+                lm4.submit(d)
+            host_ms[n_slots] = (time.perf_counter() - t_h) * 1e3 / 64
             _, wall_g4, tickets = sweep(lambda d: lm4.submit(d), f'graph{n_slots}')
             r4 = [lm4.result(t)['indices0'][-1] for t in tickets]
             torch.cuda.synchronize()
@@ -281,6 +286,7 @@ def secondary_b1(dev, n_pairs=224):
         'graph_1_slot_ms_per_pair': ms_g1, 'graph_1_slot_wall_ms_per_pair': wall_g1,
         'graph_4_slots_wall_ms_per_pair': multi[4][0], 'graph_8_slots_wall_ms_per_pair': multi[8][0],
         'pairs_per_s_in_flight': 1e3 / multi[best_slots][0], 'best_slots': best_slots,
+        'host_ms_per_submit': host_ms[best_slots],
         'graphs_captured_1_slot': lm1.captures, 'graphs_captured_4_slots': multi[4][1], 'first_sweep_incl_capture_s': build_s,
         'graph_results_equal_eager': bool(same1 and same4),
         'note': 'DGNNS.produce_matches(only_last=True); LatencyMatcher = bucketed (128) static shapes + CUDA-graph replay, '

@@ -75,14 +75,27 @@ class LatencyMatcher:
         self._next = 0
         self.captures = 0
 
+    # per-submit scalars travel in ONE small pinned -> device copy: [cx0, cy0, scale0, cx1, cy1, scale1, N0, N1]
+    _RING = 64
+
     def _capture(self, slot, Nb: int):
         m, dev = slot['model'], self.device
         st = {'descriptors0': torch.zeros(1, Nb, 256, device=dev), 'descriptors1': torch.zeros(1, Nb, 256, device=dev),
-              'norm_keypoints0': torch.zeros(1, Nb, 2, device=dev), 'norm_keypoints1': torch.zeros(1, Nb, 2, device=dev),
               'keypoints0': torch.zeros(1, Nb, 2, device=dev), 'keypoints1': torch.zeros(1, Nb, 2, device=dev),
-              'scores0': torch.zeros(1, Nb, device=dev), 'scores1': torch.zeros(1, Nb, device=dev),
-              'n_keypoints0': torch.full((1,), Nb, dtype=torch.int32, device=dev),
-              'n_keypoints1': torch.full((1,), Nb, dtype=torch.int32, device=dev)}
+              'scores0': torch.zeros(1, Nb, device=dev), 'scores1': torch.zeros(1, Nb, device=dev)}
+        params = torch.tensor([0., 0., 1., 0., 0., 1., float(Nb), float(Nb)], device=dev)
+
+        def forward():
+            # keypoint normalisation (nets/layers.py:49-56: (kpts - size / 2) / (0.7 max(w, h))) and the per-pair counts
+            # from the parameter vector, INSIDE the graph: same fp32 operations in the same order as normalize_keypoints
+            d = dict(st)
+            # (multiplication by the fp32 reciprocal: that is what ATen's div_(python scalar) in normalize_keypoints does)
+            d['norm_keypoints0'] = (st['keypoints0'] - params[0:2]) * params[2]
+            d['norm_keypoints1'] = (st['keypoints1'] - params[3:5]) * params[5]
+            d['n_keypoints0'] = params[6:7].to(torch.int32)
+            d['n_keypoints1'] = params[7:8].to(torch.int32)
+            return m.produce_matches(d, p=self.p, only_last=self.only_last)
+
         # A captured graph bakes in the ADDRESSES of every buffer the model caches between calls (Sinkhorn workspaces, the
         # dist buffer, the engine workspace of this bucket).  Those caches are bounded and evict: start from empty caches,
         # and after the capture move their contents into the graph entry, which then owns them for its lifetime.
@@ -94,18 +107,29 @@ class LatencyMatcher:
         reset_caches()
         with torch.no_grad():
             for _ in range(2):                      # warm-up on this stream: weight packing, workspaces, func attributes
-                m.produce_matches(st, p=self.p, only_last=self.only_last)
+                forward()
             slot['stream'].synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=slot['stream']):
-                out = m.produce_matches(st, p=self.p, only_last=self.only_last)
+                out = forward()
         keep = (m._sk_cache, m.__dict__.get('_dist'), m.__dict__.get('_last_sk'), list(m.engine()._ws.values()))
         reset_caches()
         self.captures += 1
-        return {'graph': g, 'static': st, 'out': out, 'keep': keep}
+        pin = torch.cuda.is_available()
+        host_params = torch.zeros(self._RING, 8, pin_memory=pin)
+        return {'graph': g, 'static': st, 'params': params, 'out': out, 'keep': keep, 'host_params': host_params,
+                'host_np': host_params.numpy(), 'host_events': [None] * self._RING, 'n': 0}
+
+    @staticmethod
+    def _norm_params(data, side: str):
+        """(cx, cy, 1/scale) such that norm_kpts = (kpts - (cx, cy)) * (1/scale); (0, 0, 1) when the caller already normalised."""
+        if 'norm_keypoints0' in data and 'norm_keypoints1' in data:
+            return 0.0, 0.0, 1.0
+        _, _, height, width = data['image' + side].shape
+        scale = torch.tensor(float(max(width, height)), dtype=torch.float32) * 0.7            # as normalize_keypoints
+        return float(width) / 2, float(height) / 2, float(torch.tensor(1.0, dtype=torch.float32) / scale)
 
     def submit(self, data: Dict[str, torch.Tensor]):
-        from .nets.layers import normalize_keypoints
         N0, N1 = data['descriptors0'].shape[1], data['descriptors1'].shape[1]
         if data['descriptors0'].shape[0] != 1:
             raise ValueError('LatencyMatcher handles one pair per call (use the batched model API for batches)')
@@ -120,17 +144,21 @@ class LatencyMatcher:
             if e is None:
                 e = slot['graphs'][Nb] = self._capture(slot, Nb)
             st = e['static']
-            if 'norm_keypoints0' in data and 'norm_keypoints1' in data:
-                nk0, nk1 = data['norm_keypoints0'], data['norm_keypoints1']
-            else:
-                nk0 = normalize_keypoints(data['keypoints0'], data['image0'].shape)
-                nk1 = normalize_keypoints(data['keypoints1'], data['image1'].shape)
-            for k, v, n in (('descriptors0', data['descriptors0'], N0), ('descriptors1', data['descriptors1'], N1),
-                            ('norm_keypoints0', nk0, N0), ('norm_keypoints1', nk1, N1),
-                            ('scores0', data['scores0'], N0), ('scores1', data['scores1'], N1)):
-                st[k][:, :n].copy_(v, non_blocking=True)
-            st['n_keypoints0'].fill_(N0)
-            st['n_keypoints1'].fill_(N1)
+            pre = 'norm_keypoints0' in data and 'norm_keypoints1' in data
+            k = e['n'] % self._RING
+            e['n'] += 1
+            if e['host_events'][k] is not None:
+                e['host_events'][k].synchronize()   # the copy that last used this pinned row has completed
+            e['host_np'][k, :] = self._norm_params(data, '0') + self._norm_params(data, '1') + (float(N0), float(N1))
+            e['params'].copy_(e['host_params'][k], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(s)
+            e['host_events'][k] = ev
+            for key, v, n in (('descriptors0', data['descriptors0'], N0), ('descriptors1', data['descriptors1'], N1),
+                              ('keypoints0', data['norm_keypoints0'] if pre else data['keypoints0'], N0),
+                              ('keypoints1', data['norm_keypoints1'] if pre else data['keypoints1'], N1),
+                              ('scores0', data['scores0'], N0), ('scores1', data['scores1'], N1)):
+                st[key][:, :n].copy_(v, non_blocking=True)
             e['graph'].replay()
             i0 = e['out']['indices0'][-1][:, :N0].clone()
             m0 = e['out']['mscores0'][-1][:, :N0].clone()

@@ -57,20 +57,26 @@ def match_sharded(match_fn: Callable[[Sequence[int]], Tuple[torch.Tensor, torch.
 
 
 def evaluate_sharded(model, get_pair: Callable[[int], dict], n_pairs: int, n_max: int, rank: int, world: int,
-                     slots: int = 4, p: float = 0.2):
+                     slots: int = 4, p: float = 0.2, matcher=None):
     """BASELINE.json configs[3]: the one-pair-per-call evaluation of eval/eval_imp.py:155-173
     (``produce_matches(only_last=True)`` per pair, ragged keypoint counts) sharded over ranks.  Every rank replays bucketed
     CUDA graphs with ``slots`` pairs in flight (graphed.LatencyMatcher); ``get_pair(i)`` returns pair i's data dict
     (device tensors, or pinned host tensors -- they are staged on the slot's stream).  Rank 0 gets
-    ([n_pairs, n_max] indices0, [n_pairs, n_max] mscores0), -1 / 0 padded."""
+    ([n_pairs, n_max] indices0, [n_pairs, n_max] mscores0), -1 / 0 padded.  Pass a ``matcher`` (LatencyMatcher) to keep the
+    captured graphs across calls; otherwise one is built (and its graphs captured, ~50 ms per bucket and slot) per call."""
     from .graphed import LatencyMatcher
     dev = next(model.parameters()).device
-    lm = LatencyMatcher(model, slots=slots, p=p, only_last=True)
+    lm = matcher if matcher is not None else LatencyMatcher(model, slots=slots, p=p, only_last=True)
+
+    timing = {}
 
     def match_fn(ids: Sequence[int]):
+        import time
         i0 = torch.full((len(ids), n_max), -1, dtype=torch.int64, device=dev)
         s0 = torch.zeros(len(ids), n_max, dtype=torch.float32, device=dev)
+        t0 = time.perf_counter()
         tickets = [lm.submit(get_pair(i)) for i in ids]
+        timing['submit_s'] = time.perf_counter() - t0        # host time to enqueue everything (no synchronisation inside)
         for k, t in enumerate(tickets):
             out = lm.result(t)
             n = out['indices0'][-1].shape[1]
@@ -79,4 +85,6 @@ def evaluate_sharded(model, get_pair: Callable[[int], dict], n_pairs: int, n_max
         return i0, s0
 
     with torch.no_grad():
-        return match_sharded(match_fn, n_pairs, n_max, rank, world)
+        out = match_sharded(match_fn, n_pairs, n_max, rank, world)
+    evaluate_sharded.last_timing = timing
+    return out

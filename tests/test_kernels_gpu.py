@@ -463,3 +463,75 @@ def test_attention_high_precision_mode():
         errs[mode] = err
     assert errs['high'] < 1e-4, errs
     assert errs['high'] < errs['fp16'] / 5, errs
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# round 2 kernels
+@pytest.mark.parametrize('M,N,K1,K2,mode', [(1000, 768, 256, 0, 'f16'), (2500, 512, 256, 256, 'f32'), (640, 256, 512, 0, 'resid'),
+                                             (129, 520, 128, 0, 'f32')])
+def test_gemm_cta_pair_kernel_is_bit_identical(M, N, K1, K2, mode):
+    """cta_group::2 CTA-pair GEMM (256 x 256 tiles, half of B per CTA) against the single-CTA kernel: same bits, incl.
+    ragged M / N edges, two K segments, every output mode, and against fp64."""
+    a, a2, w = _rand(M, K1, seed=31), _rand(M, max(K2, 64), seed=32), _rand(N, K1 + K2, seed=33, scale=0.05)
+    bias, res = _rand(N, seed=34), _rand(M, N, seed=35)
+    pa, pa2, pw, pres = ops.split_planes(a), ops.split_planes(a2), ops.split_planes(w), ops.split_planes(res)
+    outs = {}
+    try:
+        for variant in (3, 2):                                   # 3 = never pairs, 2 = pairs wherever N > 128
+            ops.set_option(ops.OPT_GEMM_VARIANT, variant)
+            if mode == 'f32':
+                o0, o1 = torch.zeros(M, N, device=DEV), None
+            else:
+                o0 = torch.zeros(M, N, device=DEV, dtype=torch.float16)
+                o1 = torch.zeros_like(o0) if mode == 'resid' else None
+            ops.gemm(pa, pw, M=M, N=N, K1=K1, K2=K2, a2=(pa2 if K2 else None), a_row_stride=K1, a2_row_stride=K2,
+                     b_row_stride=K1 + K2, bias=bias, out_mode={'f32': ops.OUT_F32, 'f16': ops.OUT_F16, 'resid': ops.OUT_SPLIT_RESID}[mode],
+                     out0=o0, out1=o1, out_row_stride=N, res=(pres if mode == 'resid' else None))
+            outs[variant] = (o0.float() + (o1.float() if o1 is not None else 0)).clone()
+    finally:
+        ops.set_option(ops.OPT_GEMM_VARIANT, 0)
+    assert torch.equal(outs[2], outs[3])
+    ref = (torch.cat([a, a2[:, :K2]], 1) if K2 else a).double() @ w.double().t() + bias.double()
+    if mode == 'resid':
+        ref = ref + res.double()
+    assert _rel(outs[2], ref) < (1e-3 if mode == 'f16' else 3e-6)
+
+
+@pytest.mark.parametrize('n_img,Np,ns', [(3, 200, [200, 131, 7]), (2, 1000, [1000, 977]), (5, 128, [128, 1, 64, 128, 100])])
+def test_fused_instance_norm(n_img, Np, ns):
+    """InstanceNorm1d(eps=1e-3) + ReLU of the MLP hidden layer (nets/layers.py:68-72), fused: statistics from the epilogue of
+    the producing GEMM (tiles straddling two images, ragged token counts), then (a) the streaming apply pass and (b) the
+    normalising A-operand path of the consuming GEMM, both against an fp64 instance norm."""
+    C_, K = 512, 256
+    T = n_img * Np
+    x, w0 = _rand(T, K, seed=41), _rand(C_, K, seed=42, scale=0.08)
+    b0 = _rand(C_, seed=43)
+    w1, b1 = _rand(256, C_, seed=44, scale=0.05), _rand(256, seed=45)
+    res = _rand(T, 256, seed=46)
+    px, pw0, pw1, pres = ops.split_planes(x), ops.split_planes(w0), ops.split_planes(w1), ops.split_planes(res)
+    nst = torch.tensor(ns, dtype=torch.int32, device=DEV)
+    H = torch.zeros(T, C_, device=DEV)
+    st = ops.InstNormStats(n_img, Np, C_, DEV)
+    ops.gemm(px, pw0, M=T, N=C_, K1=K, a_row_stride=K, b_row_stride=K, bias=b0, out_mode=ops.OUT_F32, out0=H, out_row_stride=C_,
+             stats=st, ns=nst, Np=Np)
+    Hn = ops.Planes.empty((T, C_), DEV)
+    ops.instnorm_apply(H, st, batch=n_img, Nmax=Np, C_=C_, ns=nst, out=Hn)
+    h3 = H.view(n_img, Np, C_).double()
+    got = Hn.float().view(n_img, Np, C_)
+    ref_n = torch.zeros(n_img, Np, C_, dtype=torch.float64, device=DEV)
+    for i, n in enumerate(ns):
+        v = h3[i, :n]
+        ref_n[i, :n] = torch.relu((v - v.mean(0)) / torch.sqrt(v.var(0, unbiased=False) + 1e-3))
+        assert float((got[i, :n].double() - ref_n[i, :n]).abs().max()) < 2e-5, i
+    # consumer GEMM with the normalisation in its A path == plain GEMM on the applied planes (bit for bit), and == fp64
+    o_plain, o_fused = ops.Planes.empty((T, 256), DEV), ops.Planes.empty((T, 256), DEV)
+    ops.gemm(Hn, pw1, M=T, N=256, K1=C_, a_row_stride=C_, b_row_stride=C_, bias=b1, out_mode=ops.OUT_SPLIT_RESID, out0=o_plain.hi,
+             out1=o_plain.lo, out_row_stride=256, res=pres)
+    ops.instnorm_apply(H, st, batch=n_img, Nmax=Np, C_=C_, ns=nst, out=None)
+    ops.gemm(Hn, pw1, M=T, N=256, K1=C_, a_row_stride=C_, b_row_stride=C_, bias=b1, out_mode=ops.OUT_SPLIT_RESID, out0=o_fused.hi,
+             out1=o_fused.lo, out_row_stride=256, res=pres, a_f32=H, a_stats=st, Np=Np)
+    a3, b3 = o_plain.float().view(n_img, Np, 256), o_fused.float().view(n_img, Np, 256)
+    for i, n in enumerate(ns):
+        assert torch.equal(a3[i, :n], b3[i, :n]), i
+        ref = ref_n[i, :n] @ w1.double().t() + b1.double() + res.view(n_img, Np, 256)[i, :n].double()
+        assert _rel(b3[i, :n], ref) < 1e-5
