@@ -350,6 +350,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }
 
 
+// ---------------------------------------------------------------------------------------------------------------
 template <int BN, int STG, int MINB, bool SPLIT>
 static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   CUtensorMap tq, tk, tv, tql, tkl, tvl;

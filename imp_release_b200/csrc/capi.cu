@@ -38,6 +38,7 @@ IMP_API int imp_set_option(int32_t key, int32_t value) {
     case IMP_OPT_SK_RESIDENT: imp::sinkhorn_set_resident(value); return 0;
     case IMP_OPT_ATTN_VARIANT: imp::attention_set_variant(value); return 0;
     case IMP_OPT_GEMM_VARIANT: imp::gemm_set_variant(value); return 0;
+    case IMP_OPT_SM_LIMIT: imp::set_sm_limit(value); return 0;
     default: imp::set_error("imp_set_option: unknown key %d", key); return 2;
   }
 }

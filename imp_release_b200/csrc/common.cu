@@ -74,7 +74,11 @@ int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
   return 0;
 }
 
+static int g_sm_limit = 0;
+void set_sm_limit(int n) { g_sm_limit = n > 0 ? n : 0; }
+
 int num_sms() {
+  if (g_sm_limit > 0) return g_sm_limit;
   static int n = 0;
   if (n == 0) {
     int dev = 0;

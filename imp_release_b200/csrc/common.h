@@ -37,7 +37,10 @@ int make_tmap_f16_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_
 int make_tmap_f32_3d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t rows, uint64_t batch, uint64_t row_stride,
                      uint64_t batch_stride, uint32_t box_rows);
 
+// SMs the next launches may use: the device's count, or the limit the host layer set before launching onto a stream of an
+// SM partition (green context) -- persistent kernels size their grids with it.
 int num_sms();
+void set_sm_limit(int n);
 
 // cudaFuncSetAttribute state (dynamic shared memory limit, carve-out) is PER DEVICE: a launcher configures its kernels the
 // first time it runs on each device of the process, not once per process.

@@ -240,7 +240,7 @@ def default_sk_storage() -> str:
     return os.environ.get('IMP_SK_STORAGE', 'fp32')
 
 
-OPT_SK_RESIDENT, OPT_ATTN_VARIANT, OPT_GEMM_VARIANT = 1, 2, 3
+OPT_SK_RESIDENT, OPT_ATTN_VARIANT, OPT_GEMM_VARIANT, OPT_SM_LIMIT = 1, 2, 3, 4
 
 
 def set_option(key: int, value: int):

@@ -34,8 +34,11 @@ IMP_API int imp_abi_version(void);
 /* Run-time knobs of the library (process-wide; no reference counterpart -- the reference has no kernels to tune).
  * IMP_OPT_SK_RESIDENT: 1 (default) = small Sinkhorn problems run the shared-memory-resident kernel, 0 = every problem
  * takes the streaming kernels the big batches use (what the parity tests switch on to cover that path with the
- * reference fixtures).  IMP_OPT_ATTN_VARIANT / IMP_OPT_GEMM_VARIANT: kernel variants (0 = default), for tuning runs. */
-enum { IMP_OPT_SK_RESIDENT = 1, IMP_OPT_ATTN_VARIANT = 2, IMP_OPT_GEMM_VARIANT = 3 };
+ * reference fixtures).  IMP_OPT_ATTN_VARIANT / IMP_OPT_GEMM_VARIANT: kernel variants (0 = default), for tuning runs.
+ * IMP_OPT_SM_LIMIT: number of SMs the following launches may assume (0 = the whole device).  The host layer sets it before it
+ * launches onto a stream that belongs to an SM partition (CUDA green context), so that persistent kernels size their grids for
+ * the partition instead of the device. */
+enum { IMP_OPT_SK_RESIDENT = 1, IMP_OPT_ATTN_VARIANT = 2, IMP_OPT_GEMM_VARIANT = 3, IMP_OPT_SM_LIMIT = 4 };
 IMP_API int imp_set_option(int32_t key, int32_t value);
 
 /* ---- fp32 <-> hi/lo planes (boundary conversions; `addend` may be NULL) -------------------------------------- */
