@@ -13,7 +13,7 @@ import torch  # noqa: F401  (loads libcudart.so.12, which libimp_b200.so links a
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libimp_b200.so')
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 
 class ImpLibraryError(RuntimeError):
@@ -70,6 +70,17 @@ class PoolArgs(C.Structure):
                 ('changed', c_vp), ('thresh', c_f32), ('n_min_tokens', c_i32), ('batch', c_i32), ('_pad', c_i32)]
 
 
+class SpConvArgs(C.Structure):
+    _fields_ = [('in_hi', c_vp), ('in_lo', c_vp), ('w_hi', c_vp), ('w_lo', c_vp), ('bias', c_vp), ('out_hi', c_vp), ('out_lo', c_vp),
+                ('B', c_i32), ('H', c_i32), ('W', c_i32), ('Cin', c_i32), ('Cout', c_i32), ('relu', c_i32)]
+
+
+class SpSelectArgs(C.Structure):
+    _fields_ = [('scores', c_vp), ('mask', c_vp), ('H', c_i32), ('W', c_i32), ('threshold', c_f32), ('border', c_i32),
+                ('max_keypoints', c_i32), ('cap', c_i32), ('rowcnt', c_vp), ('rowoff', c_vp), ('total', c_vp), ('cand_yx', c_vp),
+                ('cand_score', c_vp), ('keys', c_vp), ('kpts_xy', c_vp), ('kscores', c_vp), ('n_out', c_vp)]
+
+
 # name -> (restype, argtypes): every symbol include/imp_b200.h declares
 SIGNATURES = {
     'imp_last_error': (C.c_char_p, []),
@@ -95,6 +106,14 @@ SIGNATURES = {
     'imp_pool_select': (C.c_int, [C.POINTER(PoolArgs), c_vp]),
     'imp_scatter_matches': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'imp_gather_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sp_conv3x3': (C.c_int, [C.POINTER(SpConvArgs), c_vp]),
+    'imp_sp_conv1a': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sp_maxpool2': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sp_scores': (C.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sp_nms': (C.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sp_select': (C.c_int, [C.POINTER(SpSelectArgs), c_vp]),
+    'imp_sp_l2norm_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp]),
+    'imp_sp_sample_descriptors': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
 }
 
 _lib = None

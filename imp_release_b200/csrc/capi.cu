@@ -24,6 +24,16 @@ void sinkhorn_set_resident(int on);
 void attention_set_variant(int v);
 void gemm_set_variant(int v);
 float sinkhorn_iter_ms();
+int launch_sp_conv3x3(const imp_sp_conv_args& a, cudaStream_t st);
+int launch_sp_conv1a(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo, int B, int H, int W,
+                     cudaStream_t st);
+int launch_sp_maxpool2(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int B, int H, int W, int C, cudaStream_t st);
+int launch_sp_scores(const float* logits, int ld, float* scores, int B, int Hc, int Wc, cudaStream_t st);
+int launch_sp_nms(const float* scores, uint8_t* mask, uint8_t* supp, int B, int H, int W, int radius, cudaStream_t st);
+int launch_sp_select(const imp_sp_select_args& a, cudaStream_t st);
+int launch_sp_l2norm_rows(float* x, long long rows, int ld, cudaStream_t st);
+int launch_sp_sample_descriptors(const float* dmap, const float* kpts_xy, const int* n_kpts, float* out, int Hc, int Wc, int max_k,
+                                 cudaStream_t st);
 }  // namespace imp
 
 #define ST(s) reinterpret_cast<cudaStream_t>(s)
@@ -109,4 +119,28 @@ IMP_API int imp_gather_rows(const void* in, int64_t in_bs, int32_t row_bytes_in,
                                  max_rows, batch, ST(stream));
 }
 
+IMP_API int imp_sp_conv3x3(const imp_sp_conv_args* args, void* stream) { return imp::launch_sp_conv3x3(*args, ST(stream)); }
+IMP_API int imp_sp_conv1a(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo, int32_t B, int32_t H,
+                          int32_t W, void* stream) {
+  return imp::launch_sp_conv1a(img, w, bias, out_hi, out_lo, B, H, W, ST(stream));
+}
+IMP_API int imp_sp_maxpool2(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int32_t B, int32_t H, int32_t W,
+                            int32_t C, void* stream) {
+  return imp::launch_sp_maxpool2(in_hi, in_lo, out_hi, out_lo, B, H, W, C, ST(stream));
+}
+IMP_API int imp_sp_scores(const float* logits, int32_t ld, float* scores, int32_t B, int32_t Hc, int32_t Wc, void* stream) {
+  return imp::launch_sp_scores(logits, ld, scores, B, Hc, Wc, ST(stream));
+}
+IMP_API int imp_sp_nms(const float* scores, uint8_t* mask, uint8_t* supp, int32_t B, int32_t H, int32_t W, int32_t radius,
+                       void* stream) {
+  return imp::launch_sp_nms(scores, mask, supp, B, H, W, radius, ST(stream));
+}
+IMP_API int imp_sp_select(const imp_sp_select_args* args, void* stream) { return imp::launch_sp_select(*args, ST(stream)); }
+IMP_API int imp_sp_l2norm_rows(float* x, int64_t rows, int32_t ld, void* stream) {
+  return imp::launch_sp_l2norm_rows(x, rows, ld, ST(stream));
+}
+IMP_API int imp_sp_sample_descriptors(const float* dmap, const float* kpts_xy, const int32_t* n_kpts, float* out, int32_t Hc,
+                                      int32_t Wc, int32_t max_k, void* stream) {
+  return imp::launch_sp_sample_descriptors(dmap, kpts_xy, n_kpts, out, Hc, Wc, max_k, ST(stream));
+}
 }  // extern "C"

@@ -1,0 +1,179 @@
+"""SuperPoint front-end with the reference's Python API (nets/superpoint.py:97-235), executed by the sm_100a kernels of
+libimp_b200.so (csrc/superpoint.cu): image -> keypoints, scores, 256-d descriptors, i.e. the inputs of the matcher.
+
+Same class name, constructor config, ``state_dict`` keys / shapes (``conv1a.weight`` ... ``convDb.bias``, so the published
+``superpoint_v1.pth`` loads unchanged), ``forward`` / ``extract`` signatures and return layout as the reference.  There is no
+CPU / PyTorch fallback: parameters live in ``nn.Conv2d`` containers that are never called.
+
+Kernel schedule (one launch each unless noted): conv1a (SIMT, C_in = 1) -> 7 tcgen05 implicit-GEMM 3 x 3 convolutions with 3
+max-pools in between -> convPa / convDa (3 x 3, tcgen05) -> convPb / convDb (1 x 1 = the matcher's split-precision GEMM) ->
+65-way softmax + depth-to-space -> simple_nms (5 launches) -> ordered compaction + top-k (4 launches per image) -> descriptor
+L2 normalisation -> bilinear sampling + L2 normalisation.  Activations are NHWC fp16 hi/lo planes.
+"""
+from __future__ import annotations
+
+from typing import Dict, List
+
+import torch
+import torch.nn as nn
+
+from .. import ops
+from ..ops import Planes
+
+
+class SuperPoint(nn.Module):
+    default_config = {                 # nets/superpoint.py:106-112
+        'descriptor_dim': 256,
+        'nms_radius': 4,
+        'keypoint_threshold': 0.0025,
+        'max_keypoints': -1,
+        'remove_borders': 4,
+    }
+
+    def __init__(self, config):
+        super().__init__()
+        self.config = {**self.default_config, **config}
+        if self.config['descriptor_dim'] != 256:
+            raise NotImplementedError('the B200 kernels are specialised for 256-d descriptors')
+        c1, c2, c3, c4, c5 = 64, 64, 128, 128, 256
+        # parameter containers only (same names / shapes as nets/superpoint.py:122-143); never called
+        self.conv1a = nn.Conv2d(1, c1, kernel_size=3, stride=1, padding=1)
+        self.conv1b = nn.Conv2d(c1, c1, kernel_size=3, stride=1, padding=1)
+        self.conv2a = nn.Conv2d(c1, c2, kernel_size=3, stride=1, padding=1)
+        self.conv2b = nn.Conv2d(c2, c2, kernel_size=3, stride=1, padding=1)
+        self.conv3a = nn.Conv2d(c2, c3, kernel_size=3, stride=1, padding=1)
+        self.conv3b = nn.Conv2d(c3, c3, kernel_size=3, stride=1, padding=1)
+        self.conv4a = nn.Conv2d(c3, c4, kernel_size=3, stride=1, padding=1)
+        self.conv4b = nn.Conv2d(c4, c4, kernel_size=3, stride=1, padding=1)
+        self.convPa = nn.Conv2d(c4, c5, kernel_size=3, stride=1, padding=1)
+        self.convPb = nn.Conv2d(c5, 65, kernel_size=1, stride=1, padding=0)
+        self.convDa = nn.Conv2d(c4, c5, kernel_size=3, stride=1, padding=1)
+        self.convDb = nn.Conv2d(c5, self.config['descriptor_dim'], kernel_size=1, stride=1, padding=0)
+        # the reference requires config['weight_path'] (nets/superpoint.py:146-147); None / absent = keep the initialisation
+        # (B200-side allowance: pretrained weights are not always at hand, e.g. in the parity tests)
+        path = self.config.get('weight_path', None)
+        if path is not None:
+            self.load_state_dict(torch.load(str(path), map_location='cpu'))
+            print('Loaded SuperPoint model')
+        mk = self.config['max_keypoints']
+        if mk == 0 or mk < -1:
+            raise ValueError('"max_keypoints" must be positive or "-1"')
+        self._packed = None
+        self._packed_key = None
+        self._sel_ws: Dict[tuple, ops.SpSelectWorkspace] = {}
+
+    # ------------------------------------------------------------------ weight packing
+    def _apply(self, fn, *a, **kw):
+        self._packed = None
+        return super()._apply(fn, *a, **kw)
+
+    def load_state_dict(self, *a, **kw):
+        self._packed = None
+        return super().load_state_dict(*a, **kw)
+
+    def _weights(self):
+        w0 = self.conv1a.weight
+        key = (w0.device, w0.data_ptr(), w0._version)
+        if self._packed is None or self._packed_key != key:
+            if not w0.is_cuda:
+                raise ops._lib.ImpLibraryError('move the model to a CUDA device first (net.cuda()); the B200 path has no CPU '
+                                               'implementation')
+            P = {}
+            f = lambda t: t.detach().float().contiguous()
+            P['conv1a'] = (f(self.conv1a.weight).reshape(64, 9).contiguous(), f(self.conv1a.bias))
+            for n in ('conv1b', 'conv2a', 'conv2b', 'conv3a', 'conv3b', 'conv4a', 'conv4b', 'convPa', 'convDa'):
+                m = getattr(self, n)
+                w = f(m.weight).permute(0, 2, 3, 1).reshape(m.weight.shape[0], -1).contiguous()   # [Cout, (ky, kx, ci)]
+                P[n] = (ops.split_planes(w), f(m.bias))
+            wp = torch.zeros(128, 256, device=w0.device)
+            wp[:65] = f(self.convPb.weight)[:, :, 0, 0]
+            bp = torch.zeros(128, device=w0.device)
+            bp[:65] = f(self.convPb.bias)
+            P['convPb'] = (ops.split_planes(wp), bp)
+            P['convDb'] = (ops.split_planes(f(self.convDb.weight)[:, :, 0, 0].contiguous()), f(self.convDb.bias))
+            self._packed, self._packed_key = P, key
+        return self._packed
+
+    # ------------------------------------------------------------------ dense part
+    def _dense(self, image: torch.Tensor):
+        """image [B, 1, H, W] -> (scores [B, 8 Hc, 8 Wc] before NMS, normalised descriptor map [B, Hc, Wc, 256])."""
+        if image.dim() != 4 or image.shape[1] != 1:
+            raise ValueError('SuperPoint expects a [B, 1, H, W] grayscale image')
+        ops._require_cuda(image)
+        P = self._weights()
+        dev = image.device
+        B, _, H, W = image.shape
+        if H < 8 or W < 8:
+            raise ValueError('image smaller than one 8 x 8 cell')
+        img = image.reshape(B, H, W).float().contiguous()
+
+        def conv(x: Planes, name: str) -> Planes:
+            w, b = P[name]
+            out = Planes.empty((x.hi.shape[0], x.hi.shape[1], x.hi.shape[2], w.hi.shape[0]), dev)
+            return ops.sp_conv3x3(x, w, b, out, relu=True)
+
+        def pool(x: Planes) -> Planes:
+            b_, h_, w_, c_ = x.hi.shape
+            return ops.sp_maxpool2(x, Planes.empty((b_, h_ // 2, w_ // 2, c_), dev))
+
+        x = ops.sp_conv1a(img, P['conv1a'][0], P['conv1a'][1], Planes.empty((B, H, W, 64), dev))
+        x = pool(conv(x, 'conv1b'))
+        x = pool(conv(conv(x, 'conv2a'), 'conv2b'))
+        x = pool(conv(conv(x, 'conv3a'), 'conv3b'))
+        x = conv(conv(x, 'conv4a'), 'conv4b')
+        Hc, Wc = x.hi.shape[1], x.hi.shape[2]
+        M = B * Hc * Wc
+        # detector head
+        cPa = conv(x, 'convPa')
+        logits = torch.empty(M, 128, dtype=torch.float32, device=dev)
+        wp, bp = P['convPb']
+        ops.gemm(Planes(cPa.hi.view(M, 256), cPa.lo.view(M, 256)), wp, M=M, N=128, K1=256, a_row_stride=256, b_row_stride=256,
+                 bias=bp, out_mode=ops.OUT_F32, out0=logits, out_row_stride=128)
+        scores = torch.empty(B, Hc * 8, Wc * 8, dtype=torch.float32, device=dev)
+        ops.sp_scores(logits, scores, B, Hc, Wc)
+        # descriptor head
+        cDa = conv(x, 'convDa')
+        dmap = torch.empty(M, 256, dtype=torch.float32, device=dev)
+        wd, bd = P['convDb']
+        ops.gemm(Planes(cDa.hi.view(M, 256), cDa.lo.view(M, 256)), wd, M=M, N=256, K1=256, a_row_stride=256, b_row_stride=256,
+                 bias=bd, out_mode=ops.OUT_F32, out0=dmap, out_row_stride=256)
+        ops.sp_l2norm_rows(dmap)
+        return scores, dmap.view(B, Hc, Wc, 256)
+
+    def extract(self, data):
+        """Dense scores [B, H, W] (no NMS) and descriptors [B, 256, Hc, Wc] (nets/superpoint.py:154-183)."""
+        scores, dmap = self._dense(data['image'])
+        return scores, dmap.permute(0, 3, 1, 2)
+
+    def forward(self, data):
+        """{'image': [B, 1, H, W]} -> {'keypoints': [[K, 2] (x, y)], 'scores': [[K]], 'descriptors': [[256, K]]}
+        (nets/superpoint.py:185-235)."""
+        scores, dmap = self._dense(data['image'])
+        B, Hs, Ws = scores.shape
+        Hc, Wc = dmap.shape[1], dmap.shape[2]
+        dev = scores.device
+        mask = torch.empty(B, Hs, Ws, dtype=torch.uint8, device=dev)
+        supp = torch.empty(B, Hs, Ws, dtype=torch.uint8, device=dev)
+        ops.sp_nms(scores, mask, supp, self.config['nms_radius'])
+        mk = self.config['max_keypoints']
+        key = (Hs, Ws, mk, str(dev))
+        ws = self._sel_ws.get(key)
+        if ws is None:
+            if len(self._sel_ws) > 4:
+                self._sel_ws.clear()
+            ws = self._sel_ws[key] = ops.SpSelectWorkspace(Hs, Ws, mk, dev)
+        keypoints: List[torch.Tensor] = []
+        kscores: List[torch.Tensor] = []
+        descriptors: List[torch.Tensor] = []
+        for b in range(B):
+            ops.sp_select(scores[b], mask[b], ws, self.config['keypoint_threshold'], self.config['remove_borders'], mk)
+            n = int(ws.n_out.item())          # the reference synchronises here too (torch.nonzero)
+            kp = ws.kpts[:n].clone()
+            sc = ws.kscores[:n].clone()
+            desc = torch.empty(max(n, 1), 256, dtype=torch.float32, device=dev)
+            if n > 0:
+                ops.sp_sample_descriptors(dmap[b], kp, None, desc, Hc, Wc, n)
+            keypoints.append(kp)
+            kscores.append(sc)
+            descriptors.append(desc[:n].t())
+        return {'keypoints': keypoints, 'scores': kscores, 'descriptors': descriptors}

@@ -402,3 +402,92 @@ def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: to
         check(_lib.load().imp_gather_rows(ptr(src), src.stride(0) * src.element_size(), rb_in, ptr(ids), ids.stride(0),
                                           ptr(cnt), ptr(out), out.stride(0) * out.element_size(), rb_out, copy, max_rows,
                                           batch, stream_ptr()), 'imp_gather_rows')
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SuperPoint front-end (csrc/superpoint.cu; reference nets/superpoint.py)
+def sp_conv3x3(x: Planes, w: Planes, bias: torch.Tensor, out: Planes, relu: bool = True):
+    """x planes [B, H, W, Cin] -> out planes [B, H, W, Cout]; w planes [Cout, 9 * Cin] (tap-major)."""
+    B, H, W, Cin = x.hi.shape
+    Cout = w.hi.shape[0]
+    a = _lib.SpConvArgs()
+    a.in_hi, a.in_lo, a.w_hi, a.w_lo, a.bias = ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), ptr(bias)
+    a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
+    a.B, a.H, a.W, a.Cin, a.Cout, a.relu = B, H, W, Cin, Cout, int(relu)
+    with _Span(f'sp_conv3x3_{Cin}_{Cout}', 1, 2.0 * B * H * W * 9 * Cin * Cout):
+        check(_lib.load().imp_sp_conv3x3(C.byref(a), stream_ptr()), 'imp_sp_conv3x3')
+    return out
+
+
+def sp_conv1a(img: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, out: Planes):
+    B, H, W = img.shape
+    with _Span('sp_conv1a', 1):
+        check(_lib.load().imp_sp_conv1a(ptr(img), ptr(w), ptr(bias), ptr(out.hi), ptr(out.lo), B, H, W, stream_ptr()), 'imp_sp_conv1a')
+    return out
+
+
+def sp_maxpool2(x: Planes, out: Planes):
+    B, H, W, Cc = x.hi.shape
+    with _Span('sp_maxpool2', 1):
+        check(_lib.load().imp_sp_maxpool2(ptr(x.hi), ptr(x.lo), ptr(out.hi), ptr(out.lo), B, H, W, Cc, stream_ptr()), 'imp_sp_maxpool2')
+    return out
+
+
+def sp_scores(logits: torch.Tensor, scores: torch.Tensor, B: int, Hc: int, Wc: int):
+    with _Span('sp_scores', 1):
+        check(_lib.load().imp_sp_scores(ptr(logits), logits.shape[-1], ptr(scores), B, Hc, Wc, stream_ptr()), 'imp_sp_scores')
+    return scores
+
+
+def sp_nms(scores: torch.Tensor, mask: torch.Tensor, supp: torch.Tensor, radius: int):
+    B, H, W = scores.shape
+    with _Span('sp_nms', 5):
+        check(_lib.load().imp_sp_nms(ptr(scores), ptr(mask), ptr(supp), B, H, W, radius, stream_ptr()), 'imp_sp_nms')
+    return mask
+
+
+class SpSelectWorkspace:
+    """Scratch + outputs of the keypoint selection of one H x W image."""
+
+    def __init__(self, H: int, W: int, max_keypoints: int, device):
+        self.H, self.W = H, W
+        self.cap = H * W
+        np2 = 1
+        while np2 < self.cap:
+            np2 <<= 1
+        i32 = dict(dtype=torch.int32, device=device)
+        self.rowcnt, self.rowoff = torch.zeros(H, **i32), torch.zeros(H, **i32)
+        self.total, self.n_out = torch.zeros(1, **i32), torch.zeros(1, **i32)
+        self.cand_yx = torch.zeros(self.cap, 2, **i32)
+        self.cand_score = torch.zeros(self.cap, dtype=torch.float32, device=device)
+        self.keys = torch.zeros(np2, dtype=torch.int64, device=device)
+        self.max_out = self.cap if max_keypoints < 0 else min(self.cap, max_keypoints)
+        self.kpts = torch.zeros(max(self.max_out, 1), 2, dtype=torch.float32, device=device)
+        self.kscores = torch.zeros(max(self.max_out, 1), dtype=torch.float32, device=device)
+
+
+def sp_select(scores: torch.Tensor, mask: torch.Tensor, ws: SpSelectWorkspace, threshold: float, border: int, max_keypoints: int):
+    """scores / mask: [H, W] of one image.  Results in ws.kpts[:n], ws.kscores[:n] with n = ws.n_out (device)."""
+    a = _lib.SpSelectArgs()
+    a.scores, a.mask, a.H, a.W = ptr(scores), ptr(mask), ws.H, ws.W
+    a.threshold, a.border, a.max_keypoints, a.cap = float(threshold), int(border), int(max_keypoints), ws.cap
+    a.rowcnt, a.rowoff, a.total = ptr(ws.rowcnt), ptr(ws.rowoff), ptr(ws.total)
+    a.cand_yx, a.cand_score, a.keys = ptr(ws.cand_yx), ptr(ws.cand_score), ptr(ws.keys)
+    a.kpts_xy, a.kscores, a.n_out = ptr(ws.kpts), ptr(ws.kscores), ptr(ws.n_out)
+    with _Span('sp_select', 4):
+        check(_lib.load().imp_sp_select(C.byref(a), stream_ptr()), 'imp_sp_select')
+
+
+def sp_l2norm_rows(x: torch.Tensor):
+    rows = x.numel() // x.shape[-1]
+    with _Span('sp_l2norm_rows', 1):
+        check(_lib.load().imp_sp_l2norm_rows(ptr(x), rows, x.shape[-1], stream_ptr()), 'imp_sp_l2norm_rows')
+    return x
+
+
+def sp_sample_descriptors(dmap: torch.Tensor, kpts: torch.Tensor, n_kpts: Optional[torch.Tensor], out: torch.Tensor, Hc: int, Wc: int,
+                          max_k: int):
+    with _Span('sp_sample_descriptors', 1):
+        check(_lib.load().imp_sp_sample_descriptors(ptr(dmap), ptr(kpts), ptr(n_kpts), ptr(out), Hc, Wc, max_k, stream_ptr()),
+              'imp_sp_sample_descriptors')
+    return out

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define IMP_B200_ABI_VERSION 3
+#define IMP_B200_ABI_VERSION 4
 #if defined(__GNUC__)
 #define IMP_API __attribute__((visibility("default")))
 #else
@@ -256,6 +256,68 @@ IMP_API int imp_scatter_matches(const int64_t* idx0, const float* ms0, int32_t l
 IMP_API int imp_gather_rows(const void* in, int64_t in_batch_stride_bytes, int32_t row_bytes_in, const int32_t* ids,
                     int32_t ids_ld, const int32_t* cnt, void* out, int64_t out_batch_stride_bytes,
                     int32_t row_bytes_out, int32_t copy_bytes, int32_t max_rows, int32_t batch, void* stream);
+
+/* ==== SuperPoint front-end (reference nets/superpoint.py:97-235) ===================================
+ * The step before the matcher: image -> keypoints, scores, 256-d descriptors.  Activations are NHWC fp16 hi/lo planes
+ * [B, H, W, C] (x = hi + lo, the matcher's split-precision format), weights are [C_out, 9 * C_in] hi/lo planes with
+ * k = (3 * ky + kx) * C_in + ci, i.e. conv.weight.permute(0, 2, 3, 1). */
+
+/* 3 x 3 convolution, stride 1, zero padding 1, + bias (+ ReLU): conv1b ... convPa / convDa (nets/superpoint.py:126-141,
+ * 186-197).  tcgen05 implicit GEMM; C_in % 64 == 0, C_out in {64, 128, 256}. */
+typedef struct imp_sp_conv_args {
+  const void* in_hi;  /* fp16 [B, H, W, Cin] */
+  const void* in_lo;
+  const void* w_hi;   /* fp16 [Cout, 9 * Cin] */
+  const void* w_lo;
+  const float* bias;  /* [Cout] */
+  void* out_hi;       /* fp16 [B, H, W, Cout] */
+  void* out_lo;
+  int32_t B, H, W, Cin, Cout, relu;
+} imp_sp_conv_args;
+IMP_API int imp_sp_conv3x3(const imp_sp_conv_args* args, void* stream);
+
+/* conv1a (1 -> 64 channels, nets/superpoint.py:125) + ReLU: img fp32 [B, H, W], w fp32 [64, 9], out planes [B, H, W, 64] */
+IMP_API int imp_sp_conv1a(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo, int32_t B, int32_t H,
+                          int32_t W, void* stream);
+/* nn.MaxPool2d(2, 2) on planes (nets/superpoint.py:122): [B, H, W, C] -> [B, H/2, W/2, C] */
+IMP_API int imp_sp_maxpool2(const void* in_hi, const void* in_lo, void* out_hi, void* out_lo, int32_t B, int32_t H, int32_t W,
+                            int32_t C, void* stream);
+/* softmax over the 65 logits of a cell, dust bin dropped, depth-to-space (nets/superpoint.py:199-203):
+ * logits fp32 [B * Hc * Wc, ld] (first 65 columns) -> scores fp32 [B, 8 Hc, 8 Wc] */
+IMP_API int imp_sp_scores(const float* logits, int32_t ld, float* scores, int32_t B, int32_t Hc, int32_t Wc, void* stream);
+/* simple_nms (nets/superpoint.py:50-66): mask[b, y, x] = 1 where the score survives; supp is a scratch of the same size */
+IMP_API int imp_sp_nms(const float* scores, uint8_t* mask, uint8_t* supp, int32_t B, int32_t H, int32_t W, int32_t radius,
+                       void* stream);
+
+/* keypoints of ONE image (nets/superpoint.py:206-225): nonzero(nms > threshold) in row-major order, remove_borders, top-k by
+ * score (all candidates in row-major order when there are at most max_keypoints, or max_keypoints < 0); (h, w) -> (x, y). */
+typedef struct imp_sp_select_args {
+  const float* scores;   /* [H, W] */
+  const uint8_t* mask;   /* [H, W] from imp_sp_nms */
+  int32_t H, W;
+  float threshold;
+  int32_t border;
+  int32_t max_keypoints;
+  int32_t cap;           /* capacity of the candidate arrays */
+  int32_t* rowcnt;       /* scratch [H] */
+  int32_t* rowoff;       /* scratch [H] */
+  int32_t* total;        /* out: number of candidates */
+  int32_t* cand_yx;      /* scratch [cap, 2] */
+  float* cand_score;     /* scratch [cap] */
+  uint64_t* keys;        /* scratch [next power of two >= cap] */
+  float* kpts_xy;        /* out [min(cap, max_keypoints), 2] */
+  float* kscores;        /* out */
+  int32_t* n_out;        /* out: number of keypoints */
+} imp_sp_select_args;
+IMP_API int imp_sp_select(const imp_sp_select_args* args, void* stream);
+
+/* x[r, :256] /= max(||x[r, :256]||, 1e-12) (F.normalize over the channels of the dense descriptor map, :229) */
+IMP_API int imp_sp_l2norm_rows(float* x, int64_t rows, int32_t ld, void* stream);
+/* sample_descriptors (nets/superpoint.py:83-95): bilinear interpolation of the normalised [Hc * Wc, 256] map at the keypoints
+ * (grid_sample with its default align_corners=False -- the reference's version test `int(torch.__version__[2]) > 2` is false
+ * for 1.12 and for 2.x alike -- zero padding), then a second L2 normalisation.  out fp32 [n, 256], n = min(*n_kpts, max_k). */
+IMP_API int imp_sp_sample_descriptors(const float* dmap, const float* kpts_xy, const int32_t* n_kpts, float* out, int32_t Hc,
+                                      int32_t Wc, int32_t max_k, void* stream);
 
 #ifdef __cplusplus
 }

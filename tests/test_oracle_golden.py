@@ -173,3 +173,30 @@ def test_restated_drivers_equal_unmodified_drivers_on_reference_model():
         import sys
         for k in [k for k in sys.modules if k == 'nets' or k.startswith('nets.') or k == 'eval' or k.startswith('eval.') or k == 'tools' or k.startswith('tools.')]:
             del sys.modules[k]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SuperPoint front-end: oracle/superpoint_oracle.py against the unmodified reference class
+from oracle import superpoint_oracle as spo  # noqa: E402
+from tests.golden.make_golden_superpoint import CASES as SP_CASES, DEFAULT as SP_DEFAULT, probe_dirs  # noqa: E402
+
+SPG = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'reference_superpoint.npz'))
+
+
+@pytest.mark.parametrize('name', list(SP_CASES))
+def test_superpoint_oracle_matches_reference(name):
+    wseed, iseed, H, W, B, over = SP_CASES[name]
+    sd = spo.make_state_dict(wseed)
+    img = spo.make_image(iseed, H, W, B)
+    assert sum(float(v.double().abs().sum()) for v in sd.values()) == pytest.approx(float(SPG[f'{name}/weights_checksum']), rel=1e-12)
+    assert float(img.double().sum()) == pytest.approx(float(SPG[f'{name}/image_checksum']), rel=1e-12), 'RNG drift'
+    with torch.no_grad():
+        scores, _ = spo.dense(sd, img)
+        out = spo.forward(sd, img, {**SP_DEFAULT, **over})
+    assert np.abs(scores[:, ::8, ::8].numpy() - SPG[f'{name}/dense_scores_8x']).max() < 1e-7
+    for b in range(B):
+        assert np.array_equal(out['keypoints'][b].numpy().astype(np.int32), SPG[f'{name}/{b}/keypoints'])
+        assert np.abs(out['scores'][b].numpy() - SPG[f'{name}/{b}/scores']).max() < 1e-7
+        d = out['descriptors'][b]
+        assert np.abs(d[:, :48].numpy() - SPG[f'{name}/{b}/descriptors_head']).max() < 1e-6
+        assert np.abs((d.t() @ probe_dirs()).numpy() - SPG[f'{name}/{b}/descriptor_probes']).max() < 1e-5
