@@ -72,7 +72,7 @@ class PoolArgs(C.Structure):
 
 class SpConvArgs(C.Structure):
     _fields_ = [('in_hi', c_vp), ('in_lo', c_vp), ('w_hi', c_vp), ('w_lo', c_vp), ('bias', c_vp), ('out_hi', c_vp), ('out_lo', c_vp),
-                ('B', c_i32), ('H', c_i32), ('W', c_i32), ('Cin', c_i32), ('Cout', c_i32), ('relu', c_i32)]
+                ('B', c_i32), ('H', c_i32), ('W', c_i32), ('Cin', c_i32), ('Cout', c_i32), ('relu', c_i32), ('pool', c_i32), ('_pad', c_i32)]
 
 
 class SpSelectArgs(C.Structure):

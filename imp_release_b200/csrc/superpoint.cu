@@ -29,7 +29,7 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, ui
 }
 
 struct ConvParams {
-  int B, H, W, Cin, Cout, relu;
+  int B, H, W, Cin, Cout, relu, pool;
   const float* bias;
   __half *out_hi, *out_lo;
 };
@@ -120,8 +120,11 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
     const int row = quarter * 32 + lane_id();
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int py = y0 + row / CV_BW, px = x0 + row % CV_BW;
-    const bool ok = py < p.H && px < p.W;
-    const long long pix = ((long long)b * p.H + py) * p.W + px;
+    // pool: nn.MaxPool2d(2, 2) fused (nets/superpoint.py:189,192,195).  A warp holds two image rows of 16 pixels, so the 2 x 2
+    // partners of a pixel are lanes ^ 1 and ^ 16; the lane of the even / even pixel writes the pooled one (a trailing odd row
+    // or column is dropped, as MaxPool2d does).  Same planes as pooling after the split: rounding is monotone.
+    const bool ok = p.pool ? ((row & 1) == 0 && (row & 16) == 0 && py + 1 < p.H && px + 1 < p.W) : (py < p.H && px < p.W);
+    const long long pix = p.pool ? ((long long)b * (p.H / 2) + py / 2) * (p.W / 2) + px / 2 : ((long long)b * p.H + py) * p.W + px;
     mbar_wait(acc_full, 0);
     tc_fence_after();
 #pragma unroll 1
@@ -130,8 +133,19 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
       tmem_ld_x32(tmem_base + lane_off + cb, r);
       tmem_ld_x32(tmem_base + lane_off + BN + cb, r2);
       tmem_wait_ld();
+      float v[32];
 #pragma unroll
-      for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) + __uint_as_float(r2[c]));
+      for (int c = 0; c < 32; ++c) {
+        v[c] = (__uint_as_float(r[c]) + __uint_as_float(r2[c])) + __ldg(p.bias + cb + c);
+        if (p.relu) v[c] = fmaxf(v[c], 0.f);
+      }
+      if (p.pool) {
+#pragma unroll
+        for (int c = 0; c < 32; ++c) {
+          v[c] = fmaxf(v[c], __shfl_xor_sync(0xffffffffu, v[c], 1));
+          v[c] = fmaxf(v[c], __shfl_xor_sync(0xffffffffu, v[c], 16));
+        }
+      }
       if (ok) {
         __half* oh = p.out_hi + pix * p.Cout + cb;
         __half* ol = p.out_lo + pix * p.Cout + cb;
@@ -140,15 +154,9 @@ conv3x3_kernel(const __grid_constant__ CUtensorMap tm_ah, const __grid_constant_
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
-            float v0 = __uint_as_float(r[c + 2 * u]) + __ldg(p.bias + cb + c + 2 * u);
-            float v1 = __uint_as_float(r[c + 2 * u + 1]) + __ldg(p.bias + cb + c + 2 * u + 1);
-            if (p.relu) {
-              v0 = fmaxf(v0, 0.f);
-              v1 = fmaxf(v1, 0.f);
-            }
             __half h0, l0, h1, l1;
-            split_f16x2(v0, h0, l0);
-            split_f16x2(v1, h1, l1);
+            split_f16x2(v[c + 2 * u], h0, l0);
+            split_f16x2(v[c + 2 * u + 1], h1, l1);
             __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
             hi[u] = *reinterpret_cast<uint32_t*>(&hh);
             lo[u] = *reinterpret_cast<uint32_t*>(&ll);
@@ -205,6 +213,7 @@ static int launch_conv3x3_impl(const imp_sp_conv_args& a, cudaStream_t st) {
   p.Cin = a.Cin;
   p.Cout = a.Cout;
   p.relu = a.relu;
+  p.pool = a.pool;
   p.bias = a.bias;
   p.out_hi = reinterpret_cast<__half*>(a.out_hi);
   p.out_lo = reinterpret_cast<__half*>(a.out_lo);
@@ -233,52 +242,56 @@ int launch_sp_conv3x3(const imp_sp_conv_args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 // conv1a (nets/superpoint.py:125, 1 -> 64 channels): K = 9, far too thin for the tensor cores.  A thread owns one pixel and
 // 8 output channels; fp32 FMA in the reference's accumulation order does not matter at 9 terms.
-__global__ void conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/, const float* __restrict__ bias,
-                              __half* __restrict__ out_hi, __half* __restrict__ out_lo, int B, int H, int W) {
-  __shared__ float sw[64 * 9], sb[64];
-  for (int i = threadIdx.x; i < 64 * 9; i += blockDim.x) sw[i] = w[i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
-  __syncthreads();
-  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const long long pix = t >> 3;
-  const int g = t & 7;
-  if (pix >= (long long)B * H * W) return;
-  const int x = pix % W, y = (pix / W) % H;
-  const float* im = img + (pix - (long long)y * W - x);
-  float v[9];
+__global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
+                                                     const float* __restrict__ bias, __half* __restrict__ out_hi,
+                                                     __half* __restrict__ out_lo, int B, int H, int W) {
+  const int g = threadIdx.x & 7;  // 8 output channels g*8 .. g*8+7, their 72 weights live in registers
+  float wr[8][9], br[8];
 #pragma unroll
-  for (int tp = 0; tp < 9; ++tp) {
-    const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
-    v[tp] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? im[(long long)yy * W + xx] : 0.f;
+  for (int e = 0; e < 8; ++e) {
+    br[e] = bias[g * 8 + e];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) wr[e][tp] = w[(g * 8 + e) * 9 + tp];
   }
-  uint32_t hi[4], lo[4];
+  const long long npix = (long long)B * H * W;
+  for (long long pix = (long long)blockIdx.x * 32 + (threadIdx.x >> 3); pix < npix; pix += (long long)gridDim.x * 32) {
+    const int x = pix % W, y = (pix / W) % H;
+    const float* im = img + (pix - (long long)y * W - x);
+    float v[9];
 #pragma unroll
-  for (int u = 0; u < 4; ++u) {
-    float o[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int co = g * 8 + 2 * u + e;
-      float acc = 0.f;
-#pragma unroll
-      for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[tp], sw[co * 9 + tp], acc);
-      o[e] = fmaxf(acc + sb[co], 0.f);
+    for (int tp = 0; tp < 9; ++tp) {
+      const int yy = y + tp / 3 - 1, xx = x + tp % 3 - 1;
+      v[tp] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(im + (long long)yy * W + xx) : 0.f;
     }
-    __half h0, l0, h1, l1;
-    split_f16x2(o[0], h0, l0);
-    split_f16x2(o[1], h1, l1);
-    __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
-    hi[u] = *reinterpret_cast<uint32_t*>(&hh);
-    lo[u] = *reinterpret_cast<uint32_t*>(&ll);
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float o[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        float acc = 0.f;
+#pragma unroll
+        for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[tp], wr[2 * u + e][tp], acc);
+        o[e] = fmaxf(acc + br[2 * u + e], 0.f);
+      }
+      __half h0, l0, h1, l1;
+      split_f16x2(o[0], h0, l0);
+      split_f16x2(o[1], h1, l1);
+      __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+      hi[u] = *reinterpret_cast<uint32_t*>(&hh);
+      lo[u] = *reinterpret_cast<uint32_t*>(&ll);
+    }
+    *reinterpret_cast<uint4*>(out_hi + pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out_lo + pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-  *reinterpret_cast<uint4*>(out_hi + pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(out_lo + pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 int launch_sp_conv1a(const float* img, const float* w, const float* bias, void* out_hi, void* out_lo, int B, int H, int W,
                      cudaStream_t st) {
-  const long long n = (long long)B * H * W * 8;
-  conv1a_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(img, w, bias, reinterpret_cast<__half*>(out_hi),
-                                                            reinterpret_cast<__half*>(out_lo), B, H, W);
+  const long long npix = (long long)B * H * W;
+  const long long want = (npix + 32 * 16 - 1) / (32 * 16);  // ~16 pixels per thread
+  const int grid = (int)(want < 1 ? 1 : (want > 65535 * 16 ? 65535 * 16 : want));
+  conv1a_kernel<<<grid, 256, 0, st>>>(img, w, bias, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), B, H, W);
   IMP_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -485,44 +498,89 @@ __global__ void sel_write_kernel(const float* __restrict__ s, const uint8_t* __r
 }
 // top-k (torch.topk: sorted by descending score; equal scores: lower row-major index first) or, when there are at most k
 // candidates, all of them in row-major order (top_k_keypoints returns its input unchanged, nets/superpoint.py:79-80).
-// One CTA; bitonic sort of 64-bit keys (monotone score bits | inverted index) in a global scratch buffer.
+// One CTA.  Keys are 64 bit (monotone score bits | inverted index), hence distinct.  k <= 4096 (the usual 1000-4000 keypoints):
+// 8-pass radix select of the k-th largest key over the candidates (tens of thousands on a 1600-pixel image), gather of the
+// k keys >= it into shared memory, bitonic sort there.  Larger k: bitonic sort of all keys in a global scratch buffer.
+static constexpr int SEL_SMEM_K = 4096;
+__device__ __forceinline__ unsigned long long sel_key(const float* cand_score, int i) {
+  return ((unsigned long long)__float_as_uint(cand_score[i]) << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);  // scores > 0
+}
+template <typename KeyArray>
+__device__ __forceinline__ void bitonic_desc(KeyArray keys, int np2) {
+  for (int size = 2; size <= np2; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));  // index of the lower element of pair i
+        const int hi = lo + stride;
+        const bool desc = (lo & size) == 0;  // descending blocks first -> the whole array ends up descending
+        const unsigned long long a = keys[lo], b2 = keys[hi];
+        if ((a < b2) == desc) {
+          keys[lo] = b2;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+}
 __global__ void __launch_bounds__(1024) sel_topk_kernel(const int* __restrict__ cand_yx, const float* __restrict__ cand_score,
                                                          const int* __restrict__ total, unsigned long long* __restrict__ keys, int cap,
                                                          int k, float* __restrict__ kpts_xy, float* __restrict__ kscores,
                                                          int* __restrict__ n_out) {
+  __shared__ unsigned long long sel[SEL_SMEM_K];
+  __shared__ int hist[256];
+  __shared__ unsigned long long s_prefix;
+  __shared__ int s_remaining, s_slot;
   const int n = min(*total, cap);
   const bool all = k < 0 || n <= k;
   const int m = all ? n : k;
-  if (!all) {
-    int np2 = 1;
-    while (np2 < n) np2 <<= 1;
-    for (int i = threadIdx.x; i < np2; i += blockDim.x) {
-      unsigned long long key = 0ull;
-      if (i < n) {
-        const unsigned u = __float_as_uint(cand_score[i]);  // scores are positive: the bit pattern is monotone
-        key = ((unsigned long long)u << 32) | (unsigned)(0xFFFFFFFFu - (unsigned)i);
+  const unsigned long long* sorted = keys;
+  if (!all && k <= SEL_SMEM_K) {
+    if (threadIdx.x == 0) {
+      s_prefix = 0ull;
+      s_remaining = k;
+      s_slot = 0;
+    }
+    unsigned long long mask = 0ull;
+    for (int shift = 56; shift >= 0; shift -= 8) {
+      for (int i = threadIdx.x; i < 256; i += blockDim.x) hist[i] = 0;
+      __syncthreads();
+      const unsigned long long prefix = s_prefix;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const unsigned long long key = sel_key(cand_score, i);
+        if ((key & mask) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1);
       }
-      keys[i] = key;
+      __syncthreads();
+      if (threadIdx.x == 0) {  // the digit of the k-th largest key among those that share the prefix
+        int rem = s_remaining, b = 255;
+        while (b > 0 && hist[b] < rem) rem -= hist[b--];
+        s_remaining = rem;
+        s_prefix = prefix | ((unsigned long long)b << shift);
+      }
+      mask |= 255ull << shift;
+      __syncthreads();
+    }
+    const unsigned long long kth = s_prefix;  // exactly k keys are >= kth
+    int np2 = 1;
+    while (np2 < k) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) sel[i] = 0ull;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const unsigned long long key = sel_key(cand_score, i);
+      if (key >= kth) sel[atomicAdd(&s_slot, 1)] = key;
     }
     __syncthreads();
-    for (int size = 2; size <= np2; size <<= 1) {
-      for (int stride = size >> 1; stride > 0; stride >>= 1) {
-        for (int i = threadIdx.x; i < np2 / 2; i += blockDim.x) {
-          const int lo = 2 * i - (i & (stride - 1));  // index of the lower element of pair i
-          const int hi = lo + stride;
-          const bool desc = (lo & size) == 0;  // descending blocks first -> the whole array ends up descending
-          const unsigned long long a = keys[lo], b2 = keys[hi];
-          if ((a < b2) == desc) {
-            keys[lo] = b2;
-            keys[hi] = a;
-          }
-        }
-        __syncthreads();
-      }
-    }
+    bitonic_desc(sel, np2);
+    sorted = sel;
+  } else if (!all) {
+    int np2 = 1;
+    while (np2 < n) np2 <<= 1;
+    for (int i = threadIdx.x; i < np2; i += blockDim.x) keys[i] = i < n ? sel_key(cand_score, i) : 0ull;
+    __syncthreads();
+    bitonic_desc(keys, np2);
   }
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
-    const int src = all ? i : (int)(0xFFFFFFFFu - (unsigned)(keys[i] & 0xFFFFFFFFull));
+    const int src = all ? i : (int)(0xFFFFFFFFu - (unsigned)(sorted[i] & 0xFFFFFFFFull));
     kpts_xy[2 * i] = (float)cand_yx[2 * src + 1];  // (h, w) -> (x, y), nets/superpoint.py:225
     kpts_xy[2 * i + 1] = (float)cand_yx[2 * src];
     kscores[i] = cand_score[src];

@@ -5,8 +5,8 @@ Same class name, constructor config, ``state_dict`` keys / shapes (``conv1a.weig
 ``superpoint_v1.pth`` loads unchanged), ``forward`` / ``extract`` signatures and return layout as the reference.  There is no
 CPU / PyTorch fallback: parameters live in ``nn.Conv2d`` containers that are never called.
 
-Kernel schedule (one launch each unless noted): conv1a (SIMT, C_in = 1) -> 7 tcgen05 implicit-GEMM 3 x 3 convolutions with 3
-max-pools in between -> convPa / convDa (3 x 3, tcgen05) -> convPb / convDb (1 x 1 = the matcher's split-precision GEMM) ->
+Kernel schedule (one launch each unless noted): conv1a (SIMT, C_in = 1) -> 7 tcgen05 implicit-GEMM 3 x 3 convolutions, the 3
+max-pools fused into their epilogues -> convPa / convDa (3 x 3, tcgen05) -> convPb / convDb (1 x 1 = the matcher's split-precision GEMM) ->
 65-way softmax + depth-to-space -> simple_nms (5 launches) -> ordered compaction + top-k (4 launches per image) -> descriptor
 L2 normalisation -> bilinear sampling + L2 normalisation.  Activations are NHWC fp16 hi/lo planes.
 """
@@ -107,19 +107,20 @@ class SuperPoint(nn.Module):
             raise ValueError('image smaller than one 8 x 8 cell')
         img = image.reshape(B, H, W).float().contiguous()
 
-        def conv(x: Planes, name: str) -> Planes:
+        def conv(x: Planes, name: str, pool: bool = False) -> Planes:
             w, b = P[name]
-            out = Planes.empty((x.hi.shape[0], x.hi.shape[1], x.hi.shape[2], w.hi.shape[0]), dev)
-            return ops.sp_conv3x3(x, w, b, out, relu=True)
+            b_, h_, w_, _ = x.hi.shape
+            if pool:                       # nn.MaxPool2d(2, 2) fused into the convolution's epilogue
+                h_, w_ = h_ // 2, w_ // 2
+            out = Planes(torch.empty((b_, h_, w_, w.hi.shape[0]), dtype=torch.float16, device=dev),
+                         torch.empty((b_, h_, w_, w.hi.shape[0]), dtype=torch.float16, device=dev))
+            return ops.sp_conv3x3(x, w, b, out, relu=True, pool=pool)
 
-        def pool(x: Planes) -> Planes:
-            b_, h_, w_, c_ = x.hi.shape
-            return ops.sp_maxpool2(x, Planes.empty((b_, h_ // 2, w_ // 2, c_), dev))
-
-        x = ops.sp_conv1a(img, P['conv1a'][0], P['conv1a'][1], Planes.empty((B, H, W, 64), dev))
-        x = pool(conv(x, 'conv1b'))
-        x = pool(conv(conv(x, 'conv2a'), 'conv2b'))
-        x = pool(conv(conv(x, 'conv3a'), 'conv3b'))
+        x = Planes(torch.empty((B, H, W, 64), dtype=torch.float16, device=dev), torch.empty((B, H, W, 64), dtype=torch.float16, device=dev))
+        x = ops.sp_conv1a(img, P['conv1a'][0], P['conv1a'][1], x)
+        x = conv(x, 'conv1b', pool=True)
+        x = conv(conv(x, 'conv2a'), 'conv2b', pool=True)
+        x = conv(conv(x, 'conv3a'), 'conv3b', pool=True)
         x = conv(conv(x, 'conv4a'), 'conv4b')
         Hc, Wc = x.hi.shape[1], x.hi.shape[2]
         M = B * Hc * Wc

@@ -406,14 +406,15 @@ def gather_rows(src: torch.Tensor, ids: torch.Tensor, cnt: torch.Tensor, out: to
 
 # ---------------------------------------------------------------------------------------------------------------
 # SuperPoint front-end (csrc/superpoint.cu; reference nets/superpoint.py)
-def sp_conv3x3(x: Planes, w: Planes, bias: torch.Tensor, out: Planes, relu: bool = True):
-    """x planes [B, H, W, Cin] -> out planes [B, H, W, Cout]; w planes [Cout, 9 * Cin] (tap-major)."""
+def sp_conv3x3(x: Planes, w: Planes, bias: torch.Tensor, out: Planes, relu: bool = True, pool: bool = False):
+    """x planes [B, H, W, Cin] -> out planes [B, H, W, Cout] ([B, H/2, W/2, Cout] with the fused 2 x 2 max pooling);
+    w planes [Cout, 9 * Cin] (tap-major)."""
     B, H, W, Cin = x.hi.shape
     Cout = w.hi.shape[0]
     a = _lib.SpConvArgs()
     a.in_hi, a.in_lo, a.w_hi, a.w_lo, a.bias = ptr(x.hi), ptr(x.lo), ptr(w.hi), ptr(w.lo), ptr(bias)
     a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
-    a.B, a.H, a.W, a.Cin, a.Cout, a.relu = B, H, W, Cin, Cout, int(relu)
+    a.B, a.H, a.W, a.Cin, a.Cout, a.relu, a.pool = B, H, W, Cin, Cout, int(relu), int(pool)
     with _Span(f'sp_conv3x3_{Cin}_{Cout}', 1, 2.0 * B * H * W * 9 * Cin * Cout):
         check(_lib.load().imp_sp_conv3x3(C.byref(a), stream_ptr()), 'imp_sp_conv3x3')
     return out

@@ -273,6 +273,8 @@ typedef struct imp_sp_conv_args {
   void* out_hi;       /* fp16 [B, H, W, Cout] */
   void* out_lo;
   int32_t B, H, W, Cin, Cout, relu;
+  int32_t pool;       /* 1: nn.MaxPool2d(2, 2) fused into the epilogue, out is [B, H/2, W/2, Cout] */
+  int32_t _pad;
 } imp_sp_conv_args;
 IMP_API int imp_sp_conv3x3(const imp_sp_conv_args* args, void* stream);
 

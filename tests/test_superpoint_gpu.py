@@ -34,6 +34,9 @@ def test_conv3x3_kernel(Cin, Cout, H, W, B):
     wp = ops.split_planes(w.permute(0, 2, 3, 1).reshape(Cout, -1).contiguous().to(DEV))
     out = ops.Planes.empty((B, H, W, Cout), DEV)
     ops.sp_conv3x3(xp, wp, bias.to(DEV), out, relu=True)
+    pooled = ops.Planes.empty((B, H // 2, W // 2, Cout), DEV)      # fused nn.MaxPool2d(2, 2): same planes as pooling afterwards
+    ops.sp_conv3x3(xp, wp, bias.to(DEV), pooled, relu=True, pool=True)
+    assert torch.equal(pooled.float().permute(0, 3, 1, 2), F.max_pool2d(out.float().permute(0, 3, 1, 2), 2, 2))
     got = out.float().permute(0, 3, 1, 2).double().cpu()
     # fp32-level, not fp32-exact: the tensor core adds every 16-deep partial product into the TMEM accumulator with truncation,
     # so the error grows with K = 9 C_in (measured 7e-6 relative at C_in = 128; an fp16 / TF32 convolution is at 5e-4)
@@ -72,7 +75,7 @@ def test_nms_and_selection_exact(radius):
     supp = torch.empty_like(mask)
     ops.sp_nms(sc, mask, supp, radius)
     assert torch.equal(torch.where(mask.bool(), sc, torch.zeros_like(sc)).cpu(), ref)
-    for mk in (-1, 40, 100000):
+    for mk in (-1, 40, 5000, 100000):     # radix select (k <= 4096), global bitonic sort (radius 0: ~10 k candidates), all
         k_ref, s_ref = spo.detect(ref[0], 0.0025, 4, mk)
         ws = ops.SpSelectWorkspace(H, W, mk, DEV)
         ops.sp_select(sc[0], mask[0], ws, 0.0025, 4, mk)
