@@ -198,6 +198,8 @@ def run_secondary(dev, peaks, n_pairs=224):
         out.update(secondary_pose(dev))
     except ImportError as e:             # no OpenCV on the box
         out['eval loop with host pose'] = {'skipped': str(e)}
+    torch.cuda.empty_cache()
+    out.update(secondary_superpoint(dev))
     return out
 
 
@@ -333,6 +335,55 @@ def secondary_pose(dev, n_pairs=32):
         'serial_pairs_per_s': n_pairs / serial, 'overlapped_pairs_per_s': n_pairs / overlapped, 'pose_workers': workers,
         'note': 'serial = match -> blocking D2H -> RANSAC -> next pair (the reference loop); overlapped = 4 pairs in flight on '
                 'the GPU, RANSAC in worker threads; wall clock, device-resident inputs'}}
+
+
+def secondary_superpoint(dev):
+    """SURVEY.md 8(f) rank 2, measured: the SuperPoint front-end (nets/superpoint.py) and the whole image pair -> matches
+    pipeline on the GPU (SuperPoint on both images, IMP 15 iterations, produce_matches(only_last=True)); the reference algorithm
+    (oracle/superpoint_oracle.py, a port of the reference class pinned by its goldens) timed on the host cores beside it."""
+    from imp_release_b200 import DGNNS
+    from imp_release_b200.nets.superpoint import SuperPoint
+    from oracle import superpoint_oracle as spo
+    from oracle import synth
+    out = {}
+    sp = SuperPoint({'max_keypoints': N_KPTS})
+    sp.load_state_dict(spo.make_state_dict(11))
+    sp = sp.to(dev).eval()
+    with torch.no_grad():
+        for (H, W) in ((480, 640), (1200, 1600)):
+            img = spo.make_image(21, H, W).to(dev)
+            ms = _timed(lambda: sp({'image': img}), 3, 10)
+            dense = _timed(lambda: sp._dense(img), 3, 10)
+            row = {'forward_ms': ms, 'dense_part_ms': dense, 'keypoints': int(sp({'image': img})['keypoints'][0].shape[0])}
+            if H == 480:
+                sd, cfg, cpu_img = spo.make_state_dict(11), {'nms_radius': 4, 'keypoint_threshold': 0.0025, 'remove_borders': 4,
+                                                            'max_keypoints': N_KPTS}, img.cpu()
+                spo.forward(sd, cpu_img, cfg)
+                t0 = time.perf_counter()
+                spo.forward(sd, cpu_img, cfg)
+                row['cpu_port_ms'] = (time.perf_counter() - t0) * 1e3
+                row['cpu_threads'] = torch.get_num_threads()
+            out[f'SuperPoint front-end (SURVEY 8(f) rank 2), {H}x{W} image, top-{N_KPTS} keypoints'] = row
+        # image pair -> matches, everything on the GPU
+        net = DGNNS(model_config(15))
+        net.load_state_dict(synth.make_state_dict('DGNNS', 15, seed=7))
+        net = net.to(dev).eval()
+        imgs = [spo.make_image(30 + i, 1200, 1600).to(dev) for i in range(2)]
+        shape = torch.zeros(1, 1, 1200, 1600)
+
+        def pipeline():
+            f = [sp({'image': im}) for im in imgs]
+            data = {'image0': shape, 'image1': shape}
+            for i in (0, 1):
+                data[f'keypoints{i}'] = f[i]['keypoints'][0][None]
+                data[f'scores{i}'] = f[i]['scores'][0][None]
+                data[f'descriptors{i}'] = f[i]['descriptors'][0].t()[None].contiguous()
+            return net.produce_matches(data, p=0.2, only_last=True)
+
+        ms = _timed(pipeline, 3, 10)
+        out['image pair -> matches on the GPU (2 x SuperPoint 1200x1600 + IMP 15 iters, one pair per call, eager)'] = {
+            'ms_per_pair': ms, 'keypoints_per_image': N_KPTS}
+    return out
 
 
 def secondary_sinkhorn(dev, peaks):

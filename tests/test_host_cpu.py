@@ -73,6 +73,9 @@ def test_product_path_fails_loudly_without_cuda():
 def test_dropin_exports_reference_module_paths():
     code = ('import sys; sys.path.insert(0, %r); from nets.gms import DGNNS; from nets.adgm import AdaGMN; '
             'from nets.gm import GM, normalize_keypoints; from nets.layers import normalize_keypoints as nk2; '
+            'from nets.superpoint import SuperPoint; from components.readers import standard_reader; '
+            'from components.extractors import ExtractSuperpoint; import imp_release_b200.nets.superpoint as sp; '
+            'assert SuperPoint is sp.SuperPoint; '
             'import imp_release_b200 as p; assert DGNNS is p.DGNNS and AdaGMN is p.AdaGMN and GM is p.GM; print("ok")'
             % os.path.join(ROOT, 'dropin'))
     r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, cwd=ROOT)
