@@ -11,7 +11,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
 def to_bytes(v, u):
     m = {'byte': 1, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
     return float(v) * m.get(u, 1)
-out = [f'# ncu --set full summaries, tag {tag}\n', 'Captured with `tools/ncu_capture.sh` (bench workload: 64 pairs, N=2000, 9 iterations; '
+out = [f'# ncu --set full summaries, tag {tag}\n', 'Captured with `tools/ncu_capture.sh` / `tools/ncu_capture_r02c.sh` (bench workload: 64 pairs, N=2000, 9 iterations; '
        '`ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 2 python bench.py --ncu --warmup 1`). '
        'Durations under ncu are serialised / cold-cache; bench.py reports the in-situ CUDA-event times.\n']
 traffic = {}
@@ -32,7 +32,7 @@ for rep in sorted(f for f in os.listdir('gpurun_out') if f.startswith(tag + '_')
         fmt = {'0': 'fp32', '1': 'fp16', '2': 'fp24'}
         full = r[idx['Kernel Name']]
         first_arg = full.split('<')[1].split(',')[0].replace('(int)', '').strip() if '<' in full else ''
-        key = 'attention' if 'attention_kernel' in name else (('sinkhorn_' + fmt.get(first_arg, 'fp32')) if 'skq_iter' in name or 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
+        key = 'superpoint_conv3x3' if 'conv3x3' in name else 'superpoint_conv1a' if 'conv1a' in name else 'attention' if 'attention_kernel' in name else (('sinkhorn_' + fmt.get(first_arg, 'fp32')) if 'skq_iter' in name or 'sk_ring' in name else ('gemm' if 'gemm' in name else 'instnorm'))
         traffic.setdefault(key, []).append(tb)
     src = subprocess.run(['ncu', '-i', os.path.join('gpurun_out', rep), '--page', 'source', '--csv'], capture_output=True, text=True).stdout
     p = subprocess.run([sys.executable, 'tools/ncu_src.py', '0', '12'], input=src, capture_output=True, text=True).stdout
