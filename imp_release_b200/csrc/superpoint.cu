@@ -598,6 +598,12 @@ __global__ void __launch_bounds__(1024) sel_topk_kernel(const int* __restrict__ 
     kpts_xy[2 * i + 1] = (float)cand_yx[2 * src];
     kscores[i] = cand_score[src];
   }
+  // fixed-capacity consumers (SuperPoint.detect_padded -> the matcher's 'n_keypoints' convention) want zero padding up to k
+  for (int i = m + threadIdx.x; i < min(k, cap); i += blockDim.x) {
+    kpts_xy[2 * i] = 0.f;
+    kpts_xy[2 * i + 1] = 0.f;
+    kscores[i] = 0.f;
+  }
   if (threadIdx.x == 0) *n_out = m;
 }
 
@@ -642,7 +648,12 @@ __global__ void sample_desc_kernel(const float* __restrict__ dmap /*[Hc*Wc][256]
                                    const int* __restrict__ n_kpts, float* __restrict__ out /*[K][256]*/, int Hc, int Wc, int max_k) {
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   const int n = n_kpts ? min(*n_kpts, max_k) : max_k;
-  if (k >= n) return;
+  if (k >= max_k) return;
+  if (k >= n) {  // zero padding behind the real keypoints (fixed-capacity output)
+    float4* o = reinterpret_cast<float4*>(out + (long long)k * 256);
+    o[lane] = o[lane + 32] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
   const float s = 8.f;
   // keypoints - s/2 + 0.5, / (w s - s/2 - 0.5), * 2 - 1, then grid_sample
   float gx = (kpts_xy[2 * k] - s / 2 + 0.5f) / (Wc * s - s / 2 - 0.5f);

@@ -146,6 +146,46 @@ class SuperPoint(nn.Module):
         scores, dmap = self._dense(data['image'])
         return scores, dmap.permute(0, 3, 1, 2)
 
+    def detect_padded(self, image: torch.Tensor):
+        """B200-side entry point WITHOUT any host synchronisation: fixed-capacity outputs in the matcher's input layout,
+        {'keypoints': [B, K, 2] (x, y), 'scores': [B, K], 'descriptors': [B, K, 256], 'n_keypoints': [B] int32 (device)},
+        K = config['max_keypoints'] > 0, rows behind the n real keypoints of an image zeroed.  Hand the tensors to
+        ``produce_matches`` as ``keypoints0/scores0/descriptors0/n_keypoints0`` (imp_release_b200/pipeline.py): the whole
+        image pair -> matches path then runs without the host ever waiting for the GPU (``forward`` has to read the keypoint
+        count back, like the reference's torch.nonzero)."""
+        K = self.config['max_keypoints']
+        if K <= 0:
+            raise ValueError('detect_padded needs a positive max_keypoints (the fixed output capacity)')
+        scores, dmap = self._dense(image)
+        B, Hs, Ws = scores.shape
+        Hc, Wc = dmap.shape[1], dmap.shape[2]
+        dev = scores.device
+        mask = torch.empty(B, Hs, Ws, dtype=torch.uint8, device=dev)
+        supp = torch.empty(B, Hs, Ws, dtype=torch.uint8, device=dev)
+        ops.sp_nms(scores, mask, supp, self.config['nms_radius'])
+        ws = self._select_ws(Hs, Ws, K, dev)
+        kpts = torch.empty(B, K, 2, dtype=torch.float32, device=dev)
+        ksc = torch.empty(B, K, dtype=torch.float32, device=dev)
+        desc = torch.empty(B, K, 256, dtype=torch.float32, device=dev)
+        cnt = torch.empty(B, dtype=torch.int32, device=dev)
+        for b in range(B):
+            ops.sp_select(scores[b], mask[b], ws, self.config['keypoint_threshold'], self.config['remove_borders'], K)
+            kpts[b].copy_(ws.kpts[:K])          # stream-ordered copies out of the shared selection workspace
+            ksc[b].copy_(ws.kscores[:K])
+            cnt[b:b + 1].copy_(ws.n_out)
+            ops.sp_sample_descriptors(dmap[b], kpts[b], cnt[b:b + 1], desc[b], Hc, Wc, K)
+        return {'keypoints': kpts, 'scores': ksc, 'descriptors': desc, 'n_keypoints': cnt}
+
+    def _select_ws(self, Hs, Ws, mk, dev):
+        # one workspace per (shape, stream): calls on different streams may be in flight at the same time
+        key = (Hs, Ws, mk, str(dev), torch.cuda.current_stream(dev).cuda_stream)
+        ws = self._sel_ws.get(key)
+        if ws is None:
+            if len(self._sel_ws) > 16:
+                self._sel_ws.clear()
+            ws = self._sel_ws[key] = ops.SpSelectWorkspace(Hs, Ws, mk, dev)
+        return ws
+
     def forward(self, data):
         """{'image': [B, 1, H, W]} -> {'keypoints': [[K, 2] (x, y)], 'scores': [[K]], 'descriptors': [[256, K]]}
         (nets/superpoint.py:185-235)."""
@@ -157,12 +197,7 @@ class SuperPoint(nn.Module):
         supp = torch.empty(B, Hs, Ws, dtype=torch.uint8, device=dev)
         ops.sp_nms(scores, mask, supp, self.config['nms_radius'])
         mk = self.config['max_keypoints']
-        key = (Hs, Ws, mk, str(dev))
-        ws = self._sel_ws.get(key)
-        if ws is None:
-            if len(self._sel_ws) > 4:
-                self._sel_ws.clear()
-            ws = self._sel_ws[key] = ops.SpSelectWorkspace(Hs, Ws, mk, dev)
+        ws = self._select_ws(Hs, Ws, mk, dev)
         keypoints: List[torch.Tensor] = []
         kscores: List[torch.Tensor] = []
         descriptors: List[torch.Tensor] = []

@@ -307,7 +307,7 @@ typedef struct imp_sp_select_args {
   int32_t* cand_yx;      /* scratch [cap, 2] */
   float* cand_score;     /* scratch [cap] */
   uint64_t* keys;        /* scratch [next power of two >= cap] */
-  float* kpts_xy;        /* out [min(cap, max_keypoints), 2] */
+  float* kpts_xy;        /* out [min(cap, max_keypoints), 2]; rows behind the n_out keypoints are zeroed up to max_keypoints */
   float* kscores;        /* out */
   int32_t* n_out;        /* out: number of keypoints */
 } imp_sp_select_args;
@@ -317,7 +317,7 @@ IMP_API int imp_sp_select(const imp_sp_select_args* args, void* stream);
 IMP_API int imp_sp_l2norm_rows(float* x, int64_t rows, int32_t ld, void* stream);
 /* sample_descriptors (nets/superpoint.py:83-95): bilinear interpolation of the normalised [Hc * Wc, 256] map at the keypoints
  * (grid_sample with its default align_corners=False -- the reference's version test `int(torch.__version__[2]) > 2` is false
- * for 1.12 and for 2.x alike -- zero padding), then a second L2 normalisation.  out fp32 [n, 256], n = min(*n_kpts, max_k). */
+ * for 1.12 and for 2.x alike -- zero padding), then a second L2 normalisation.  out fp32 [max_k, 256]: rows n = min(*n_kpts, max_k) .. max_k are zeroed (n_kpts NULL: n = max_k). */
 IMP_API int imp_sp_sample_descriptors(const float* dmap, const float* kpts_xy, const int32_t* n_kpts, float* out, int32_t Hc,
                                       int32_t Wc, int32_t max_k, void* stream);
 

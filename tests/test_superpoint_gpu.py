@@ -141,3 +141,54 @@ def test_extractor_interface(tmp_path):
     assert np.abs(np.linalg.norm(desc, axis=1) - 1).max() < 1e-5
     assert (np.diff(kpt[:, 2]) <= 0).all()          # top-k: descending scores
     assert kpt[:, 0].max() < 260 and kpt[:, 1].max() < 200
+
+
+def test_image_pair_pipeline_without_host_sync():
+    """ImagePairMatcher (SuperPoint.detect_padded -> produce_matches with device-side keypoint counts) against the two-step
+    path with exact-size tensors (SuperPoint.forward, host reads the counts, then the matcher)."""
+    from imp_release_b200 import DGNNS
+    from imp_release_b200.pipeline import ImagePairMatcher
+    from oracle import synth
+    img0 = spo.make_image(41, 240, 320).to(DEV)
+    img1 = torch.roll(img0, shifts=(6, -9), dims=(2, 3)).contiguous()
+    with torch.no_grad():            # capacity K a little above the number of keypoints the images really have
+        cnt = [_net(11, {'max_keypoints': -1, 'keypoint_threshold': 0.03})({'image': im})['keypoints'][0].shape[0] for im in (img0, img1)]
+    assert min(cnt) > 0
+    K = max(cnt) + 37
+    sp = _net(11, {'max_keypoints': K, 'keypoint_threshold': 0.03})
+    nl = 3
+    net = DGNNS(dict(n_layers=nl, GNN_layers=['self', 'cross'] * nl, norm_fn='in', ac_fn='relu', sinkhorn_iterations=20,
+                     with_sinkhorn=True, descriptor_dim=256))
+    net.load_state_dict(synth.make_state_dict('DGNNS', nl, seed=7))
+    net = net.cuda().eval()
+    with torch.no_grad():
+        f0, f1 = sp({'image': img0}), sp({'image': img1})
+        n0, n1 = f0['keypoints'][0].shape[0], f1['keypoints'][0].shape[0]
+        assert 0 < n0 < K and 0 < n1 < K, (n0, n1)
+        data = {'image0': img0, 'image1': img1}
+        for i, f in ((0, f0), (1, f1)):
+            data[f'keypoints{i}'] = f['keypoints'][0][None]
+            data[f'scores{i}'] = f['scores'][0][None]
+            data[f'descriptors{i}'] = f['descriptors'][0].t()[None].contiguous()
+        ref = net.produce_matches(data, p=0.2, only_last=True)
+        out = ImagePairMatcher(sp, net)(img0, img1)
+    assert int(out['n_keypoints0']) == n0 and int(out['n_keypoints1']) == n1
+    assert torch.equal(out['keypoints0'][:n0], f0['keypoints'][0]) and torch.equal(out['keypoints1'][:n1], f1['keypoints'][0])
+    assert float(out['keypoints0'][n0:].abs().sum()) == 0.0
+    assert torch.equal(out['indices0'][:n0], ref['indices0'][-1][0])
+    assert float((out['mscores0'][:n0] - ref['mscores0'][-1][0]).abs().max()) < 1e-4
+    assert int((out['indices0'][:n0] > -1).sum()) > 0          # the shifted image does produce matches
+    assert bool((out['indices0'][n0:] == -1).all())
+    # different image sizes go through two separate detections
+    out2 = ImagePairMatcher(sp, net)(img0, img1[:, :, :200, :280].contiguous())
+    assert out2['indices0'].shape == (K,)
+
+
+def test_no_keypoints_is_an_empty_result():
+    sp = _net(11, {'max_keypoints': 64, 'keypoint_threshold': 0.9})      # nothing passes
+    img = spo.make_image(5, 64, 96).to(DEV)
+    with torch.no_grad():
+        out = sp({'image': img})
+        pad = sp.detect_padded(img)
+    assert out['keypoints'][0].shape == (0, 2) and out['scores'][0].shape == (0,) and out['descriptors'][0].shape == (256, 0)
+    assert int(pad['n_keypoints'][0]) == 0 and float(pad['descriptors'].abs().sum()) == 0.0 and float(pad['keypoints'].abs().sum()) == 0.0
