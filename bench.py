@@ -188,18 +188,23 @@ def run_secondary(dev, peaks, n_pairs=224):
     one-pair-per-call evaluation shape of eval/eval_imp.py:155-173 on ONE rank: >= 200 pairs with distinct ragged keypoint
     counts, 15 iterations, produce_matches(only_last=True)."""
     out = {}
-    out.update(secondary_eimp(dev))
-    torch.cuda.empty_cache()
-    out.update(secondary_b1(dev, n_pairs))
-    torch.cuda.empty_cache()
-    out.update(secondary_sinkhorn(dev, peaks))
-    torch.cuda.empty_cache()
-    try:
-        out.update(secondary_pose(dev))
-    except ImportError as e:             # no OpenCV on the box
-        out['eval loop with host pose'] = {'skipped': str(e)}
-    torch.cuda.empty_cache()
-    out.update(secondary_superpoint(dev))
+
+    def leg(name, fn):       # a failing secondary configuration must never take the headline line down with it
+        try:
+            out.update(fn())
+        except Exception as e:  # noqa: BLE001
+            out[name] = {'error': f'{type(e).__name__}: {e}'[:300]}
+            print(f'[secondary] {name} failed: {e}', file=sys.stderr, flush=True)
+        try:
+            torch.cuda.empty_cache()
+        except Exception:  # noqa: BLE001  (a sticky CUDA error: the headline numbers are already measured)
+            pass
+
+    leg('configs[2] EIMP', lambda: secondary_eimp(dev))
+    leg('configs[3] one rank', lambda: secondary_b1(dev, n_pairs))
+    leg('configs[4] Sinkhorn-only', lambda: secondary_sinkhorn(dev, peaks))
+    leg('eval loop with host pose', lambda: secondary_pose(dev))
+    leg('SuperPoint front-end', lambda: secondary_superpoint(dev))
     return out
 
 

@@ -41,6 +41,7 @@ class AdaGMN(GM):
         eng.received_attention(st, 'cross', a_cross)      # rows already belong to the key image
         return a_self, a_cross
 
+    @ops.on_model_device
     def produce_matches(self, data, p=0.2, mscore_th=0.1, uncertainty_ratio=1., **kwargs):
         desc0, desc1 = data['descriptors0'], data['descriptors1']
         nk0, nk1 = self._norm_kpts(data)
@@ -120,6 +121,7 @@ class AdaGMN(GM):
         return self.produce_matches(data=data, p=p)
 
     # ------------------------------------------------------------------ B = 1 iterative path
+    @ops.on_model_device
     def pool(self, pred_score, prob00, prob01, prob11, prob10, mscore_th=0.1, uncertainty_ratio=1.0, n_min_tokens=256):
         """AdaGMN.pool (nets/adgm.py:552-605): which keypoints of each image to keep; the caller compacts
         (eval/matching.py:166-174).  ``prob*`` are the opaque AttentionStash handles of this model."""

@@ -146,6 +146,7 @@ class GM(nn.Module):
         return r
 
     # ------------------------------------------------------------------ batched entry points
+    @ops.on_model_device
     def forward(self, data, mode=0):
         if self.training:
             raise NotImplementedError('training (forward_train) is out of scope of the B200 inference path')
@@ -276,6 +277,7 @@ class GM(nn.Module):
         holder = _ScoreHolder(scores, am[3] if want_mass else None, am[4] if want_mass else None)
         return scores, i0, i1, m0, m1, holder
 
+    @ops.on_model_device
     def produce_matches(self, data, p=0.2, only_last=False, **kwargs):
         """GM.produce_matches (nets/gm.py:145-247): all GNN layers, then scoring of every iteration (or the last)."""
         desc0, desc1 = data['descriptors0'], data['descriptors1']
@@ -313,6 +315,7 @@ class GM(nn.Module):
         return {'p': out['scores'][-1]}
 
     # ------------------------------------------------------------------ per-layer API (eval/matching.py)
+    @ops.on_model_device
     def encode_keypoint(self, norm_kpts0, norm_kpts1, scores0, scores1):
         """nets/gm.py:287-288 -> (enc0 [B,256,N0], enc1 [B,256,N1]) fp32, channels-first like the reference."""
         eng = self.engine()
@@ -359,6 +362,7 @@ class GM(nn.Module):
         self._io = (o0, o1, o0._version, o1._version)
         return o0, o1
 
+    @ops.on_model_device
     def forward_one_layer(self, desc0, desc1, M0, M1, layer_i):
         """nets/gms.py:260-282 / nets/adgm.py:528-550: one self or cross layer on both images; stateful (the stashed
         attention of a non-sharing layer is consumed by the sharing layer of the next iteration)."""
@@ -374,6 +378,7 @@ class GM(nn.Module):
             self.self_prob1 = AttentionStash('self', 1, self._token)
         return self._export_state(st)
 
+    @ops.on_model_device
     def compute_distance(self, desc0, desc1, layer_id=-1):
         """nets/gm.py:290-295 -> dist [B,N0,N1] (a view of a padded buffer)."""
         st = self._load_state(desc0, desc1)
@@ -385,6 +390,7 @@ class GM(nn.Module):
         eng.distance(st, st.ws.Y, st.N0, st.N1, dist, ldd)
         return dist[:, :, :st.N1]
 
+    @ops.on_model_device
     def compute_score(self, dist, dustbin, iteration):
         """nets/gm.py:297-303 -> scores [B,N0+1,N1+1] (a view of a padded buffer; a real torch.Tensor)."""
         if dist.stride(2) != 1 or dist.stride(1) % 4 != 0:
@@ -401,6 +407,7 @@ class GM(nn.Module):
         self._last_sk = None
         return ops.dual_softmax(dist, dist.stride(1), bin_t.float(), N0, N1, B, dist_batch_stride=dist.stride(0))
 
+    @ops.on_model_device
     def compute_matches(self, scores, p=0.2):
         """nets/gm.py:305-320."""
         B, N0, N1 = scores.shape[0], scores.shape[1] - 1, scores.shape[2] - 1

@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import torch
 
+from .. import ops
 from .gm import GM
 from .layers import SHARING_LAYERS, normalize_keypoints  # noqa: F401
 
@@ -21,6 +22,7 @@ class DGNNS(GM):
             self.__dict__['_side'] = s
         return s
 
+    @ops.on_model_device
     def produce_matches(self, data, p=0.2, only_last=False, **kwargs):
         """nets/gms.py:139-258: per iteration self layer, cross layer, then (every iteration or last only)
         final_proj -> Sinkhorn -> matches.  The reference also returns the four [B,4,N,M] attention maps per

@@ -141,11 +141,13 @@ class SuperPoint(nn.Module):
         ops.sp_l2norm_rows(dmap)
         return scores, dmap.view(B, Hc, Wc, 256)
 
+    @ops.on_model_device
     def extract(self, data):
         """Dense scores [B, H, W] (no NMS) and descriptors [B, 256, Hc, Wc] (nets/superpoint.py:154-183)."""
         scores, dmap = self._dense(data['image'])
         return scores, dmap.permute(0, 3, 1, 2)
 
+    @ops.on_model_device
     def detect_padded(self, image: torch.Tensor):
         """B200-side entry point WITHOUT any host synchronisation: fixed-capacity outputs in the matcher's input layout,
         {'keypoints': [B, K, 2] (x, y), 'scores': [B, K], 'descriptors': [B, K, 256], 'n_keypoints': [B] int32 (device)},
@@ -186,6 +188,7 @@ class SuperPoint(nn.Module):
             ws = self._sel_ws[key] = ops.SpSelectWorkspace(Hs, Ws, mk, dev)
         return ws
 
+    @ops.on_model_device
     def forward(self, data):
         """{'image': [B, 1, H, W]} -> {'keypoints': [[K, 2] (x, y)], 'scores': [[K]], 'descriptors': [[256, K]]}
         (nets/superpoint.py:185-235)."""

@@ -43,6 +43,23 @@ class _Span:
         return False
 
 
+def on_model_device(fn):
+    """Decorator for the public entry points of the host classes: run with the model's own GPU as the current CUDA device.
+    The kernels launch on the CURRENT device's current stream, so a model living on cuda:1 while the caller's current device
+    is cuda:0 would otherwise launch on the wrong GPU (one process driving several GPUs; per-device kernel attributes are
+    handled by DeviceOnce in the launchers)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(self, *a, **kw):
+        p = next(self.parameters(), None)
+        if p is None or not p.is_cuda or p.device.index == torch.cuda.current_device():
+            return fn(self, *a, **kw)
+        with torch.cuda.device(p.device):
+            return fn(self, *a, **kw)
+    return wrapped
+
+
 def _require_cuda(t: torch.Tensor):
     if not t.is_cuda:
         raise _lib.ImpLibraryError('imp_release_b200 kernels need CUDA tensors (there is no CPU path)')

@@ -330,3 +330,28 @@ def test_evaluate_pairs_overlaps_gpu_matching_with_host_pose():
             assert n in calls
             if r is not None:
                 assert r[3].shape == (n,) and r[1].shape == (3, 3)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason='needs two GPUs in one process')
+def test_model_on_second_gpu_while_first_is_current():
+    """One process driving two GPUs: a model that lives on cuda:1 is called while cuda:0 is the current device.  The entry
+    points switch to the model's device (ops.on_model_device) and the launchers configure their kernels per device."""
+    from imp_release_b200 import DGNNS
+    nl = 3
+    cfg = dict(n_layers=nl, GNN_layers=['self', 'cross'] * nl, norm_fn='in', ac_fn='relu', sinkhorn_iterations=20,
+               with_sinkhorn=True, descriptor_dim=256)
+    sd = synth.make_state_dict('DGNNS', nl, seed=7)
+    data = synth.make_pair_batch(seed=4, batch=2, n0=300, n1=260)
+    outs = []
+    torch.cuda.set_device(0)
+    for dev in ('cuda:0', 'cuda:1'):
+        net = DGNNS(cfg)
+        net.load_state_dict(sd)
+        net = net.to(dev).eval()
+        with torch.no_grad():
+            o = net({k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()})
+        assert torch.cuda.current_device() == 0
+        assert o['indices0'][-1].device == torch.device(dev)
+        outs.append(o)
+    assert torch.equal(outs[0]['indices0'][-1].cpu(), outs[1]['indices0'][-1].cpu())
+    assert float((outs[0]['mscores0'][-1].cpu() - outs[1]['mscores0'][-1].cpu()).abs().max()) < 1e-5
