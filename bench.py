@@ -409,12 +409,25 @@ def secondary_superpoint(dev):
         torch.cuda.synchronize()
         ms_flight = (time.perf_counter() - t0) * 1e3 / n_pairs
         same = all(torch.equal(r['indices0'], res[0]['indices0']) for r in res[1:])
+        # ... and as CUDA-graph replay (one graph per slot holds both detections and the matcher: ~600 launches per pair)
+        from imp_release_b200.pipeline import GraphedImagePairMatcher
+        gm = GraphedImagePairMatcher(sp, net, slots=slots)
+        for _ in range(2 * slots):
+            gm(imgs[0], imgs[1])
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        tickets = [gm.submit(imgs[0], imgs[1]) for _ in range(n_pairs)]
+        gres = [gm.result(t) for t in tickets]
+        torch.cuda.synchronize()
+        ms_graph = (time.perf_counter() - t0) * 1e3 / n_pairs
+        same = same and all(torch.equal(r['indices0'], res[0]['indices0']) for r in gres)
         out['image pair -> matches on the GPU (2 x SuperPoint 1200x1600 + IMP 15 iters, one pair per call, eager)'] = {
             'two_step_ms_per_pair': ms_two, 'no_host_sync_ms_per_pair': ms_pipe, 'no_host_sync_4_in_flight_ms_per_pair': ms_flight,
-            'in_flight_results_identical': same, 'keypoints_per_image': N_KPTS,
+            'graph_replay_4_in_flight_ms_per_pair': ms_graph, 'in_flight_results_identical': same, 'keypoints_per_image': N_KPTS,
             'note': 'two_step = SuperPoint.forward (host reads the keypoint counts) then produce_matches; no_host_sync = '
                     'imp_release_b200.pipeline.ImagePairMatcher (device-side counts, the host only enqueues): 10 pairs '
-                    'back to back between two CUDA events; 4_in_flight = 32 pairs round-robin over 4 streams, wall clock'}
+                    'back to back between two CUDA events; 4_in_flight = 32 pairs round-robin over 4 streams, wall clock; graph_replay = '
+                    'the same with one CUDA graph per slot (pipeline.GraphedImagePairMatcher)'}
     return out
 
 

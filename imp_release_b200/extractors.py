@@ -1,6 +1,11 @@
-"""ExtractSuperpoint with the reference's interface (components/extractors.py:50-89): image file -> (kpt [N, 3] = x, y, score in
-original-image pixels; desc [N, 256]), on top of the B200 SuperPoint.  Host-side image reading / resizing stays on the host
-(cv2), exactly as in the reference."""
+"""Feature extraction with the reference's interface (components/extractors.py:50-89, ``ExtractSuperpoint``): an image file
+goes in, ``(kpt [N, 3] = x, y, score in original-image pixels, desc [N, 256])`` comes out -- on top of the B200 SuperPoint
+(imp_release_b200/nets/superpoint.py).  Reading and resizing the image stay on the host (cv2), as in the reference.
+
+Behaviour kept on purpose: the config key ``det_th`` travels as ``detection_threshold``, which SuperPoint never reads (its
+default ``keypoint_threshold`` applies); ``padding`` tops the result up to ``num_kpt`` with random keypoints of score 0 and
+random unit descriptors.
+"""
 from __future__ import annotations
 
 import numpy as np
@@ -10,51 +15,54 @@ from .nets.superpoint import SuperPoint
 
 
 def resize(img, resize):
-    """components/extractors.py:14-24: longest side (one value) or (h, w) (two values)."""
+    """components/extractors.py:14-24.  ``resize`` = [longest side] or [height, width]; returns the uint8 image and the
+    (x, y) scale factors that map original to resized coordinates."""
     import cv2
-    img_h, img_w = img.shape[0], img.shape[1]
-    cur_size = max(img_h, img_w)
+    h, w = img.shape[:2]
     if len(resize) == 1:
-        scale1, scale2 = resize[0] / cur_size, resize[0] / cur_size
+        sy = sx = resize[0] / max(h, w)
     else:
-        scale1, scale2 = resize[0] / img_h, resize[1] / img_w
-    new_h, new_w = int(img_h * scale1), int(img_w * scale2)
-    new_img = cv2.resize(img.astype('float32'), (new_w, new_h)).astype('uint8')
-    return new_img, np.asarray([scale2, scale1])
+        sy, sx = resize[0] / h, resize[1] / w
+    out = cv2.resize(img.astype('float32'), (int(w * sx), int(h * sy))).astype('uint8')
+    return out, np.asarray([sx, sy])
 
 
 class ExtractSuperpoint(object):
     def __init__(self, config):
-        default_config = {
-            'descriptor_dim': 256,
-            'nms_radius': 4,
-            'detection_threshold': config['det_th'],   # sic: SuperPoint reads 'keypoint_threshold', so its default applies
-            'max_keypoints': config['num_kpt'],
-            'remove_borders': 4,
-            'weight_path': config.get('weight_path', '../weights/superpoint_v1.pth'),
-        }
-        self.superpoint_extractor = SuperPoint(default_config)
-        self.superpoint_extractor.eval(), self.superpoint_extractor.cuda()
+        sp_config = dict(descriptor_dim=256, nms_radius=4, remove_borders=4,
+                         detection_threshold=config['det_th'],
+                         max_keypoints=config['num_kpt'],
+                         weight_path=config.get('weight_path', '../weights/superpoint_v1.pth'))
+        self.superpoint_extractor = SuperPoint(sp_config).eval().cuda()
         self.num_kp = config['num_kpt']
-        self.padding = config['padding'] if 'padding' in config.keys() else False
+        self.padding = bool(config.get('padding', False))
         self.resize = config['resize']
 
+    def _pad(self, kpt, desc, extent):
+        """Random filler up to num_kp (components/extractors.py:79-88): positions uniform in [0, extent), score 0."""
+        missing = int(self.num_kp - len(kpt))
+        if missing <= 0:
+            return kpt, desc
+        xy = np.random.uniform(size=[missing, 2]) * extent
+        filler_desc = np.random.uniform(size=[missing, 256])
+        filler_desc /= np.linalg.norm(filler_desc, axis=-1, keepdims=True)
+        filler_kpt = np.concatenate([xy, np.zeros([missing, 1])], axis=-1)
+        return np.concatenate([kpt, filler_kpt], axis=0), np.concatenate([desc, filler_desc], axis=0)
+
     def run_image(self, img: np.ndarray):
-        """Grayscale uint8 image [H, W] (already read) -> (kpt [N, 3], desc [N, 256])."""
+        """Grayscale uint8 image [H, W] (already decoded) -> (kpt [N, 3], desc [N, 256])."""
         scale = 1
         if self.resize[0] != -1:
             img, scale = resize(img, self.resize)
+        image = torch.from_numpy(img / 255.).float()[None, None].cuda()
         with torch.no_grad():
-            result = self.superpoint_extractor({'image': torch.from_numpy(img / 255.).float()[None, None].cuda()})
-        score, kpt, desc = result['scores'][0], result['keypoints'][0], result['descriptors'][0]
-        score, kpt, desc = score.cpu().numpy(), kpt.cpu().numpy(), desc.cpu().numpy().T
-        kpt = np.concatenate([kpt / scale, score[:, np.newaxis]], axis=-1)
-        if self.padding and len(kpt) < self.num_kp:      # components/extractors.py:79-88 (random padding)
-            res = int(self.num_kp - len(kpt))
-            pad_x, pad_desc = np.random.uniform(size=[res, 2]) * (img.shape[0] + img.shape[1]) / 2, np.random.uniform(size=[res, 256])
-            pad_kpt = np.concatenate([pad_x, np.zeros([res, 1])], axis=-1)
-            pad_desc = pad_desc / np.linalg.norm(pad_desc, axis=-1)[:, np.newaxis]
-            kpt, desc = np.concatenate([kpt, pad_kpt], axis=0), np.concatenate([desc, pad_desc], axis=0)
+            feats = self.superpoint_extractor({'image': image})
+        xy = feats['keypoints'][0].cpu().numpy() / scale
+        score = feats['scores'][0].cpu().numpy()
+        desc = feats['descriptors'][0].t().contiguous().cpu().numpy()
+        kpt = np.concatenate([xy, score[:, None]], axis=-1)
+        if self.padding:
+            kpt, desc = self._pad(kpt, desc, (img.shape[0] + img.shape[1]) / 2)
         return kpt, desc
 
     def run(self, img_path):

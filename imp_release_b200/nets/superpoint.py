@@ -30,25 +30,19 @@ class SuperPoint(nn.Module):
         'remove_borders': 4,
     }
 
+    # (name, C_in, C_out, kernel): shared encoder, detector head (Pa, Pb), descriptor head (Da, Db)
+    LAYERS = (('conv1a', 1, 64, 3), ('conv1b', 64, 64, 3), ('conv2a', 64, 64, 3), ('conv2b', 64, 64, 3), ('conv3a', 64, 128, 3),
+              ('conv3b', 128, 128, 3), ('conv4a', 128, 128, 3), ('conv4b', 128, 128, 3), ('convPa', 128, 256, 3),
+              ('convPb', 256, 65, 1), ('convDa', 128, 256, 3), ('convDb', 256, 256, 1))
+
     def __init__(self, config):
         super().__init__()
         self.config = {**self.default_config, **config}
         if self.config['descriptor_dim'] != 256:
             raise NotImplementedError('the B200 kernels are specialised for 256-d descriptors')
-        c1, c2, c3, c4, c5 = 64, 64, 128, 128, 256
-        # parameter containers only (same names / shapes as nets/superpoint.py:122-143); never called
-        self.conv1a = nn.Conv2d(1, c1, kernel_size=3, stride=1, padding=1)
-        self.conv1b = nn.Conv2d(c1, c1, kernel_size=3, stride=1, padding=1)
-        self.conv2a = nn.Conv2d(c1, c2, kernel_size=3, stride=1, padding=1)
-        self.conv2b = nn.Conv2d(c2, c2, kernel_size=3, stride=1, padding=1)
-        self.conv3a = nn.Conv2d(c2, c3, kernel_size=3, stride=1, padding=1)
-        self.conv3b = nn.Conv2d(c3, c3, kernel_size=3, stride=1, padding=1)
-        self.conv4a = nn.Conv2d(c3, c4, kernel_size=3, stride=1, padding=1)
-        self.conv4b = nn.Conv2d(c4, c4, kernel_size=3, stride=1, padding=1)
-        self.convPa = nn.Conv2d(c4, c5, kernel_size=3, stride=1, padding=1)
-        self.convPb = nn.Conv2d(c5, 65, kernel_size=1, stride=1, padding=0)
-        self.convDa = nn.Conv2d(c4, c5, kernel_size=3, stride=1, padding=1)
-        self.convDb = nn.Conv2d(c5, self.config['descriptor_dim'], kernel_size=1, stride=1, padding=0)
+        # parameter containers only -- same names, shapes and registration order as nets/superpoint.py:122-143; never called
+        for name, cin, cout, k in self.LAYERS:
+            setattr(self, name, nn.Conv2d(cin, cout, kernel_size=k, stride=1, padding=k // 2))
         # the reference requires config['weight_path'] (nets/superpoint.py:146-147); None / absent = keep the initialisation
         # (B200-side allowance: pretrained weights are not always at hand, e.g. in the parity tests)
         path = self.config.get('weight_path', None)

@@ -53,3 +53,73 @@ class ImagePairMatcher:
         return {'keypoints0': f0['keypoints'][0], 'keypoints1': f1['keypoints'][0],
                 'n_keypoints0': f0['n_keypoints'], 'n_keypoints1': f1['n_keypoints'],
                 'indices0': out['indices0'][-1][0], 'mscores0': out['mscores0'][-1][0]}
+
+
+class GraphedImagePairMatcher:
+    """The same pipeline as CUDA-graph replay with several pairs in flight: one graph per (slot, image shapes) holds the whole
+    image pair -> matches computation (two SuperPoint detections + the matcher's 15 iterations, ~600 launches), so a submit
+    costs the host two image copies, one graph launch and a few result clones.  ``ticket = g.submit(img0, img1)``,
+    ``out = g.result(ticket)`` (or ``out = g(img0, img1)``); results as from ``ImagePairMatcher``."""
+
+    def __init__(self, superpoint, matcher, slots: int = 4, p: float = 0.2):
+        self.device = next(matcher.parameters()).device
+        self.slots = [dict(ipm=ipm, stream=torch.cuda.Stream(device=self.device), graphs={})
+                      for ipm in ImagePairMatcher.slots(superpoint, matcher, slots, p)]
+        self._next = 0
+        self.captures = 0
+
+    @staticmethod
+    def _reset_caches(m):
+        m._sk_cache = {}
+        m._last_sk = None
+        for k in ('_dist', '_dist_key', '_n_tok_cache'):
+            m.__dict__.pop(k, None)
+
+    def _capture(self, slot, shape0, shape1):
+        ipm, dev = slot['ipm'], self.device
+        m = ipm.matcher
+        img0, img1 = torch.zeros(shape0, device=dev), torch.zeros(shape1, device=dev)
+        # the graph bakes in the addresses of every cached buffer: start from empty caches and let the graph entry own them
+        # afterwards (the model's caches are bounded and evict; see graphed.LatencyMatcher._capture)
+        self._reset_caches(m)
+        with torch.no_grad():
+            for _ in range(2):                       # warm-up on this stream: weight packing, workspaces, kernel attributes
+                ipm(img0, img1)
+            slot['stream'].synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=slot['stream']):
+                out = ipm(img0, img1)
+        keep = (m._sk_cache, m.__dict__.get('_dist'), m.__dict__.get('_last_sk'), list(m.engine()._ws.values()),
+                dict(ipm.sp._sel_ws))
+        self._reset_caches(m)
+        self.captures += 1
+        return {'graph': g, 'img0': img0, 'img1': img1, 'out': out, 'keep': keep}
+
+    def submit(self, image0: torch.Tensor, image1: torch.Tensor):
+        slot = self.slots[self._next]
+        self._next = (self._next + 1) % len(self.slots)
+        cur = torch.cuda.current_stream(self.device)
+        s = slot['stream']
+        s.wait_stream(cur)                           # the images were produced on the caller's stream
+        key = (tuple(image0.shape), tuple(image1.shape))
+        with torch.cuda.stream(s):
+            e = slot['graphs'].get(key)
+            if e is None:
+                e = slot['graphs'][key] = self._capture(slot, *key)
+            e['img0'].copy_(image0, non_blocking=True)
+            e['img1'].copy_(image1, non_blocking=True)
+            e['graph'].replay()
+            res = {k: v.clone() for k, v in e['out'].items()}
+            done = torch.cuda.Event()
+            done.record(s)
+        for t in res.values():
+            t.record_stream(cur)
+        res['done'] = done
+        return res
+
+    def result(self, ticket):
+        torch.cuda.current_stream(self.device).wait_event(ticket['done'])
+        return {k: v for k, v in ticket.items() if k != 'done'}
+
+    def __call__(self, image0, image1):
+        return self.result(self.submit(image0, image1))

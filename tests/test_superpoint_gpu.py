@@ -182,6 +182,19 @@ def test_image_pair_pipeline_without_host_sync():
     # different image sizes go through two separate detections
     out2 = ImagePairMatcher(sp, net)(img0, img1[:, :, :200, :280].contiguous())
     assert out2['indices0'].shape == (K,)
+    # the same pipeline as CUDA-graph replay, 3 pairs in flight on 2 slots, a second shape in between
+    from imp_release_b200.pipeline import GraphedImagePairMatcher
+    gm = GraphedImagePairMatcher(sp, net, slots=2)
+    img2 = torch.roll(img0, shifts=(-3, 5), dims=(2, 3)).contiguous()
+    tickets = [gm.submit(img0, img1), gm.submit(img0, img2), gm.submit(img0[:, :, :200], img1[:, :, :200]), gm.submit(img0, img1)]
+    r = [gm.result(t) for t in tickets]
+    torch.cuda.synchronize()
+    for g_out in (r[0], r[3]):
+        assert torch.equal(g_out['indices0'], out['indices0']) and torch.equal(g_out['keypoints1'], out['keypoints1'])
+        assert float((g_out['mscores0'] - out['mscores0']).abs().max()) < 1e-4
+    ref2 = ImagePairMatcher(sp, net)(img0, img2)
+    assert torch.equal(r[1]['indices0'], ref2['indices0']) and int(r[1]['n_keypoints1']) == int(ref2['n_keypoints1'])
+    assert gm.captures == 3            # slot 0: full-size shape + cropped shape, slot 1: full-size shape
 
 
 def test_no_keypoints_is_an_empty_result():
