@@ -38,6 +38,7 @@ static constexpr float AT_RESCALE_TAU = 8.0f;
 
 struct AttnKernelParams {
   int n_img, src_offset, Nq_max, Nk_max, shared;
+  int lse_only;  // SPLIT kernel only: produce just the row LSE (no V, no P, no O): the pass EIMP's pooling statistics need
   const int *nq, *nk;
   float* lse;
   __half *out_hi, *out_lo;
@@ -115,12 +116,13 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         const int s = j % STG;
         mbar_wait(&kv_empty[s], ((j / STG) & 1) ^ 1);
         uint8_t* st = s_kv + s * STAGE_BYTES;
-        mbar_arrive_expect_tx(&kv_full[s], STAGE_BYTES);
+        const bool no_v = SPLIT && p.lse_only;
+        mbar_arrive_expect_tx(&kv_full[s], no_v ? STAGE_BYTES / 2 : STAGE_BYTES);
         tma_load_3d(st, &tm_k, &kv_full[s], h * AT_D, j * BN, src);
-        tma_load_3d(st + KV_BYTES, &tm_v, &kv_full[s], h * AT_D, j * BN, src);
+        if (!no_v) tma_load_3d(st + KV_BYTES, &tm_v, &kv_full[s], h * AT_D, j * BN, src);
         if (SPLIT) {
           tma_load_3d(st + 2 * KV_BYTES, &tm_kl, &kv_full[s], h * AT_D, j * BN, src);
-          tma_load_3d(st + 3 * KV_BYTES, &tm_vl, &kv_full[s], h * AT_D, j * BN, src);
+          if (!no_v) tma_load_3d(st + 3 * KV_BYTES, &tm_vl, &kv_full[s], h * AT_D, j * BN, src);
         }
       }
     }
@@ -152,6 +154,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         umma_commit(s_full);
         mbar_wait(p_full, j & 1);
         tc_fence_after();
+        if (!(SPLIT && p.lse_only))
 #pragma unroll
         for (int kk = 0; kk < BN / 16; ++kk) {  // 16 keys per MMA: 8 packed fp16x2 columns of P, 2 KB of V
           const uint64_t dv = make_smem_desc_sw128(v_addr + kk * 2048, 1024, 1024);
@@ -219,7 +222,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
             l_run *= alpha;
             m_run = m_new;
           }
-          if (j > 0) {
+          if (j > 0 && !(SPLIT && p.lse_only)) {
             const uint32_t o_addr = tmem_base + lane_off + COL_O;
 #pragma unroll
             for (int cb = 0; cb < AT_D; cb += 32) {
@@ -248,6 +251,18 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_ld_x32(s_addr, r);
         tmem_ld_x32(s_addr + 32, r + 32);
         tmem_wait_ld();
+        if (p.lse_only) {  // same exponentials, same summation order as below: the LSE comes out bit-identical
+#pragma unroll
+          for (int c = 0; c < BN; c += 2) {
+            float p0 = fast_exp2(fmaf(__uint_as_float(r[c]), AT_SCALE_LOG2, neg_ref));
+            float p1 = fast_exp2(fmaf(__uint_as_float(r[c + 1]), AT_SCALE_LOG2, neg_ref));
+            if (ragged) {
+              p0 = (c < nvalid) ? p0 : 0.f;
+              p1 = (c + 1 < nvalid) ? p1 : 0.f;
+            }
+            lsum += p0 + p1;
+          }
+        } else {
         uint32_t ph[BN / 2], pl[BN / 2];
 #pragma unroll
         for (int c = 0; c < BN; c += 2) {
@@ -266,6 +281,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         tmem_st_x32(s_addr, ph);
         tmem_st_x32(s_addr + BN / 2, pl);
+        }
       } else {
       // pass 2: p = exp2(s * c - ref), packed fp16 written over the score columns (chunk cb lands in columns
       // [cb/2, cb/2+16), which this thread has already consumed)
@@ -307,6 +323,10 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     __half* oh = p.out_hi + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
     __half* ol = p.out_lo + img * p.out_img_stride + (long long)qrow * AT_C + h * AT_D;
     float v[AT_D];
+    if (SPLIT && p.lse_only) {
+      if (T > 0) mbar_wait(o_done, (T - 1) & 1);
+      if (row_ok) p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow] = m_run + log2f(l_run);
+    } else {
     if (T > 0) {
       mbar_wait(o_done, (T - 1) & 1);
       tc_fence_after();
@@ -340,6 +360,7 @@ attention_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       }
       if (!p.shared) p.lse[((long long)img * AT_HEADS + h) * p.Nq_max + qrow] = m_run + log2f(l_run);
     }
+    }
     tc_fence_before();
   }
   __syncthreads();
@@ -356,14 +377,14 @@ static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   CUtensorMap tq, tk, tv, tql, tkl, tvl;
   if (make_tmap_f16_3d(&tq, a.q, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
   if (make_tmap_f16_3d(&tk, a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
-  if (make_tmap_f16_3d(&tv, a.v, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+  if (make_tmap_f16_3d(&tv, a.v != nullptr ? a.v : a.k, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
   tql = tq;
   tkl = tk;
   tvl = tv;
   if (SPLIT) {
     if (make_tmap_f16_3d(&tql, a.q_lo, AT_C, a.Nq_max, a.n_img, a.q_row_stride, a.q_img_stride, AT_D, AT_BM)) return 3;
     if (make_tmap_f16_3d(&tkl, a.k_lo, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
-    if (make_tmap_f16_3d(&tvl, a.v_lo, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
+    if (make_tmap_f16_3d(&tvl, a.v_lo != nullptr ? a.v_lo : a.k_lo, AT_C, a.Nk_max, a.n_img, a.kv_row_stride, a.kv_img_stride, AT_D, BN)) return 3;
   }
   AttnKernelParams p;
   p.n_img = a.n_img;
@@ -371,6 +392,7 @@ static int launch_attention_impl(const AttnArgs& a, cudaStream_t st) {
   p.Nq_max = a.Nq_max;
   p.Nk_max = a.Nk_max;
   p.shared = a.shared;
+  p.lse_only = (SPLIT && a.out_hi == nullptr) ? 1 : 0;
   p.nq = a.nq;
   p.nk = a.nk;
   p.lse = a.lse;
@@ -398,6 +420,11 @@ void attention_set_variant(int v) { g_attn_variant = v; }
 int launch_attention(const AttnArgs& a, cudaStream_t st) {
   IMP_REQUIRE(a.n_img > 0 && a.Nq_max > 0 && a.Nk_max > 0, "attention: empty problem");
   IMP_REQUIRE(a.q_row_stride >= AT_C && a.kv_row_stride >= AT_C, "attention: row strides must be >= 256");
+  if (a.out_hi == nullptr || a.out_lo == nullptr) {  // LSE-only pass (EIMP pooling statistics)
+    IMP_REQUIRE(a.q_lo != nullptr && a.k_lo != nullptr && !a.shared && a.lse != nullptr,
+                "attention: the LSE-only mode (out_hi = NULL) exists for the split-precision kernel (q_lo, k_lo) and writes lse");
+    return launch_attention_impl<64, 2, 2, true>(a, st);
+  }
   if (a.q_lo != nullptr || a.k_lo != nullptr || a.v_lo != nullptr) {
     IMP_REQUIRE(a.q_lo != nullptr && a.k_lo != nullptr && a.v_lo != nullptr, "attention: high-precision mode needs q_lo, k_lo and v_lo");
     return launch_attention_impl<64, 2, 2, true>(a, st);  // 96 KB smem, 128 TMEM columns -> 2 CTAs/SM

@@ -295,11 +295,12 @@ class Engine:
         lse = ws.lse[name]
         if lo and not self.hp:
             # the stashed LSE belongs to the fp16 scores of the layer; the split-precision scores need their own
-            # (high-precision attention pass: only its LSE output is used, O goes to the free message buffer)
+            # (LSE-only pass of the high-precision attention kernel: Q K^T with the 3-product split + softmax statistics,
+            # no V, no P V)
             lse = ws.lse_exact(name)
-            ops.attention(base, k_ptr, k_ptr + 2 * D, n_img=ws.n_img, src_offset=off, Nq_max=ws.Np, Nk_max=ws.Np, nq=st.n_tok,
-                          nk=nk, shared=False, lse=lse, out=ws.A, q_row_stride=3 * D, kv_row_stride=kv_rs, q_lo=base_lo,
-                          k_lo=k_lo, v_lo=k_lo + 2 * D)
+            ops.attention(base, k_ptr, None, n_img=ws.n_img, src_offset=off, Nq_max=ws.Np, Nk_max=ws.Np, nq=st.n_tok,
+                          nk=nk, shared=False, lse=lse, out=None, q_row_stride=3 * D, kv_row_stride=kv_rs, q_lo=base_lo,
+                          k_lo=k_lo, v_lo=None)
         ops.attention_colsum(base, k_ptr, n_img=ws.n_img, src_offset=off, Nq_max=ws.Np, Nk_max=ws.Np, nq=st.n_tok, nk=nk,
                              lse=lse, colsum=out, q_row_stride=3 * D, kv_row_stride=kv_rs, q_lo=base_lo, k_lo=k_lo,
                              scratch=ws.colsum_scratch(), by_key_image=True)

@@ -155,7 +155,7 @@ def _p(t):
 
 
 def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int, nq, nk, shared: bool, lse,
-              out: Planes, q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
+              out: Optional[Planes], q_row_stride: int = 256, kv_row_stride: int = 256, q_img_stride: Optional[int] = None,
               kv_img_stride: Optional[int] = None, q_lo=None, k_lo=None, v_lo=None):
     """q/k/v: fp16 tensors or raw device addresses (slices of a fused projection buffer).
     ``work_hint``: algorithmic FLOPs of this call (QK^T + PV = 4*d per score element), for the profiler only."""
@@ -169,10 +169,10 @@ def attention(q, k, v, *, n_img: int, src_offset: int, Nq_max: int, Nk_max: int,
     a.nq, a.nk = ptr(nq), ptr(nk)
     a.shared = int(shared)
     a.lse = ptr(lse)
-    a.out_hi, a.out_lo = ptr(out.hi), ptr(out.lo)
+    a.out_hi, a.out_lo = (ptr(out.hi), ptr(out.lo)) if out is not None else (None, None)   # None: LSE-only pass
     a.out_img_stride = Nq_max * 256
     a.q_lo, a.k_lo, a.v_lo = _p(q_lo), _p(k_lo), _p(v_lo)
-    with _Span('attention_shared' if shared else 'attention', 1, attn_work):
+    with _Span('attention_lse_only' if out is None else 'attention_shared' if shared else 'attention', 1, attn_work):
         check(_lib.load().imp_attention(C.byref(a), stream_ptr()), 'imp_attention')
 
 

@@ -94,7 +94,9 @@ typedef struct imp_attn_args {
   int32_t shared;         /* 1: reuse previous probabilities via lse (SharedAttentionalPropagation) */
   int32_t _pad;
   float* lse;            /* [n_img, 4, Nq_max] log2-domain LSE; written if !shared, read if shared */
-  void *out_hi, *out_lo; /* [n_img, Nq_max, 256] fp16 planes */
+  void *out_hi, *out_lo; /* [n_img, Nq_max, 256] fp16 planes.  Both NULL (with q_lo, k_lo given, shared = 0): LSE-only pass --
+                          * just the split-precision row LSE is produced (no V, no P V; v / v_lo may be NULL): what EIMP's pooling
+                          * statistics need next to imp_attention_colsum (nets/adgm.py:424-427) */
   int64_t out_img_stride;
   /* optional "lo" planes of Q, K, V (same strides).  All three non-NULL selects the high-precision mode: 3-product
    * split contractions for QK^T and PV (fp32-level attention, ~1.6x the time); NULL = single fp16 operands */

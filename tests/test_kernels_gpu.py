@@ -455,6 +455,11 @@ def test_attention_high_precision_mode():
             err = max(err, float((o[img, :nq_i].double() - ref).abs().max()))
             if mode == 'high':
                 assert float((lse[img, :, :nq_i].double() - lref).abs().max()) < 1e-3
+                # LSE-only pass (no V, no output): the same statistics bit for bit
+                lse1 = torch.zeros_like(lse)
+                ops.attention(pq.hi, pk.hi, None, n_img=n_img, src_offset=1, Nq_max=N, Nk_max=N, nq=nqs, nk=nqs, shared=False,
+                              lse=lse1, out=None, q_lo=pq.lo, k_lo=pk.lo, v_lo=None)
+                assert torch.equal(lse1[img, :, :nq_i], lse[img, :, :nq_i])
                 # shared mode with the same precision reproduces the same probabilities
                 out2 = ops.Planes.empty((n_img, N, 256), DEV)
                 ops.attention(pq.hi, pk.hi, pv.hi, n_img=n_img, src_offset=1, Nq_max=N, Nk_max=N, nq=nqs, nk=nqs, shared=True,
