@@ -68,7 +68,12 @@ inline int sk_rows_per_cta(int R, int nb, int wave_ctas, int step) {
     const long long waves = (ctas + wave - 1) / wave;
     const double eff = (double)ctas / (double)(waves * wave);
     const double balance = (double)R / (double)(((R + r - 1) / r) * r);  // ragged last block of each matrix
-    const double score = eff * balance;
+    // every work item pays a fixed price next to its r rows (v of its columns recomputed from the column-sum buffers, the
+    // column sums flushed with one atomic per column): weighted as 4 rows' worth, which keeps the measured optimum (88 rows)
+    // for batch 64 x 2001.  Without this term batch 128 x 2001 chose 8-row items (32128 of them fill 109 waves to 99.6 %)
+    // and ran 4x slower per matrix than batch 64 (measured: 0.690 vs 0.167 ms per sweep).
+    const double overhead = (double)r / (double)(r + 4);
+    const double score = eff * balance * overhead;
     if (score > best + 1e-3) {
       best = score;
       rows_per_cta = r;

@@ -4,7 +4,8 @@ Batched ``produce_matches`` (nets/adgm.py:327-526): queries are never dropped; f
 the KEYS / VALUES of every attention call are restricted to the kept ids of their image.  The reference does that
 with dense {0,1} masks over the [N, N] score matrix; here the kept K / V rows are physically compacted (gather
 kernel) and the attention kernel simply sees fewer keys -- masked probabilities are exactly 0 in the reference, so
-the two are equivalent.  The keep sets, Sinkhorn sizes and match scatter all stay on the device (no host sync per
+the two are equivalent.  The keep sets, per-sample Sinkhorn sizes and match scatter all stay on the device (one host read of the largest kept count per
+pruning round, none per
 iteration); only the final 'scores' slice needs the last sample's sizes.
 """
 from __future__ import annotations
@@ -55,6 +56,7 @@ class AdaGMN(GM):
         all_i0, all_m0 = [], []
         last_sk = None
         yc = None
+        S0, S1 = N0, N1            # capacity of the kept-subset problems (distance GEMM, Sinkhorn), see the update below
         for ni in range(nI):
             eng.layer(st, 2 * ni)
             eng.layer(st, 2 * ni + 1)
@@ -71,11 +73,11 @@ class AdaGMN(GM):
                 y3h, y3l = ws.Y.hi.view(2 * B, Np, D), ws.Y.lo.view(2 * B, Np, D)
                 ops.gather_rows(y3h, st.key_ids, st.key_cnt, yc.hi, Np)
                 ops.gather_rows(y3l, st.key_ids, st.key_cnt, yc.lo, Np)
-                ldd = (N1 + 7) // 8 * 8
-                dist = self._dist_buffer(B, N0, ldd, dev)
-                eng.distance(st, Planes(yc.hi.view(-1, D), yc.lo.view(-1, D)), N0, N1, dist, ldd)
+                ldd = (S1 + 7) // 8 * 8
+                dist = self._dist_buffer(B, N0, (N1 + 7) // 8 * 8, dev).view(-1)[:B * S0 * ldd].view(B, S0, ldd)
+                eng.distance(st, Planes(yc.hi.view(-1, D), yc.lo.view(-1, D)), S0, S1, dist, ldd)
                 n0s, n1s = st.key_cnt[:B], st.key_cnt[B:]
-                _, i0c, _, m0c, _, sk = self._score_from_dist(dist, ldd, B, N0, N1, p, False, want_mass=update,
+                _, i0c, _, m0c, _, sk = self._score_from_dist(dist, ldd, B, S0, S1, p, False, want_mass=update,
                                                               n0s=n0s, n1s=n1s, write_scores=(ni == nI - 1))
                 i0 = torch.full((B, N0), -1, dtype=torch.int64, device=dev)
                 m0 = torch.zeros(B, N0, dtype=torch.float32, device=dev)
@@ -85,8 +87,8 @@ class AdaGMN(GM):
             if update:
                 a_self, a_cross = self._received(st)
                 mass = torch.zeros(2 * B, Np, dtype=torch.float32, device=dev)
-                mass[:B, :N0] = sk.row_mass
-                mass[B:, :N1] = sk.col_mass
+                mass[:B, :sk.row_mass.shape[1]] = sk.row_mass
+                mass[B:, :sk.col_mass.shape[1]] = sk.col_mass
                 if st.key_ids is None:
                     ids_in = torch.arange(Np, dtype=torch.int32, device=dev).repeat(2 * B, 1).contiguous()
                     cnt_in = st.n_tok
@@ -94,6 +96,13 @@ class AdaGMN(GM):
                     ids_in, cnt_in = st.key_ids, st.key_cnt
                 ids_out, cnt_out, _ = ops.pool_select(mass, a_self, a_cross, ids_in, cnt_in, thresh, self.n_min_tokens)
                 st.key_ids, st.key_cnt = ids_out, cnt_out
+                # ONE host read per pruning round (3 per forward).  Kept sets only shrink, so the largest kept set of this
+                # round bounds every later distance / Sinkhorn problem: sizing them by it (instead of N with per-sample
+                # counts) halves the score GEMM and lets the Sinkhorn ring buffers hold full-width rows again -- with
+                # N-wide slots and ~1100-wide rows only half the bytes were in flight (measured at batch 128: Sinkhorn
+                # 101 of 197 ms).  Rounded up to 64 so that consecutive batches reuse the cached workspaces.
+                kmax = cnt_out.view(2, B).max(dim=1).values.tolist()
+                S0, S1 = min(N0, (kmax[0] + 63) // 64 * 64), min(N1, (kmax[1] + 63) // 64 * 64)
         if last_sk is not None and st.key_ids is not None and nI > self.first_it_to_update and sk is last_sk and n0s is not None:
             c0, c1 = int(n0s[B - 1]), int(n1s[B - 1])
             scores = [last_sk.P[B - 1:B, :c0 + 1, :c1 + 1].clone()]      # the workspace is cached and reused: hand out a copy
