@@ -875,7 +875,11 @@ static int run_compact(const SinkhornArgs& a, cudaStream_t st) {
   // persistent grid: two CTAs per SM; rows per work item = the multiple of 8 whose item count fills whole rounds of the
   // grid best
   const int ctas = 2 * num_sms();
-  const int rows_per_cta = sk_rows_per_cta(R, a.batch, ctas, 8);
+  int rows_per_cta = sk_rows_per_cta(R, a.batch, ctas, 8);
+  if (const char* e = getenv("IMP_SK_ROWS")) {  // tuning override: rows per work item (multiple of 8, 8..128)
+    const int r = atoi(e);
+    if (r >= 8 && r <= 128 && r % 8 == 0) rows_per_cta = r;
+  }
   p.rows_per_cta = rows_per_cta;
   p.blocks_per_mat = (R + rows_per_cta - 1) / rows_per_cta;
   p.n_items = p.blocks_per_mat * a.batch;
