@@ -38,8 +38,9 @@ VLEN_STR = struct.pack('<BBBBI', 0x19, 0x01, 0, 0, 16) + struct.pack('<BBBBI', 0
 
 
 class H5Writer:
-    def __init__(self):
-        self.buf = bytearray(96)            # superblock goes here at the end
+    def __init__(self, rich: bool = False, superblock: int = 0):
+        self.rich, self.superblock = rich, superblock
+        self.buf = bytearray(96 if superblock == 0 else 100)            # superblock goes here at the end
         self.gheap = []                     # (index, bytes) of the single global heap collection
         self.gheap_addr = None
         self.gheap_fixups = []              # offsets of the 8-byte collection address inside vlen elements
@@ -51,6 +52,16 @@ class H5Writer:
         return off
 
     def _object_header(self, msgs) -> int:
+        if self.rich:
+            # what libhdf5 really writes around the three essential messages: a NIL message, a modification time, a fill value,
+            # and the LAST message moved into a continuation block elsewhere in the file
+            extra = [_msg(0x0000, b'\0' * 8), _msg(0x0012, struct.pack('<B3xI', 1, 1700000000)),
+                     _msg(0x0005, struct.pack('<BBBB', 2, 2, 2, 0))]
+            tail = msgs[-1]
+            cont_addr = self._alloc(tail)
+            msgs = extra[:1] + msgs[:-1] + extra[1:] + [_msg(0x0010, struct.pack('<QQ', cont_addr, len(tail)))]
+            body = b''.join(msgs)
+            return self._alloc(struct.pack('<BBHII4x', 1, 0, len(msgs) + 1, 1, len(body)) + body)
         body = b''.join(msgs)
         return self._alloc(struct.pack('<BBHII4x', 1, 0, len(msgs), 1, len(body)) + body)
 
@@ -62,6 +73,38 @@ class H5Writer:
         data_addr = self._alloc(arr.astype(dt).tobytes()) if arr.size else UNDEF
         space = struct.pack('<BBB5x', 1, arr.ndim, 0) + b''.join(struct.pack('<Q', s) for s in arr.shape)
         layout = struct.pack('<BBQQ', 3, 1, data_addr, arr.nbytes)
+        return self._object_header([_msg(0x0001, space), _msg(0x0003, _dtype_msg(dt)), _msg(0x0008, layout)])
+
+    def compact_dataset(self, arr) -> int:
+        """small array stored inside the object header (layout class 0)."""
+        arr = np.asarray(arr)
+        dt = arr.dtype.newbyteorder('<')
+        raw = arr.astype(dt).tobytes()
+        space = struct.pack('<BBB5x', 1, arr.ndim, 0) + b''.join(struct.pack('<Q', s) for s in arr.shape)
+        layout = struct.pack('<BBH', 3, 0, len(raw)) + raw
+        return self._object_header([_msg(0x0001, space), _msg(0x0003, _dtype_msg(dt)), _msg(0x0008, layout)])
+
+    def chunked_dataset(self, arr, chunk) -> int:
+        """unfiltered chunked layout: one level-0 v1 B-tree node (type 1) over all chunks, edge chunks stored at full size."""
+        arr = np.asarray(arr)
+        dt = arr.dtype.newbyteorder('<')
+        nd = arr.ndim
+        grid = [range(0, s, c) for s, c in zip(arr.shape, chunk)]
+        import itertools
+        entries = []
+        for offs in itertools.product(*grid):
+            blk = np.zeros(chunk, dt)
+            sl = tuple(slice(o, min(o + c, s)) for o, c, s in zip(offs, chunk, arr.shape))
+            blk[tuple(slice(0, x.stop - x.start) for x in sl)] = arr[sl]
+            entries.append((offs, self._alloc(blk.tobytes()), blk.nbytes))
+        assert len(entries) <= 64
+        body = b''
+        for offs, addr, nbytes in entries:
+            body += struct.pack('<II', nbytes, 0) + b''.join(struct.pack('<Q', o) for o in offs) + struct.pack('<Q', 0) + struct.pack('<Q', addr)
+        body += struct.pack('<II', 0, 0) + b''.join(struct.pack('<Q', s) for s in arr.shape) + struct.pack('<Q', 0)   # final key
+        btree = self._alloc(b'TREE' + struct.pack('<BBHQQ', 1, 0, len(entries), UNDEF, UNDEF) + body)
+        space = struct.pack('<BBB5x', 1, nd, 0) + b''.join(struct.pack('<Q', s) for s in arr.shape)
+        layout = struct.pack('<BBB', 3, 2, nd + 1) + struct.pack('<Q', btree) + b''.join(struct.pack('<I', c) for c in chunk) + struct.pack('<I', dt.itemsize)
         return self._object_header([_msg(0x0001, space), _msg(0x0003, _dtype_msg(dt)), _msg(0x0008, layout)])
 
     def string_dataset(self, strings) -> int:
@@ -137,11 +180,13 @@ class H5Writer:
             for off in self.gheap_fixups:
                 self.buf[off:off + 8] = struct.pack('<Q', self.gheap_addr)
         ohdr, btree, heap = self.group(root_entries)
-        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', 0, 0, 0, 0, 0, 8, 8, 0, LEAF_K, INTERNAL_K, 0)
+        sb = b'\x89HDF\r\n\x1a\n' + struct.pack('<BBBBBBBBHHI', self.superblock, 0, 0, 0, 0, 8, 8, 0, LEAF_K, INTERNAL_K, 0)
+        if self.superblock == 1:
+            sb += struct.pack('<HH', 32, 0)         # indexed-storage internal node K, reserved
         sb += struct.pack('<QQQQ', 0, UNDEF, len(self.buf), UNDEF)
         sb += struct.pack('<QQII', 0, ohdr, 1, 0) + struct.pack('<QQ', btree, heap)
-        assert len(sb) == 96
-        self.buf[0:96] = sb
+        assert len(sb) == (96 if self.superblock == 0 else 100)
+        self.buf[0:len(sb)] = sb
         return bytes(self.buf)
 
 

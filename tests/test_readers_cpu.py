@@ -100,3 +100,27 @@ def test_pair_batcher_layout(pair_file, monkeypatch):
         assert torch.equal(b['scores0'][r, :n0], torch.from_numpy(p['kpt1'][:n0, 2]))
         assert torch.equal(b['descriptors0'][r, :n0], torch.from_numpy(p['desc1'][:n0]))
         assert float(b['descriptors0'][r, n0:].abs().sum()) == 0.0 and float(b['keypoints1'][r, n1:].abs().sum()) == 0.0
+
+
+def test_object_header_variants_layouts_and_superblock_1(tmp_path):
+    """The structures a libhdf5-written file shows beyond the minimum: NIL / modification-time / fill-value messages around
+    the essential ones, the last message in a continuation block, superblock version 1, compact and unfiltered chunked
+    layouts (edge chunks), big-endian-free integer and float types."""
+    rng = np.random.default_rng(5)
+    w = h5_writer.H5Writer(rich=True, superblock=1)
+    a = rng.normal(size=(37, 10)).astype(np.float32)
+    b = rng.integers(-1000, 1000, size=(5, 7)).astype(np.int32)
+    c = rng.normal(size=(3, 3))
+    d = rng.normal(size=(19, 6, 4)).astype(np.float32)
+    sub = w.group({'chunked2d': w.chunked_dataset(a, (16, 4)), 'compact': w.compact_dataset(b)})[0]
+    root = {'sub': sub, 'contig': w.dataset(c), 'chunked3d': w.chunked_dataset(d, (8, 6, 3)),
+            'names': w.string_dataset([b'alpha.jpg', b'', b'a/much/longer/path/with/directories/image_000123.png'])}
+    path = str(tmp_path / 'rich.h5')
+    open(path, 'wb').write(w.finish(root))
+    f = readers.H5Lite(path)
+    assert np.array_equal(f['sub']['chunked2d'][()], a) and f['sub/chunked2d'].shape == (37, 10)
+    assert np.array_equal(f['sub']['compact'][()], b) and f['sub']['compact'][()].dtype == np.int32
+    assert np.array_equal(np.asarray(f['contig']), c)
+    assert np.array_equal(f['chunked3d'][()], d)
+    assert [x.decode() for x in f['names'][()]] == ['alpha.jpg', '', 'a/much/longer/path/with/directories/image_000123.png']
+    assert np.array_equal(f['sub']['chunked2d'][3:9], a[3:9])
