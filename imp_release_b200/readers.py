@@ -380,6 +380,22 @@ class standard_reader:
         return len(self.dataset['K1'])
 
 
+class reader_set(standard_reader):
+    """components/readers.py:41-75 -- the same records behind the ``torch.utils.data.Dataset`` protocol (``ds[index]``)."""
+
+    def __getitem__(self, index):
+        return self.run(index)
+
+
+try:        # make it a real Dataset subclass when torch is importable (it always is in this package; kept lazy for tools)
+    from torch.utils.data import Dataset as _Dataset_t
+
+    class reader_set(reader_set, _Dataset_t):  # noqa: F811
+        pass
+except ImportError:  # pragma: no cover
+    pass
+
+
 class PairBatcher:
     """Packs consecutive pairs of a ``standard_reader`` into fixed-capacity batch arrays in the matcher's input layout
     (what ``imp_release_b200.feeder.PairFeeder`` stages): keypoints [B, N, 2], scores [B, N], descriptors [B, N, 256] for both

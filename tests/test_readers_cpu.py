@@ -52,6 +52,9 @@ def test_standard_reader_matches_the_written_pairs(pair_file, monkeypatch):
     with pytest.raises(KeyError):
         rd.dataset['K1']['41']
     rd.close()
+    ds = readers.reader_set({'rawdata_dir': '', 'dataset_dir': path, 'num_kpt': 1000, 'read_images': False})
+    from torch.utils.data import Dataset
+    assert isinstance(ds, Dataset) and len(ds) == len(pairs) and np.array_equal(ds[3]['desc2'], pairs[3]['desc2'][:1000])
 
 
 def test_big_group_uses_a_multi_level_btree(tmp_path):
