@@ -248,17 +248,33 @@ int launch_sp_conv3x3(const imp_sp_conv_args& a, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------------------------
 // conv1a (nets/superpoint.py:125, 1 -> 64 channels): K = 9, far too thin for the tensor cores.  A thread owns one pixel and
 // 8 output channels; fp32 FMA in the reference's accumulation order does not matter at 9 terms.
+__device__ __forceinline__ uint64_t sp_pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void sp_unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t sp_fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
 __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                      __half* __restrict__ out_lo, int B, int H, int W) {
   const int g = threadIdx.x & 7;  // 8 output channels g*8 .. g*8+7, their 72 weights live in registers
-  float wr[8][9], br[8];
+  // ... as 36 packed fp32x2 pairs (channels 2u, 2u+1): one FFMA2 does the tap of two channels (same bits as two FFMAs)
+  uint64_t w2[4][9];
+  float br[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    br[e] = bias[g * 8 + e];
+  for (int e = 0; e < 8; ++e) br[e] = bias[g * 8 + e];
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) wr[e][tp] = w[(g * 8 + e) * 9 + tp];
-  }
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) w2[u][tp] = sp_pack2(w[(g * 8 + 2 * u) * 9 + tp], w[(g * 8 + 2 * u + 1) * 9 + tp]);
   const unsigned npix = (unsigned)B * H * W;  // < 2^31 (checked by the launcher): 32-bit index arithmetic
   for (unsigned pix = blockIdx.x * 32u + (threadIdx.x >> 3); pix < npix; pix += gridDim.x * 32u) {
     const unsigned rowi = pix / (unsigned)W;
@@ -275,17 +291,19 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ i
         v[tp] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(c + (tp / 3 - 1) * W + (tp % 3 - 1)) : 0.f;
       }
     }
+    uint64_t vv[9];
+#pragma unroll
+    for (int tp = 0; tp < 9; ++tp) vv[tp] = sp_pack2(v[tp], v[tp]);
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
+      uint64_t acc = sp_pack2(0.f, 0.f);
+#pragma unroll
+      for (int tp = 0; tp < 9; ++tp) acc = sp_fma2(vv[tp], w2[u][tp], acc);
       float o[2];
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        float acc = 0.f;
-#pragma unroll
-        for (int tp = 0; tp < 9; ++tp) acc = fmaf(v[tp], wr[2 * u + e][tp], acc);
-        o[e] = fmaxf(acc + br[2 * u + e], 0.f);
-      }
+      sp_unpack2(acc, o[0], o[1]);
+      o[0] = fmaxf(o[0] + br[2 * u], 0.f);
+      o[1] = fmaxf(o[1] + br[2 * u + 1], 0.f);
       __half h0, l0, h1, l1;
       split_f16x2(o[0], h0, l0);
       split_f16x2(o[1], h1, l1);
