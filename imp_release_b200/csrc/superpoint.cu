@@ -265,18 +265,21 @@ __device__ __forceinline__ uint64_t sp_fma2(uint64_t a, uint64_t b, uint64_t c) 
 __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ img, const float* __restrict__ w /*[64][9]*/,
                                                      const float* __restrict__ bias, __half* __restrict__ out_hi,
                                                      __half* __restrict__ out_lo, int B, int H, int W) {
-  const int g = threadIdx.x & 7;  // 8 output channels g*8 .. g*8+7, their 72 weights live in registers
-  // ... as 36 packed fp32x2 pairs (channels 2u, 2u+1): one FFMA2 does the tap of two channels (same bits as two FFMAs)
-  uint64_t w2[4][9];
-  float br[8];
+  // A thread owns 4 output channels (g*4 .. g*4+3) of one pixel at a time; 16 threads share a pixel.  Their 36 weights live
+  // in registers as 18 packed fp32x2 pairs (channels 2u, 2u+1): one FFMA2 does the tap of two channels (same bits as two
+  // FFMAs).  4 rather than 8 channels per thread keeps the kernel at ~64 registers: it is latency-bound (9 dependent-free
+  // loads, then compute, then two stores per pixel), so resident warps matter more than per-thread reuse.
+  const int g = threadIdx.x & 15;
+  uint64_t w2[2][9];
+  float br[4];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) br[e] = bias[g * 8 + e];
+  for (int e = 0; e < 4; ++e) br[e] = bias[g * 4 + e];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) w2[u][tp] = sp_pack2(w[(g * 8 + 2 * u) * 9 + tp], w[(g * 8 + 2 * u + 1) * 9 + tp]);
+    for (int tp = 0; tp < 9; ++tp) w2[u][tp] = sp_pack2(w[(g * 4 + 2 * u) * 9 + tp], w[(g * 4 + 2 * u + 1) * 9 + tp]);
   const unsigned npix = (unsigned)B * H * W;  // < 2^31 (checked by the launcher): 32-bit index arithmetic
-  for (unsigned pix = blockIdx.x * 32u + (threadIdx.x >> 3); pix < npix; pix += gridDim.x * 32u) {
+  for (unsigned pix = blockIdx.x * 16u + (threadIdx.x >> 4); pix < npix; pix += gridDim.x * 16u) {
     const unsigned rowi = pix / (unsigned)W;
     const int x = (int)(pix - rowi * (unsigned)W), y = (int)(rowi % (unsigned)H);
     const float* c = img + pix;
@@ -291,15 +294,12 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ i
         v[tp] = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? __ldg(c + (tp / 3 - 1) * W + (tp % 3 - 1)) : 0.f;
       }
     }
-    uint64_t vv[9];
+    uint32_t hi[2], lo[2];
 #pragma unroll
-    for (int tp = 0; tp < 9; ++tp) vv[tp] = sp_pack2(v[tp], v[tp]);
-    uint32_t hi[4], lo[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < 2; ++u) {
       uint64_t acc = sp_pack2(0.f, 0.f);
 #pragma unroll
-      for (int tp = 0; tp < 9; ++tp) acc = sp_fma2(vv[tp], w2[u][tp], acc);
+      for (int tp = 0; tp < 9; ++tp) acc = sp_fma2(sp_pack2(v[tp], v[tp]), w2[u][tp], acc);
       float o[2];
       sp_unpack2(acc, o[0], o[1]);
       o[0] = fmaxf(o[0] + br[2 * u], 0.f);
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(256) conv1a_kernel(const float* __restrict__ i
       hi[u] = *reinterpret_cast<uint32_t*>(&hh);
       lo[u] = *reinterpret_cast<uint32_t*>(&ll);
     }
-    *reinterpret_cast<uint4*>(out_hi + (size_t)pix * 64 + g * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<uint4*>(out_lo + (size_t)pix * 64 + g * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint2*>(out_hi + (size_t)pix * 64 + g * 4) = make_uint2(hi[0], hi[1]);
+    *reinterpret_cast<uint2*>(out_lo + (size_t)pix * 64 + g * 4) = make_uint2(lo[0], lo[1]);
   }
 }
 
@@ -320,7 +320,7 @@ int launch_sp_conv1a(const float* img, const float* w, const float* bias, void* 
                      cudaStream_t st) {
   const long long npix = (long long)B * H * W;
   IMP_REQUIRE(npix > 0 && npix < (1ll << 31) - (1ll << 26), "sp_conv1a: 0 < B * H * W < 2^31");
-  const long long want = (npix + 32 * 16 - 1) / (32 * 16);  // ~16 pixels per thread
+  const long long want = (npix + 16 * 16 - 1) / (16 * 16);  // ~16 pixels per thread
   const int grid = (int)(want < 1 ? 1 : (want > 65535 * 16 ? 65535 * 16 : want));
   conv1a_kernel<<<grid, 256, 0, st>>>(img, w, bias, reinterpret_cast<__half*>(out_hi), reinterpret_cast<__half*>(out_lo), B, H, W);
   IMP_CUDA_OK(cudaGetLastError());
