@@ -106,6 +106,7 @@ SIGNATURES = {
     'imp_pool_select': (C.c_int, [C.POINTER(PoolArgs), c_vp]),
     'imp_scatter_matches': (C.c_int, [c_vp, c_vp, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp, c_vp, c_i32, c_i32, c_vp]),
     'imp_gather_rows': (C.c_int, [c_vp, c_i64, c_i32, c_vp, c_i32, c_vp, c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_vp]),
+    'imp_sinkhorn_rows_per_item': (C.c_int, [c_i32, c_i32, c_i32]),
     'imp_sp_conv3x3': (C.c_int, [C.POINTER(SpConvArgs), c_vp]),
     'imp_sp_conv1a': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp]),
     'imp_sp_maxpool2': (C.c_int, [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_vp]),

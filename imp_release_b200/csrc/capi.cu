@@ -19,6 +19,7 @@ int launch_dual_softmax(const float* dist, long long d_bs, int ldd, const float*
                         int ldp, float* row_lse, float* col_lse, int N0, int N1, int batch, const int* n0s, const int* n1s,
                         cudaStream_t st);
 long long sinkhorn_q_store_bytes(int batch, int N0max, int N1max, int storage);
+int sinkhorn_rows_per_item(int batch, int N0max, int resident_ctas);
 void sinkhorn_set_profiling(int on);
 void sinkhorn_set_resident(int on);
 void attention_set_variant(int v);
@@ -86,6 +87,9 @@ IMP_API int imp_small_linear(const float* X, int32_t ldx, const float* W, const 
 IMP_API int imp_sinkhorn(const imp_sinkhorn_args* args, void* stream) { return imp::launch_sinkhorn(*args, ST(stream)); }
 IMP_API int64_t imp_sinkhorn_q_store_bytes(int32_t batch, int32_t N0max, int32_t N1max, int32_t storage) {
   return imp::sinkhorn_q_store_bytes(batch, N0max, N1max, storage);
+}
+IMP_API int imp_sinkhorn_rows_per_item(int32_t batch, int32_t N0max, int32_t resident_ctas) {
+  return imp::sinkhorn_rows_per_item(batch, N0max, resident_ctas);
 }
 IMP_API int imp_set_profiling(int32_t on) {
   imp::sinkhorn_set_profiling(on);

@@ -949,6 +949,10 @@ static int dispatch_nv(const SinkhornArgs& a, cudaStream_t st) {
   return 2;
 }
 
+// geometry query (no GPU needed): rows per work item the streaming kernels use for `batch` matrices of N0max + 1 rows on a
+// persistent grid of `resident_ctas` CTAs
+int sinkhorn_rows_per_item(int batch, int N0max, int resident_ctas) { return sk_rows_per_cta(N0max + 1, batch, resident_ctas, 8); }
+
 int run_sinkhorn_compact(const SinkhornArgs& a, cudaStream_t st) {
   const int storage = a.storage & ~IMP_SK_NO_RESIDENT;
   if (storage == IMP_SK_STORE_F32) return dispatch_nv<QF32>(a, st);

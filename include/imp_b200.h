@@ -192,6 +192,9 @@ IMP_API int64_t imp_sinkhorn_q_store_bytes(int32_t batch, int32_t N0max, int32_t
 /* Measurement aid for bench.py: with profiling on, imp_sinkhorn brackets its iteration launches with CUDA events on the
  * launching stream; imp_sinkhorn_iter_ms() waits for them and returns the mean duration of one iteration kernel of the
  * most recent call (< 0 if none was recorded). */
+/* geometry query, no GPU needed: rows per work item of the streaming Sinkhorn kernels for `batch` matrices of N0max + 1 rows on a
+ * persistent grid of `resident_ctas` CTAs (2 per SM).  Exposed for the regression test of the work-decomposition heuristic. */
+IMP_API int imp_sinkhorn_rows_per_item(int32_t batch, int32_t N0max, int32_t resident_ctas);
 IMP_API int imp_set_profiling(int32_t on);
 IMP_API float imp_sinkhorn_iter_ms(void);
 
